@@ -1,0 +1,406 @@
+// Finite-volume residual/Jacobian assembly for sm_100a.
+//
+// Reference path replaced (variant A, hard-coded TPFA,
+// src/conservation/conservation.jl): update_accumulation! (:558-568),
+// update_half_face_flux_tpfa! (:606-626, AD w.r.t. the self cell of each
+// half-face = "local perspective", src/ad/local_ad.jl:54-79), apply_forces!
+// (src/models.jl:889-901) and fill_conservation_eq! (:373-430). The reference
+// stores ne x nhf Duals (285 MB at 1M cells) between evaluate and fill; here the
+// three stages are fused so a flux never leaves registers:
+//
+//   twophase_state_kernel   — "secondary variables": one 32-byte record per cell
+//                             {p, Sw, rho_w, rho_o}; a neighbour gather is then a
+//                             single sector.
+//   twophase_assemble_kernel — row-owner form: LPC lanes per cell, one half-face
+//                             per lane. A lane evaluates the two-point flux from
+//                             the self perspective (-> r and the diagonal block,
+//                             combined over the lanes by shuffles) and from the
+//                             neighbour's perspective (-> J[self, other] =
+//                             -dF_{other->self}/dx_other, exactly the entry the
+//                             reference writes from the neighbour's loop), and
+//                             writes its 2x2 block into the row it owns. Every
+//                             Jacobian entry is written exactly once: no zeroing,
+//                             no atomics, deterministic.
+//   twophase_faces_kernel   — variant B of the reference (fvm_face_assembly!,
+//                             src/conservation/fvm_assembly.jl:253-283): one lane
+//                             per face, off-diagonal blocks written directly,
+//                             r and diagonal blocks scattered with FP64 atomics
+//                             (kept for comparison; order-dependent rounding).
+//
+// Physics: builder-defined two-phase immiscible plug-in for the face_flux! slot
+// (src/conservation/conservation.jl:642-649), see SURVEY.md §8(d) / DESIGN.md.
+#include "jb_internal.cuh"
+#include "jb_reduce.cuh"
+
+struct TPParams { double rho0[2], c[2], mu[2], p0; };
+
+__global__ void __launch_bounds__(256) twophase_state_kernel(i64 nc, TPParams P, const double* __restrict__ p, const double* __restrict__ s,
+                                                             double4* __restrict__ rec) {
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (i64)gridDim.x * blockDim.x) {
+        const double pc = __ldg(p + c);
+        const double sw = __ldg(s + 2 * c);
+        double4 o;
+        o.x = pc; o.y = sw;
+        o.z = P.rho0[0] * exp(P.c[0] * (pc - P.p0));
+        o.w = P.rho0[1] * exp(P.c[1] * (pc - P.p0));
+        rec[c] = o;
+    }
+}
+
+__device__ __forceinline__ double4 ld_rec(const double4* __restrict__ p) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+struct CellP {            // properties of a cell needed by the flux, with d/dp and d/dSw of the mobility
+    double p, rho[2], mob[2], dmob_dp[2], dmob_ds[2];
+};
+__device__ __forceinline__ CellP cell_props(const TPParams& P, const double4 r) {
+    CellP o;
+    o.p = r.x;
+    const double S[2] = {r.y, 1.0 - r.y};
+    const double dS[2] = {1.0, -1.0};
+    o.rho[0] = r.z; o.rho[1] = r.w;
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+        const double kr = S[a] * S[a];
+        o.mob[a] = (o.rho[a] * kr) / P.mu[a];
+        o.dmob_dp[a] = (P.c[a] * o.rho[a] * kr) / P.mu[a];
+        o.dmob_ds[a] = (o.rho[a] * (2.0 * S[a] * dS[a])) / P.mu[a];
+    }
+    return o;
+}
+// Flux of phase a out of `self` towards `other`, value and d/d(p_self), d/d(Sw_self).
+__device__ __forceinline__ void flux_phase(const TPParams& P, const CellP& self, const CellP& other, int a, double T, double sgdz,
+                                           double& F, double& dFdp, double& dFds) {
+    const double rho_avg = 0.5 * (self.rho[a] + other.rho[a]);
+    const double theta = self.p - other.p + sgdz * rho_avg;
+    const double dtheta = 1.0 + sgdz * (0.5 * (P.c[a] * self.rho[a]));
+    const double q = T * theta;
+    const double dq = T * dtheta;
+    if (q > 0) {  // upstream = self
+        F = self.mob[a] * q;
+        dFdp = self.mob[a] * dq + q * self.dmob_dp[a];
+        dFds = q * self.dmob_ds[a];
+    } else {      // upstream = other: constant w.r.t. self
+        F = other.mob[a] * q;
+        dFdp = other.mob[a] * dq;
+        dFds = 0.0;
+    }
+}
+
+template <int LPC, bool JAC>
+__global__ void __launch_bounds__(256) twophase_assemble_kernel(i64 nc, TPParams P, const int32_t* __restrict__ hf_pos,
+                                                                const int32_t* __restrict__ hf_other, const int32_t* __restrict__ hf_rowpos,
+                                                                const double* __restrict__ hf_T, const double* __restrict__ hf_sgdz,
+                                                                const int32_t* __restrict__ diag_pos, const double4* __restrict__ rec,
+                                                                const double* __restrict__ pv, const double* __restrict__ M0,
+                                                                const double* __restrict__ src, double inv_dt_unused, double dt,
+                                                                double* __restrict__ nz, double* __restrict__ r) {
+    constexpr int CELLS_PER_WARP = 32 / LPC;
+    const int lane = threadIdx.x % LPC;
+    const i64 warps_per_cta = blockDim.x >> 5;
+    const i64 stride = (i64)gridDim.x * warps_per_cta * CELLS_PER_WARP;
+    for (i64 base = ((i64)blockIdx.x * warps_per_cta + (threadIdx.x >> 5)) * CELLS_PER_WARP; base < nc; base += stride) {
+        const i64 c = base + (threadIdx.x & 31) / LPC;
+        const bool live = c < nc;
+        // accumulators: residual (2) and diagonal block (column-major: [e + 2*d])
+        double racc[2] = {0.0, 0.0};
+        double dacc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (live) {
+            const double4 rs = ld_rec(rec + c);
+            const CellP self = cell_props(P, rs);
+            const int32_t h0 = __ldg(hf_pos + c), h1 = __ldg(hf_pos + c + 1);
+            for (int32_t i = h0 + lane; i < h1; i += LPC) {
+                const int32_t o = __ldg(hf_other + i);
+                const double T = __ldg(hf_T + i);
+                const double sg = __ldg(hf_sgdz + i);
+                const CellP other = cell_props(P, ld_rec(rec + o));
+                double blk[4];
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    double F, dFdp, dFds;
+                    flux_phase(P, self, other, a, T, sg, F, dFdp, dFds);
+                    racc[a] += F;
+                    dacc[a] += dFdp;
+                    dacc[2 + a] += dFds;
+                    if (JAC) {
+                        // the neighbour's half-face towards us: J[self, other] = -dF_{o->c}/dx_o
+                        double Fo, dFo_dp, dFo_ds;
+                        flux_phase(P, other, self, a, T, -sg, Fo, dFo_dp, dFo_ds);
+                        blk[a] = -dFo_dp;
+                        blk[2 + a] = -dFo_ds;
+                    }
+                }
+                if (JAC) {
+                    double2* dst = reinterpret_cast<double2*>(nz + (size_t)__ldg(hf_rowpos + i) * 4);
+                    dst[0] = make_double2(blk[0], blk[1]);
+                    dst[1] = make_double2(blk[2], blk[3]);
+                }
+            }
+            if (lane == 0) {
+                // accumulation term (M - M0)/dt with its partials, plus sources on the diagonal entries
+                const double S[2] = {rs.y, 1.0 - rs.y};
+                const double dS[2] = {1.0, -1.0};
+                const double pvc = __ldg(pv + c);
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    const double mass = pvc * (self.rho[a] * S[a]);
+                    double acc = (mass - __ldg(M0 + 2 * c + a)) / dt;
+                    if (src) acc += __ldg(src + 2 * c + a);
+                    racc[a] += acc;
+                    dacc[a] += (pvc * (P.c[a] * self.rho[a] * S[a])) / dt;
+                    dacc[2 + a] += (pvc * (self.rho[a] * dS[a])) / dt;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = LPC / 2; o > 0; o >>= 1) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) racc[e] += __shfl_xor_sync(0xffffffffu, racc[e], o);
+            if (JAC) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) dacc[q] += __shfl_xor_sync(0xffffffffu, dacc[q], o);
+            }
+        }
+        if (live && lane == 0) {
+            reinterpret_cast<double2*>(r)[c] = make_double2(racc[0], racc[1]);
+            if (JAC) {
+                double2* dst = reinterpret_cast<double2*>(nz + (size_t)__ldg(diag_pos + c) * 4);
+                dst[0] = make_double2(dacc[0], dacc[1]);
+                dst[1] = make_double2(dacc[2], dacc[3]);
+            }
+        }
+    }
+}
+
+// ---- variant B: face-parallel with atomics -----------------------------------------------
+__global__ void __launch_bounds__(256) twophase_acc_kernel(i64 nc, TPParams P, const double4* __restrict__ rec, const double* __restrict__ pv,
+                                                           const double* __restrict__ M0, const double* __restrict__ src, double dt,
+                                                           const int32_t* __restrict__ diag_pos, double* __restrict__ nz,
+                                                           double* __restrict__ r) {
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (i64)gridDim.x * blockDim.x) {
+        const double4 rs = ld_rec(rec + c);
+        const double S[2] = {rs.y, 1.0 - rs.y};
+        const double dS[2] = {1.0, -1.0};
+        const double rho[2] = {rs.z, rs.w};
+        const double pvc = __ldg(pv + c);
+        double ra[2], da[4];
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            const double mass = pvc * (rho[a] * S[a]);
+            ra[a] = (mass - __ldg(M0 + 2 * c + a)) / dt;
+            if (src) ra[a] += __ldg(src + 2 * c + a);
+            da[a] = (pvc * (P.c[a] * rho[a] * S[a])) / dt;
+            da[2 + a] = (pvc * (rho[a] * dS[a])) / dt;
+        }
+        reinterpret_cast<double2*>(r)[c] = make_double2(ra[0], ra[1]);
+        double2* dst = reinterpret_cast<double2*>(nz + (size_t)__ldg(diag_pos + c) * 4);
+        dst[0] = make_double2(da[0], da[1]);
+        dst[1] = make_double2(da[2], da[3]);
+    }
+}
+__global__ void __launch_bounds__(256) twophase_faces_kernel(i64 nf, TPParams P, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                                             const double* __restrict__ fT, const double* __restrict__ fgdz,
+                                                             const int32_t* __restrict__ pos_lr, const int32_t* __restrict__ pos_rl,
+                                                             const int32_t* __restrict__ diag_pos, const double4* __restrict__ rec,
+                                                             double* __restrict__ nz, double* __restrict__ r) {
+    for (i64 f = (i64)blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += (i64)gridDim.x * blockDim.x) {
+        const int32_t l = __ldg(left + f), rr = __ldg(right + f);
+        const double T = __ldg(fT + f), g = __ldg(fgdz + f);
+        const CellP L = cell_props(P, ld_rec(rec + l)), R = cell_props(P, ld_rec(rec + rr));
+        double bl[4], br[4];
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            double Fl, dl_dp, dl_ds, Fr, dr_dp, dr_ds;
+            flux_phase(P, L, R, a, T, g, Fl, dl_dp, dl_ds);     // out of left  (sign +1)
+            flux_phase(P, R, L, a, T, -g, Fr, dr_dp, dr_ds);    // out of right (sign -1)
+            atomicAdd(r + 2 * (size_t)l + a, Fl);
+            atomicAdd(r + 2 * (size_t)rr + a, Fr);
+            const size_t dl = (size_t)__ldg(diag_pos + l) * 4, dr = (size_t)__ldg(diag_pos + rr) * 4;
+            atomicAdd(nz + dl + a, dl_dp); atomicAdd(nz + dl + 2 + a, dl_ds);
+            atomicAdd(nz + dr + a, dr_dp); atomicAdd(nz + dr + 2 + a, dr_ds);
+            bl[a] = -dr_dp; bl[2 + a] = -dr_ds;   // J[l, r] = -dF_{r->l}/dx_r
+            br[a] = -dl_dp; br[2 + a] = -dl_ds;   // J[r, l] = -dF_{l->r}/dx_l
+        }
+        double2* d1 = reinterpret_cast<double2*>(nz + (size_t)__ldg(pos_lr + f) * 4);
+        d1[0] = make_double2(bl[0], bl[1]); d1[1] = make_double2(bl[2], bl[3]);
+        double2* d2 = reinterpret_cast<double2*>(nz + (size_t)__ldg(pos_rl + f) * 4);
+        d2[0] = make_double2(br[0], br[1]); d2[1] = make_double2(br[2], br[3]);
+    }
+}
+
+__global__ void __launch_bounds__(256) twophase_mass_kernel(i64 nc, TPParams P, const double* __restrict__ p, const double* __restrict__ s,
+                                                            const double* __restrict__ pv, double* __restrict__ M) {
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (i64)gridDim.x * blockDim.x) {
+        const double pc = __ldg(p + c), sw = __ldg(s + 2 * c), pvc = __ldg(pv + c);
+        const double rw = P.rho0[0] * exp(P.c[0] * (pc - P.p0));
+        const double ro = P.rho0[1] * exp(P.c[1] * (pc - P.p0));
+        reinterpret_cast<double2*>(M)[c] = make_double2(pvc * (rw * sw), pvc * (ro * (1.0 - sw)));
+    }
+}
+
+__global__ void scatter_sources_kernel(i64 nsrc, const int32_t* __restrict__ cells, const double* __restrict__ vals, double* __restrict__ src) {
+    // few entries; duplicates accumulate (serial per thread 0 keeps the order deterministic)
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (i64 k = 0; k < nsrc; k++) { src[2 * (size_t)cells[k]] += vals[2 * k]; src[2 * (size_t)cells[k] + 1] += vals[2 * k + 1]; }
+}
+
+static TPParams make_params(const jb_twophase* m) {
+    TPParams P;
+    P.rho0[0] = m->params[0]; P.rho0[1] = m->params[1]; P.c[0] = m->params[2]; P.c[1] = m->params[3];
+    P.mu[0] = m->params[4]; P.mu[1] = m->params[5]; P.p0 = m->params[6];
+    return P;
+}
+static int grid_for(jb_ctx* ctx, i64 n, int threads, int per_sm) {
+    i64 want = (n + threads - 1) / threads;
+    return (int)std::max<i64>(1, std::min<i64>(want, (i64)ctx->sm_count * per_sm));
+}
+
+int jb_launch_twophase_state(jb_twophase* m, const double* d_p, const double* d_s) {
+    jb_ctx* ctx = m->t->mesh->ctx;
+    const i64 nc = m->t->mesh->nc;
+    twophase_state_kernel<<<grid_for(ctx, nc, 256, 16), 256, 0, ctx->stream>>>(nc, make_params(m), d_p, d_s, reinterpret_cast<double4*>(m->d_rec.p));
+    JB_CHECK_LAUNCH(ctx);
+    return JB_OK;
+}
+
+int jb_launch_twophase_assemble(jb_twophase* m, const double* d_M0, double dt, double* d_r, bool jac) {
+    jb_tpfa* t = m->t;
+    jb_ctx* ctx = t->mesh->ctx;
+    const i64 nc = t->mesh->nc;
+    constexpr int LPC = 8;
+    const i64 cells_per_cta = 256 / LPC;
+    const int grid = (int)std::max<i64>(1, (nc + cells_per_cta - 1) / cells_per_cta);
+    const double* src = m->nsrc > 0 ? m->d_src.p : nullptr;
+    if (jac)
+        twophase_assemble_kernel<LPC, true><<<grid, 256, 0, ctx->stream>>>(nc, make_params(m), t->mesh->d_hf_pos.p, t->mesh->d_hf_other.p,
+                                                                           t->d_hf_rowpos.p, m->d_hf_T.p, m->d_hf_sgdz.p, t->csr->d_diag.p,
+                                                                           reinterpret_cast<const double4*>(m->d_rec.p), m->d_pv.p, d_M0, src,
+                                                                           0.0, dt, t->csr->d_val.p, d_r);
+    else
+        twophase_assemble_kernel<LPC, false><<<grid, 256, 0, ctx->stream>>>(nc, make_params(m), t->mesh->d_hf_pos.p, t->mesh->d_hf_other.p,
+                                                                            t->d_hf_rowpos.p, m->d_hf_T.p, m->d_hf_sgdz.p, t->csr->d_diag.p,
+                                                                            reinterpret_cast<const double4*>(m->d_rec.p), m->d_pv.p, d_M0, src,
+                                                                            0.0, dt, t->csr->d_val.p, d_r);
+    JB_CHECK_LAUNCH(ctx);
+    return JB_OK;
+}
+
+int jb_launch_twophase_assemble_faces(jb_twophase* m, const double* d_M0, double dt, double* d_r) {
+    jb_tpfa* t = m->t;
+    jb_ctx* ctx = t->mesh->ctx;
+    const i64 nc = t->mesh->nc, nf = t->mesh->nf;
+    const double* src = m->nsrc > 0 ? m->d_src.p : nullptr;
+    twophase_acc_kernel<<<grid_for(ctx, nc, 256, 16), 256, 0, ctx->stream>>>(nc, make_params(m), reinterpret_cast<const double4*>(m->d_rec.p),
+                                                                             m->d_pv.p, d_M0, src, dt, t->csr->d_diag.p, t->csr->d_val.p, d_r);
+    JB_CHECK_LAUNCH(ctx);
+    twophase_faces_kernel<<<grid_for(ctx, nf, 256, 16), 256, 0, ctx->stream>>>(nf, make_params(m), t->mesh->d_left.p, t->mesh->d_right.p,
+                                                                               m->d_face_T.p, m->d_face_gdz.p, m->d_pos_lr.p, m->d_pos_rl.p,
+                                                                               t->csr->d_diag.p, reinterpret_cast<const double4*>(m->d_rec.p),
+                                                                               t->csr->d_val.p, d_r);
+    JB_CHECK_LAUNCH(ctx);
+    return JB_OK;
+}
+
+int jb_launch_twophase_mass(jb_twophase* m, const double* d_p, const double* d_s, double* d_M) {
+    jb_ctx* ctx = m->t->mesh->ctx;
+    const i64 nc = m->t->mesh->nc;
+    twophase_mass_kernel<<<grid_for(ctx, nc, 256, 16), 256, 0, ctx->stream>>>(nc, make_params(m), d_p, d_s, m->d_pv.p, d_M);
+    JB_CHECK_LAUNCH(ctx);
+    return JB_OK;
+}
+
+extern "C" {
+
+int32_t jb_twophase_create(jb_tpfa* t, const double* Tf, const double* gdz, const double* pv, const double* params, jb_twophase** out) {
+    if (!t || !Tf || !gdz || !pv || !params || !out) return JB_ERR_ARG;
+    jb_mesh* mesh = t->mesh;
+    jb_ctx* ctx = mesh->ctx;
+    if (t->csr->bs != 2) JB_FAIL(ctx, JB_ERR_ARG, "jb_twophase_create: the two-phase law needs a Jacobian with 2x2 blocks");
+    jb_twophase* m = new jb_twophase();
+    m->t = t;
+    for (int i = 0; i < 7; i++) m->params[i] = params[i];
+    std::vector<double> hT(mesh->nhf), hG(mesh->nhf), fT(Tf, Tf + mesh->nf), fG(gdz, gdz + mesh->nf), hpv(pv, pv + mesh->nc);
+    for (i64 i = 0; i < mesh->nhf; i++) {
+        const int32_t f = mesh->h_hf_face[i];
+        hT[i] = Tf[f];
+        hG[i] = (double)mesh->h_hf_sign[i] * gdz[f];
+    }
+    // per-face Jacobian positions for the face-parallel variant
+    std::vector<int32_t> plr(mesh->nf), prl(mesh->nf);
+    for (i64 c = 0; c < mesh->nc; c++)
+        for (int32_t i = mesh->h_hf_pos[c]; i < mesh->h_hf_pos[c + 1]; i++) {
+            const int32_t f = mesh->h_hf_face[i];
+            if (mesh->h_hf_sign[i] > 0) plr[f] = t->h_hf_rowpos[i]; else prl[f] = t->h_hf_rowpos[i];
+        }
+    cudaStream_t s = ctx->stream;
+    bool ok = m->d_hf_T.upload(hT, s) == cudaSuccess && m->d_hf_sgdz.upload(hG, s) == cudaSuccess && m->d_face_T.upload(fT, s) == cudaSuccess &&
+              m->d_face_gdz.upload(fG, s) == cudaSuccess && m->d_pv.upload(hpv, s) == cudaSuccess && m->d_pos_lr.upload(plr, s) == cudaSuccess &&
+              m->d_pos_rl.upload(prl, s) == cudaSuccess && m->d_rec.alloc((size_t)mesh->nc * 4) == cudaSuccess;
+    if (!ok) { delete m; JB_FAIL(ctx, JB_ERR_ALLOC, "jb_twophase_create: device allocation failed"); }
+    *out = m;
+    return JB_OK;
+}
+int32_t jb_twophase_destroy(jb_twophase* m) { delete m; return JB_OK; }
+
+int32_t jb_twophase_set_sources(jb_twophase* m, int64_t nsrc, const int64_t* cells, const double* vals) {
+    if (!m || nsrc < 0 || (nsrc > 0 && (!cells || !vals))) return JB_ERR_ARG;
+    jb_ctx* ctx = m->t->mesh->ctx;
+    const i64 nc = m->t->mesh->nc;
+    m->nsrc = nsrc;
+    if (nsrc == 0) return JB_OK;
+    std::vector<int32_t> hc(nsrc);
+    for (i64 k = 0; k < nsrc; k++) {
+        if (cells[k] < 1 || cells[k] > nc) JB_FAIL(ctx, JB_ERR_ARG, "jb_twophase_set_sources: cell out of range");
+        hc[k] = (int32_t)(cells[k] - 1);
+    }
+    std::vector<double> hv(vals, vals + 2 * nsrc);
+    if (m->d_src_cells.upload(hc, ctx->stream) != cudaSuccess || m->d_src_vals.upload(hv, ctx->stream) != cudaSuccess ||
+        (m->d_src.n != (size_t)2 * nc && m->d_src.alloc((size_t)2 * nc) != cudaSuccess))
+        JB_FAIL(ctx, JB_ERR_ALLOC, "jb_twophase_set_sources: device allocation failed");
+    JB_CUDA(ctx, cudaMemsetAsync(m->d_src.p, 0, (size_t)2 * nc * sizeof(double), ctx->stream));
+    scatter_sources_kernel<<<1, 32, 0, ctx->stream>>>(nsrc, m->d_src_cells.p, m->d_src_vals.p, m->d_src.p);
+    JB_CHECK_LAUNCH(ctx);
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+
+int32_t jb_twophase_update_state(jb_twophase* m, const double* d_p, const double* d_s) {
+    if (!m || !d_p || !d_s) return JB_ERR_ARG;
+    int rc = jb_launch_twophase_state(m, d_p, d_s);
+    if (rc != JB_OK) return rc;
+    JB_CUDA(m->t->mesh->ctx, cudaStreamSynchronize(m->t->mesh->ctx->stream));
+    return JB_OK;
+}
+int32_t jb_twophase_mass(jb_twophase* m, const double* d_p, const double* d_s, double* d_M) {
+    if (!m || !d_p || !d_s || !d_M) return JB_ERR_ARG;
+    int rc = jb_launch_twophase_mass(m, d_p, d_s, d_M);
+    if (rc != JB_OK) return rc;
+    JB_CUDA(m->t->mesh->ctx, cudaStreamSynchronize(m->t->mesh->ctx->stream));
+    return JB_OK;
+}
+static int32_t assemble_common(jb_twophase* m, const double* d_p, const double* d_s, const double* d_M0, double dt, double* d_r, int variant) {
+    if (!m || !d_p || !d_s || !d_M0 || !d_r || !(dt > 0)) return JB_ERR_ARG;
+    jb_ctx* ctx = m->t->mesh->ctx;
+    int rc = jb_launch_twophase_state(m, d_p, d_s);
+    if (rc != JB_OK) return rc;
+    if (variant == 0) rc = jb_launch_twophase_assemble(m, d_M0, dt, d_r, true);
+    else if (variant == 1) rc = jb_launch_twophase_assemble_faces(m, d_M0, dt, d_r);
+    else rc = jb_launch_twophase_assemble(m, d_M0, dt, d_r, false);
+    if (rc != JB_OK) return rc;
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+int32_t jb_twophase_assemble(jb_twophase* m, const double* d_p, const double* d_s, const double* d_M0, double dt, double* d_r) {
+    return assemble_common(m, d_p, d_s, d_M0, dt, d_r, 0);
+}
+int32_t jb_twophase_assemble_faces(jb_twophase* m, const double* d_p, const double* d_s, const double* d_M0, double dt, double* d_r) {
+    return assemble_common(m, d_p, d_s, d_M0, dt, d_r, 1);
+}
+int32_t jb_twophase_residual(jb_twophase* m, const double* d_p, const double* d_s, const double* d_M0, double dt, double* d_r) {
+    return assemble_common(m, d_p, d_s, d_M0, dt, d_r, 2);
+}
+
+}  // extern "C"

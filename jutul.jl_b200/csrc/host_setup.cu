@@ -1,0 +1,325 @@
+// Setup-time host logic of libjutul_b200.so: topology (half-face CSR), Jacobian
+// sparsity, cache->Jacobian alignment and the symbolic phase of ILU(0).
+// Integer work done once per model; results are uploaded and stay resident in HBM.
+// (The per-Newton-iteration hot path is entirely in the kernel translation units.)
+#include <algorithm>
+#include <numeric>
+
+#include "jb_internal.cuh"
+
+static std::string g_err;
+void jb_set_global_error(const std::string& s) { g_err = s; }
+const std::string& jb_global_error() { return g_err; }
+
+static bool fits_i32(i64 v) { return v >= 0 && v < (i64)2147483647; }
+
+extern "C" {
+
+// ---------------------------------------------------------------- mesh
+// Half-face CSR by counting sort: stable placement in ascending face order per
+// cell reproduces "push faces in N order, then sort!" of get_cell_faces
+// (src/utils.jl:813-841) without per-cell vectors.
+int32_t jb_mesh_create(jb_ctx* ctx, int64_t nc, int64_t nf, const int64_t* N, jb_mesh** out) {
+    if (!ctx || !out || nc <= 0 || nf < 0 || (nf > 0 && !N)) JB_FAIL(ctx, JB_ERR_ARG, "jb_mesh_create: bad argument");
+    if (!fits_i32(nc) || !fits_i32(2 * nf + 1)) JB_FAIL(ctx, JB_ERR_UNSUPPORTED, "jb_mesh_create: index overflow (int32)");
+    jb_mesh* m = new jb_mesh();
+    m->ctx = ctx; m->nc = nc; m->nf = nf; m->nhf = 2 * nf;
+    m->h_left.resize(nf); m->h_right.resize(nf);
+    std::vector<int32_t> cnt(nc + 1, 0);
+    for (i64 f = 0; f < nf; f++) {
+        i64 l = N[2 * f], r = N[2 * f + 1];
+        if (l < 1 || l > nc || r < 1 || r > nc || l == r) {
+            delete m;
+            JB_FAIL(ctx, JB_ERR_ARG, "jb_mesh_create: neighbourship entry out of range or self-loop at face " + std::to_string(f + 1));
+        }
+        m->h_left[f] = (int32_t)(l - 1); m->h_right[f] = (int32_t)(r - 1);
+        cnt[l]++; cnt[r]++;
+    }
+    m->h_hf_pos.assign(nc + 1, 0);
+    for (i64 c = 0; c < nc; c++) m->h_hf_pos[c + 1] = m->h_hf_pos[c] + cnt[c + 1];
+    m->h_hf_face.resize(m->nhf); m->h_hf_other.resize(m->nhf); m->h_hf_sign.resize(m->nhf);
+    std::vector<int32_t> cur(m->h_hf_pos.begin(), m->h_hf_pos.end() - 1);
+    for (i64 f = 0; f < nf; f++) {  // ascending face order => per-cell lists come out sorted
+        int32_t l = m->h_left[f], r = m->h_right[f];
+        int32_t a = cur[l]++; m->h_hf_face[a] = (int32_t)f; m->h_hf_other[a] = r; m->h_hf_sign[a] = 1;
+        int32_t b = cur[r]++; m->h_hf_face[b] = (int32_t)f; m->h_hf_other[b] = l; m->h_hf_sign[b] = -1;
+    }
+    cudaStream_t s = ctx->stream;
+    if (m->d_left.upload(m->h_left, s) != cudaSuccess || m->d_right.upload(m->h_right, s) != cudaSuccess ||
+        m->d_hf_pos.upload(m->h_hf_pos, s) != cudaSuccess || m->d_hf_face.upload(m->h_hf_face, s) != cudaSuccess ||
+        m->d_hf_other.upload(m->h_hf_other, s) != cudaSuccess || m->d_hf_sign.upload(m->h_hf_sign, s) != cudaSuccess) {
+        delete m;
+        JB_FAIL(ctx, JB_ERR_ALLOC, "jb_mesh_create: device upload failed");
+    }
+    *out = m;
+    return JB_OK;
+}
+int32_t jb_mesh_destroy(jb_mesh* m) { delete m; return JB_OK; }
+
+int32_t jb_mesh_halfface(jb_mesh* m, int64_t* faces, int64_t* face_pos, int64_t* cells, int64_t* signs) {
+    if (!m) return JB_ERR_ARG;
+    for (i64 i = 0; i < m->nhf; i++) {
+        if (faces) faces[i] = m->h_hf_face[i] + 1;
+        if (cells) cells[i] = m->h_hf_other[i] + 1;
+        if (signs) signs[i] = m->h_hf_sign[i];
+    }
+    if (face_pos) for (i64 c = 0; c <= m->nc; c++) face_pos[c] = m->h_hf_pos[c] + 1;
+    return JB_OK;
+}
+
+// ---------------------------------------------------------------- csr
+static int csr_finish(jb_ctx* ctx, jb_csr* A) {
+    A->h_diag.assign(A->n, -1);
+    for (i64 r = 0; r < A->n; r++)
+        for (int32_t k = A->h_rowptr[r]; k < A->h_rowptr[r + 1]; k++)
+            if (A->h_colidx[k] == r) { A->h_diag[r] = k; break; }
+    cudaStream_t s = ctx->stream;
+    if (A->d_rowptr.upload(A->h_rowptr, s) != cudaSuccess || A->d_colidx.upload(A->h_colidx, s) != cudaSuccess ||
+        A->d_diag.upload(A->h_diag, s) != cudaSuccess || A->d_val.alloc((size_t)A->nnzb * A->bs * A->bs) != cudaSuccess)
+        return JB_ERR_ALLOC;
+    if (cudaMemsetAsync(A->d_val.p, 0, (size_t)A->nnzb * A->bs * A->bs * sizeof(double), s) != cudaSuccess) return JB_ERR_CUDA;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return JB_ERR_CUDA;
+    return JB_OK;
+}
+
+// Canonical CSR from COO triplets = sparse(J, I, V, n, m) transposed storage
+// (src/StaticCSR/mat.jl:73-76): per-row column lists sorted ascending, duplicates
+// merged. Two-pass counting sort on rows, then sort+unique inside each row.
+int32_t jb_csr_create_from_coo(jb_ctx* ctx, const int64_t* I, const int64_t* J, int64_t nnz_in, int64_t n, int32_t bs,
+                               jb_csr** out) {
+    if (!ctx || !out || n <= 0 || nnz_in < 0 || bs < 1 || bs > 4) JB_FAIL(ctx, JB_ERR_ARG, "jb_csr_create_from_coo: bad argument");
+    if (!fits_i32(n) || !fits_i32(nnz_in)) JB_FAIL(ctx, JB_ERR_UNSUPPORTED, "jb_csr_create_from_coo: index overflow (int32)");
+    std::vector<int32_t> ptr(n + 1, 0);
+    for (i64 k = 0; k < nnz_in; k++) {
+        if (I[k] < 1 || I[k] > n || J[k] < 1 || J[k] > n) JB_FAIL(ctx, JB_ERR_ARG, "jb_csr_create_from_coo: index out of range");
+        ptr[I[k]]++;
+    }
+    for (i64 r = 0; r < n; r++) ptr[r + 1] += ptr[r];
+    std::vector<int32_t> cols(nnz_in), cur(ptr.begin(), ptr.end() - 1);
+    for (i64 k = 0; k < nnz_in; k++) cols[cur[I[k] - 1]++] = (int32_t)(J[k] - 1);
+    jb_csr* A = new jb_csr();
+    A->ctx = ctx; A->n = n; A->bs = bs;
+    A->h_rowptr.assign(n + 1, 0);
+    A->h_colidx.reserve(nnz_in);
+    for (i64 r = 0; r < n; r++) {
+        auto b = cols.begin() + ptr[r], e = cols.begin() + ptr[r + 1];
+        std::sort(b, e);
+        e = std::unique(b, e);
+        A->h_colidx.insert(A->h_colidx.end(), b, e);
+        A->h_rowptr[r + 1] = (int32_t)A->h_colidx.size();
+    }
+    A->nnzb = (i64)A->h_colidx.size();
+    int rc = csr_finish(ctx, A);
+    if (rc != JB_OK) { delete A; JB_FAIL(ctx, rc, "jb_csr_create_from_coo: device allocation failed"); }
+    *out = A;
+    return JB_OK;
+}
+
+// TPFA pattern {(self, other) for all half-faces} U diagonal
+// (src/conservation/conservation.jl:486-505), built directly row by row.
+int32_t jb_csr_create_tpfa(jb_mesh* m, int32_t bs, jb_csr** out) {
+    if (!m || !out || bs < 1 || bs > 4) return JB_ERR_ARG;
+    jb_ctx* ctx = m->ctx;
+    if (!fits_i32(m->nhf + m->nc)) JB_FAIL(ctx, JB_ERR_UNSUPPORTED, "jb_csr_create_tpfa: index overflow (int32)");
+    jb_csr* A = new jb_csr();
+    A->ctx = ctx; A->n = m->nc; A->bs = bs;
+    A->h_rowptr.assign(m->nc + 1, 0);
+    A->h_colidx.reserve(m->nhf + m->nc);
+    std::vector<int32_t> row;
+    for (i64 c = 0; c < m->nc; c++) {
+        row.clear();
+        row.push_back((int32_t)c);
+        for (int32_t i = m->h_hf_pos[c]; i < m->h_hf_pos[c + 1]; i++) row.push_back(m->h_hf_other[i]);
+        std::sort(row.begin(), row.end());
+        row.erase(std::unique(row.begin(), row.end()), row.end());
+        A->h_colidx.insert(A->h_colidx.end(), row.begin(), row.end());
+        A->h_rowptr[c + 1] = (int32_t)A->h_colidx.size();
+    }
+    A->nnzb = (i64)A->h_colidx.size();
+    int rc = csr_finish(ctx, A);
+    if (rc != JB_OK) { delete A; JB_FAIL(ctx, rc, "jb_csr_create_tpfa: device allocation failed"); }
+    *out = A;
+    return JB_OK;
+}
+int32_t jb_csr_destroy(jb_csr* A) { delete A; return JB_OK; }
+int64_t jb_csr_nnz(jb_csr* A) { return A ? A->nnzb : -1; }
+int64_t jb_csr_nrows(jb_csr* A) { return A ? A->n : -1; }
+int32_t jb_csr_get(jb_csr* A, int64_t* rowptr, int64_t* colidx) {
+    if (!A) return JB_ERR_ARG;
+    if (rowptr) for (i64 i = 0; i <= A->n; i++) rowptr[i] = (i64)A->h_rowptr[i] + 1;
+    if (colidx) for (i64 i = 0; i < A->nnzb; i++) colidx[i] = (i64)A->h_colidx[i] + 1;
+    return JB_OK;
+}
+int32_t jb_csr_values_get(jb_csr* A, double* nz) {
+    if (!A || !nz) return JB_ERR_ARG;
+    JB_CUDA(A->ctx, cudaMemcpyAsync(nz, A->d_val.p, A->d_val.n * sizeof(double), cudaMemcpyDeviceToHost, A->ctx->stream));
+    JB_CUDA(A->ctx, cudaStreamSynchronize(A->ctx->stream));
+    return JB_OK;
+}
+int32_t jb_csr_values_set(jb_csr* A, const double* nz) {
+    if (!A || !nz) return JB_ERR_ARG;
+    JB_CUDA(A->ctx, cudaMemcpyAsync(A->d_val.p, nz, A->d_val.n * sizeof(double), cudaMemcpyHostToDevice, A->ctx->stream));
+    JB_CUDA(A->ctx, cudaStreamSynchronize(A->ctx->stream));
+    return JB_OK;
+}
+double* jb_csr_values_ptr(jb_csr* A) { return A ? A->d_val.p : nullptr; }
+
+// ---------------------------------------------------------------- alignment
+static inline int32_t find_in_row(const jb_csr* A, int32_t row, int32_t col) {
+    const int32_t* b = A->h_colidx.data() + A->h_rowptr[row];
+    const int32_t* e = A->h_colidx.data() + A->h_rowptr[row + 1];
+    const int32_t* it = std::lower_bound(b, e, col);
+    if (it == e || *it != col) return -1;
+    return (int32_t)(it - A->h_colidx.data());
+}
+
+int32_t jb_tpfa_create(jb_mesh* m, jb_csr* A, jb_tpfa** out) {
+    if (!m || !A || !out || A->n != m->nc) return JB_ERR_ARG;
+    jb_ctx* ctx = m->ctx;
+    jb_tpfa* t = new jb_tpfa();
+    t->mesh = m; t->csr = A;
+    t->h_diag_pos.resize(m->nc); t->h_hf_pos.resize(m->nhf); t->h_hf_rowpos.resize(m->nhf);
+    bool ok = true;
+    for (i64 c = 0; c < m->nc; c++) {
+        t->h_diag_pos[c] = A->h_diag[c];
+        if (A->h_diag[c] < 0) ok = false;
+        for (int32_t i = m->h_hf_pos[c]; i < m->h_hf_pos[c + 1]; i++) {
+            int32_t o = m->h_hf_other[i];
+            t->h_hf_pos[i] = find_in_row(A, o, (int32_t)c);      // (row = other, col = self)
+            t->h_hf_rowpos[i] = find_in_row(A, (int32_t)c, o);   // (row = self, col = other)
+            if (t->h_hf_pos[i] < 0 || t->h_hf_rowpos[i] < 0) ok = false;
+        }
+    }
+    if (!ok) { delete t; JB_FAIL(ctx, JB_ERR_ARG, "Jacobian alignment failed: entry not allocated in Jacobian matrix"); }
+    if (t->d_hf_pos.upload(t->h_hf_pos, ctx->stream) != cudaSuccess || t->d_hf_rowpos.upload(t->h_hf_rowpos, ctx->stream) != cudaSuccess) {
+        delete t; JB_FAIL(ctx, JB_ERR_ALLOC, "jb_tpfa_create: device upload failed");
+    }
+    *out = t;
+    return JB_OK;
+}
+int32_t jb_tpfa_destroy(jb_tpfa* t) { delete t; return JB_OK; }
+int32_t jb_tpfa_positions(jb_tpfa* t, int64_t* diag_pos, int64_t* hf_pos) {
+    if (!t) return JB_ERR_ARG;
+    if (diag_pos) for (i64 c = 0; c < t->mesh->nc; c++) diag_pos[c] = (i64)t->h_diag_pos[c] + 1;
+    if (hf_pos) for (i64 i = 0; i < t->mesh->nhf; i++) hf_pos[i] = (i64)t->h_hf_pos[i] + 1;
+    return JB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- ILU(0) symbolic
+// Split into strict-lower / strict-upper in-block parts (fixed_block,
+// src/StaticCSR/ilu0.jl:13-54) and derive the dependency levels of the row-by-row
+// IKJ factorisation (ilu0_factor! :108-144) and of the two triangular sweeps
+// (:156-187). Rows of one level are mutually independent; processing levels in
+// order and each row's L entries in ascending column order performs exactly the
+// arithmetic of the sequential loop. The per-(row, L-entry) update lists replace
+// the binary-search getindex U[k, j] of the reference (process_partial_row!).
+int jb_ilu_symbolic(jb_ilu* F, const int64_t* partition) {
+    const jb_csr* A = F->csr;
+    const i64 n = A->n;
+    std::vector<int32_t> part;
+    if (partition) {
+        part.resize(n);
+        for (i64 i = 0; i < n; i++) {
+            if (partition[i] < 1) return JB_ERR_ARG;
+            part[i] = (int32_t)(partition[i] - 1);
+        }
+    }
+    auto same = [&](int32_t a, int32_t b) { return part.empty() || part[a] == part[b]; };
+    F->h_Dmap.assign(n, -1);
+    std::vector<int32_t> nl(n, 0), nu(n, 0), levF(n, 0), levB(n, 0);
+    for (i64 r = 0; r < n; r++) {
+        int32_t lf = 0;
+        for (int32_t k = A->h_rowptr[r]; k < A->h_rowptr[r + 1]; k++) {
+            int32_t c = A->h_colidx[k];
+            if (c == r) { F->h_Dmap[r] = k; continue; }
+            if (!same((int32_t)r, c)) continue;
+            if (c < r) { nl[r]++; lf = std::max(lf, levF[c] + 1); } else nu[r]++;
+        }
+        if (F->h_Dmap[r] < 0) return JB_ERR_ARG;  // "Diagonal must be present in sparsity pattern."
+        levF[r] = lf;
+    }
+    for (i64 r = n - 1; r >= 0; r--) {
+        int32_t lb = 0;
+        for (int32_t k = A->h_rowptr[r]; k < A->h_rowptr[r + 1]; k++) {
+            int32_t c = A->h_colidx[k];
+            if (c > r && same((int32_t)r, c)) lb = std::max(lb, levB[c] + 1);
+        }
+        levB[r] = lb;
+    }
+    auto order_by_level = [&](const std::vector<int32_t>& lev, std::vector<int32_t>& order, std::vector<int32_t>& ptr) {
+        int32_t nlev = 0;
+        for (i64 r = 0; r < n; r++) nlev = std::max(nlev, lev[r] + 1);
+        ptr.assign(nlev + 1, 0);
+        for (i64 r = 0; r < n; r++) ptr[lev[r] + 1]++;
+        for (int32_t l = 0; l < nlev; l++) ptr[l + 1] += ptr[l];
+        order.resize(n);
+        std::vector<int32_t> cur(ptr.begin(), ptr.end() - 1);
+        for (i64 r = 0; r < n; r++) order[cur[lev[r]]++] = (int32_t)r;  // ascending row index inside a level
+        return nlev;
+    };
+    F->nlevF = order_by_level(levF, F->h_forder, F->h_levF_ptr);
+    F->nlevB = order_by_level(levB, F->h_border, F->h_levB_ptr);
+    // storage: L rows laid out in forward-level order, U rows in backward-level order
+    F->h_Lstart.resize(n); F->h_Lend.resize(n); F->h_Ustart.resize(n); F->h_Uend.resize(n);
+    i64 off = 0;
+    for (i64 t = 0; t < n; t++) { int32_t r = F->h_forder[t]; F->h_Lstart[r] = (int32_t)off; off += nl[r]; F->h_Lend[r] = (int32_t)off; }
+    F->nL = off;
+    off = 0;
+    for (i64 t = 0; t < n; t++) { int32_t r = F->h_border[t]; F->h_Ustart[r] = (int32_t)off; off += nu[r]; F->h_Uend[r] = (int32_t)off; }
+    F->nU = off;
+    F->h_Lcol.resize(F->nL); F->h_Lmap.resize(F->nL); F->h_Ucol.resize(F->nU); F->h_Umap.resize(F->nU);
+    for (i64 r = 0; r < n; r++) {
+        int32_t il = F->h_Lstart[r], iu = F->h_Ustart[r];
+        for (int32_t k = A->h_rowptr[r]; k < A->h_rowptr[r + 1]; k++) {
+            int32_t c = A->h_colidx[k];
+            if (c == r || !same((int32_t)r, c)) continue;
+            if (c < r) { F->h_Lcol[il] = c; F->h_Lmap[il++] = k; } else { F->h_Ucol[iu] = c; F->h_Umap[iu++] = k; }
+        }
+    }
+    // update lists. Value buffer layout: [L (nL) | D (n) | U (nU)] in blocks.
+    const i64 baseD = F->nL, baseU = F->nL + n;
+    F->h_upd_ptr.assign(F->nL + 1, 0);
+    F->h_upd_tgt.clear(); F->h_upd_src.clear();
+    // Emit in L storage order so that a row's lists are contiguous.
+    for (i64 t = 0; t < n; t++) {
+        int32_t i = F->h_forder[t];
+        for (int32_t li = F->h_Lstart[i]; li < F->h_Lend[i]; li++) {
+            int32_t k = F->h_Lcol[li];
+            // intersect U row k with {L cols of row i after li} U {i} U {U cols of row i}
+            int32_t a = li + 1, ae = F->h_Lend[i];
+            int32_t b = F->h_Ustart[i], be = F->h_Uend[i];
+            for (int32_t uk = F->h_Ustart[k]; uk < F->h_Uend[k]; uk++) {
+                int32_t j = F->h_Ucol[uk];
+                if (j < i) {
+                    while (a < ae && F->h_Lcol[a] < j) a++;
+                    if (a < ae && F->h_Lcol[a] == j) { F->h_upd_tgt.push_back(a); F->h_upd_src.push_back((int32_t)(baseU + uk)); }
+                } else if (j == i) {
+                    F->h_upd_tgt.push_back((int32_t)(baseD + i)); F->h_upd_src.push_back((int32_t)(baseU + uk));
+                } else {
+                    while (b < be && F->h_Ucol[b] < j) b++;
+                    if (b < be && F->h_Ucol[b] == j) { F->h_upd_tgt.push_back((int32_t)(baseU + b)); F->h_upd_src.push_back((int32_t)(baseU + uk)); }
+                }
+            }
+            F->h_upd_ptr[li + 1] = (int32_t)F->h_upd_tgt.size();
+        }
+    }
+    if (!fits_i32((i64)F->h_upd_tgt.size()) || !fits_i32(F->nL + n + F->nU)) return JB_ERR_UNSUPPORTED;
+    return JB_OK;
+}
+
+int jb_ilu_upload(jb_ilu* F) {
+    cudaStream_t s = F->csr->ctx->stream;
+    bool ok = F->d_forder.upload(F->h_forder, s) == cudaSuccess && F->d_border.upload(F->h_border, s) == cudaSuccess &&
+              F->d_Lstart.upload(F->h_Lstart, s) == cudaSuccess && F->d_Lend.upload(F->h_Lend, s) == cudaSuccess &&
+              F->d_Ustart.upload(F->h_Ustart, s) == cudaSuccess && F->d_Uend.upload(F->h_Uend, s) == cudaSuccess &&
+              F->d_Lcol.upload(F->h_Lcol, s) == cudaSuccess && F->d_Ucol.upload(F->h_Ucol, s) == cudaSuccess &&
+              F->d_Lmap.upload(F->h_Lmap, s) == cudaSuccess && F->d_Umap.upload(F->h_Umap, s) == cudaSuccess &&
+              F->d_Dmap.upload(F->h_Dmap, s) == cudaSuccess && F->d_upd_ptr.upload(F->h_upd_ptr, s) == cudaSuccess &&
+              F->d_upd_tgt.upload(F->h_upd_tgt, s) == cudaSuccess && F->d_upd_src.upload(F->h_upd_src, s) == cudaSuccess;
+    const size_t b2 = (size_t)F->bs * F->bs;
+    ok = ok && F->d_fv.alloc((size_t)(F->nL + F->n + F->nU) * b2) == cudaSuccess && F->d_dinv.alloc((size_t)F->n * b2) == cudaSuccess &&
+         F->d_status.alloc(1) == cudaSuccess;
+    return ok ? JB_OK : JB_ERR_ALLOC;
+}

@@ -1,0 +1,261 @@
+// ILU(0) numeric factorisation and triangular solves, level-scheduled for the GPU.
+//
+// Semantics are those of ilu0_factor! / ilu_solve! (src/StaticCSR/ilu0.jl:108-193)
+// and of ParallelILUFactorCSR over a partition (src/StaticCSR/par_ilu0.jl:47-87):
+// row-by-row IKJ elimination in ascending row order inside each block, L holding
+// the multipliers L_ik * inv(D_k), D stored inverted, couplings between blocks
+// dropped. The sequential row loop is replaced by dependency levels computed at
+// setup (host_setup.cu): rows of a level are independent, one launch per level,
+// one thread per row. Within a row the L entries are visited in ascending column
+// order and every update L_ij / D_i / U_ij -= m * U_kj is applied from a
+// precomputed (target, source) list, so the arithmetic per row equals the
+// reference's. Storage is level-major (rows of one level are contiguous in the
+// L / U value arrays) so each level streams its part of the factor once.
+#include "jb_internal.cuh"
+#include "jb_krylov_scalars.cuh"
+
+template <int BS>
+__global__ void __launch_bounds__(256) ilu_gather_kernel(i64 nL, i64 n, i64 nU, const int32_t* __restrict__ Lmap,
+                                                         const int32_t* __restrict__ Dmap, const int32_t* __restrict__ Umap,
+                                                         const double* __restrict__ A, double* __restrict__ fv) {
+    // update_values! (src/StaticCSR/ilu0.jl:83-98): refresh L, D, U from the Jacobian through the stored maps.
+    constexpr int B2 = BS * BS;
+    const i64 total = (nL + n + nU) * B2;
+    for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+        const i64 blk = idx / B2;
+        const int q = (int)(idx % B2);
+        int32_t src;
+        if (blk < nL) src = __ldg(Lmap + blk);
+        else if (blk < nL + n) src = __ldg(Dmap + (blk - nL));
+        else src = __ldg(Umap + (blk - nL - n));
+        fv[idx] = __ldg(A + (size_t)src * B2 + q);
+    }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(128) ilu_factor_level_kernel(int32_t t0, int32_t t1, i64 nL, const int32_t* __restrict__ forder,
+                                                               const int32_t* __restrict__ Lstart, const int32_t* __restrict__ Lend,
+                                                               const int32_t* __restrict__ Lcol, const int32_t* __restrict__ upd_ptr,
+                                                               const int32_t* __restrict__ upd_tgt, const int32_t* __restrict__ upd_src,
+                                                               double* __restrict__ fv, double* __restrict__ dinv, int32_t* status) {
+    constexpr int B2 = BS * BS;
+    const int32_t t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t1) return;
+    const int32_t i = __ldg(forder + t);
+    const int32_t l0 = __ldg(Lstart + i), l1 = __ldg(Lend + i);
+    for (int32_t li = l0; li < l1; li++) {
+        const int32_t k = __ldg(Lcol + li);
+        double Lik[B2], Dk[B2], m[B2];
+#pragma unroll
+        for (int q = 0; q < B2; q++) { Lik[q] = fv[(size_t)li * B2 + q]; Dk[q] = dinv[(size_t)k * B2 + q]; }
+        blk_mul<BS>(Lik, Dk, m);   // A_ik = L_ik * inv(D_kk)
+#pragma unroll
+        for (int q = 0; q < B2; q++) fv[(size_t)li * B2 + q] = m[q];
+        const int32_t u0 = __ldg(upd_ptr + li), u1 = __ldg(upd_ptr + li + 1);
+        for (int32_t u = u0; u < u1; u++) {
+            const size_t tg = (size_t)__ldg(upd_tgt + u) * B2, sr = (size_t)__ldg(upd_src + u) * B2;
+            double Ukj[B2], prod[B2];
+#pragma unroll
+            for (int q = 0; q < B2; q++) Ukj[q] = fv[sr + q];
+            blk_mul<BS>(m, Ukj, prod);
+#pragma unroll
+            for (int q = 0; q < B2; q++) fv[tg + q] -= prod[q];
+        }
+    }
+    double D[B2], Di[B2];
+#pragma unroll
+    for (int q = 0; q < B2; q++) D[q] = fv[(size_t)(nL + i) * B2 + q];
+    blk_inv<BS>(D, Di);
+    bool bad = false;
+#pragma unroll
+    for (int q = 0; q < B2; q++) { dinv[(size_t)i * B2 + q] = Di[q]; bad |= !isfinite(Di[q]); }
+    if (bad) *status = JB_BAD_PIVOT;
+}
+
+// forward sweep: x_i = b_i - sum_j L_ij x_j  (unit diagonal), rows of one level
+template <int BS>
+__global__ void __launch_bounds__(256) ilu_forward_level_kernel(int32_t t0, int32_t t1, const int32_t* __restrict__ forder,
+                                                                const int32_t* __restrict__ Lstart, const int32_t* __restrict__ Lend,
+                                                                const int32_t* __restrict__ Lcol, const double* __restrict__ fv,
+                                                                const double* __restrict__ b, double* x, const double* sc) {
+    constexpr int B2 = BS * BS;
+    if (sc && sc[KS_DONE] != 0.0) return;
+    const int32_t t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t1) return;
+    const int32_t i = __ldg(forder + t);
+    double v[BS];
+#pragma unroll
+    for (int e = 0; e < BS; e++) v[e] = b[(size_t)i * BS + e];
+    const int32_t l0 = __ldg(Lstart + i), l1 = __ldg(Lend + i);
+    for (int32_t li = l0; li < l1; li++) {
+        const int32_t j = __ldg(Lcol + li);
+        double a[B2], xj[BS];
+#pragma unroll
+        for (int q = 0; q < B2; q++) a[q] = __ldg(fv + (size_t)li * B2 + q);
+#pragma unroll
+        for (int e = 0; e < BS; e++) xj[e] = x[(size_t)j * BS + e];
+        blk_submulvec<BS>(a, xj, v);
+    }
+#pragma unroll
+    for (int e = 0; e < BS; e++) x[(size_t)i * BS + e] = v[e];
+}
+
+// backward sweep: x_i = Dinv_i (x_i - sum_j U_ij x_j)
+template <int BS>
+__global__ void __launch_bounds__(256) ilu_backward_level_kernel(int32_t t0, int32_t t1, i64 baseU, const int32_t* __restrict__ border,
+                                                                 const int32_t* __restrict__ Ustart, const int32_t* __restrict__ Uend,
+                                                                 const int32_t* __restrict__ Ucol, const double* __restrict__ fv,
+                                                                 const double* __restrict__ dinv, double* x, const double* sc) {
+    constexpr int B2 = BS * BS;
+    if (sc && sc[KS_DONE] != 0.0) return;
+    const int32_t t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t1) return;
+    const int32_t i = __ldg(border + t);
+    double v[BS], out[BS], d[B2];
+#pragma unroll
+    for (int e = 0; e < BS; e++) v[e] = x[(size_t)i * BS + e];
+    const int32_t u0 = __ldg(Ustart + i), u1 = __ldg(Uend + i);
+    for (int32_t ui = u0; ui < u1; ui++) {
+        const int32_t j = __ldg(Ucol + ui);
+        double a[B2], xj[BS];
+#pragma unroll
+        for (int q = 0; q < B2; q++) a[q] = __ldg(fv + (size_t)(baseU + ui) * B2 + q);
+#pragma unroll
+        for (int e = 0; e < BS; e++) xj[e] = x[(size_t)j * BS + e];
+        blk_submulvec<BS>(a, xj, v);
+    }
+#pragma unroll
+    for (int q = 0; q < B2; q++) d[q] = __ldg(dinv + (size_t)i * B2 + q);
+    blk_mulvec<BS>(d, v, out);
+#pragma unroll
+    for (int e = 0; e < BS; e++) x[(size_t)i * BS + e] = out[e];
+}
+
+template <int BS>
+static int ilu_factor_t(jb_ilu* F) {
+    jb_ctx* ctx = F->csr->ctx;
+    cudaStream_t s = ctx->stream;
+    JB_CUDA(ctx, cudaMemsetAsync(F->d_status.p, 0, sizeof(int32_t), s));
+    const i64 total = (F->nL + F->n + F->nU) * BS * BS;
+    int grid = (int)std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 16);
+    ilu_gather_kernel<BS><<<std::max(grid, 1), 256, 0, s>>>(F->nL, F->n, F->nU, F->d_Lmap.p, F->d_Dmap.p, F->d_Umap.p, F->csr->d_val.p, F->d_fv.p);
+    JB_CHECK_LAUNCH(ctx);
+    for (int l = 0; l < F->nlevF; l++) {
+        const int32_t t0 = F->h_levF_ptr[l], t1 = F->h_levF_ptr[l + 1];
+        if (t1 <= t0) continue;
+        ilu_factor_level_kernel<BS><<<(t1 - t0 + 127) / 128, 128, 0, s>>>(t0, t1, F->nL, F->d_forder.p, F->d_Lstart.p, F->d_Lend.p, F->d_Lcol.p,
+                                                                          F->d_upd_ptr.p, F->d_upd_tgt.p, F->d_upd_src.p, F->d_fv.p, F->d_dinv.p,
+                                                                          F->d_status.p);
+        JB_CHECK_LAUNCH(ctx);
+    }
+    return JB_OK;
+}
+
+template <int BS>
+static int ilu_apply_t(jb_ilu* F, const double* b, double* x, const double* sc) {
+    jb_ctx* ctx = F->csr->ctx;
+    cudaStream_t s = ctx->stream;
+    for (int l = 0; l < F->nlevF; l++) {
+        const int32_t t0 = F->h_levF_ptr[l], t1 = F->h_levF_ptr[l + 1];
+        if (t1 <= t0) continue;
+        ilu_forward_level_kernel<BS><<<(t1 - t0 + 255) / 256, 256, 0, s>>>(t0, t1, F->d_forder.p, F->d_Lstart.p, F->d_Lend.p, F->d_Lcol.p,
+                                                                           F->d_fv.p, b, x, sc);
+        JB_CHECK_LAUNCH(ctx);
+    }
+    for (int l = 0; l < F->nlevB; l++) {
+        const int32_t t0 = F->h_levB_ptr[l], t1 = F->h_levB_ptr[l + 1];
+        if (t1 <= t0) continue;
+        ilu_backward_level_kernel<BS><<<(t1 - t0 + 255) / 256, 256, 0, s>>>(t0, t1, F->nL + F->n, F->d_border.p, F->d_Ustart.p, F->d_Uend.p,
+                                                                            F->d_Ucol.p, F->d_fv.p, F->d_dinv.p, x, sc);
+        JB_CHECK_LAUNCH(ctx);
+    }
+    return JB_OK;
+}
+
+int jb_launch_ilu_factor(jb_ilu* F) {
+    switch (F->bs) {
+        case 1: return ilu_factor_t<1>(F);
+        case 2: return ilu_factor_t<2>(F);
+        case 3: return ilu_factor_t<3>(F);
+        case 4: return ilu_factor_t<4>(F);
+    }
+    return JB_ERR_UNSUPPORTED;
+}
+int jb_launch_ilu_apply_sc(jb_ilu* F, const double* d_b, double* d_x, const double* d_sc) {
+    switch (F->bs) {
+        case 1: return ilu_apply_t<1>(F, d_b, d_x, d_sc);
+        case 2: return ilu_apply_t<2>(F, d_b, d_x, d_sc);
+        case 3: return ilu_apply_t<3>(F, d_b, d_x, d_sc);
+        case 4: return ilu_apply_t<4>(F, d_b, d_x, d_sc);
+    }
+    return JB_ERR_UNSUPPORTED;
+}
+int jb_launch_ilu_apply(jb_ilu* F, const double* d_b, double* d_x) { return jb_launch_ilu_apply_sc(F, d_b, d_x, nullptr); }
+
+extern "C" {
+
+int32_t jb_ilu0_create(jb_csr* A, const int64_t* partition, jb_ilu** out) {
+    if (!A || !out) return JB_ERR_ARG;
+    jb_ilu* F = new jb_ilu();
+    F->csr = A; F->n = A->n; F->bs = A->bs;
+    int rc = jb_ilu_symbolic(F, partition);
+    if (rc == JB_OK) rc = jb_ilu_upload(F);
+    if (rc != JB_OK) { delete F; JB_FAIL(A->ctx, rc, "jb_ilu0_create: symbolic phase failed (missing diagonal, bad partition or allocation)"); }
+    *out = F;
+    return JB_OK;
+}
+int32_t jb_ilu0_destroy(jb_ilu* F) {
+    if (F && F->apply_graph) cudaGraphExecDestroy(F->apply_graph);
+    delete F;
+    return JB_OK;
+}
+int32_t jb_ilu0_update(jb_ilu* F) {
+    if (!F) return JB_ERR_ARG;
+    jb_ctx* ctx = F->csr->ctx;
+    int rc = jb_launch_ilu_factor(F);
+    if (rc != JB_OK) return rc;
+    int32_t st = 0;
+    JB_CUDA(ctx, cudaMemcpyAsync(&st, F->d_status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return st;
+}
+int32_t jb_ilu0_apply(jb_ilu* F, const double* d_b, double* d_x) {
+    if (!F || !d_b || !d_x) return JB_ERR_ARG;
+    int rc = jb_launch_ilu_apply(F, d_b, d_x);
+    if (rc != JB_OK) return rc;
+    JB_CUDA(F->csr->ctx, cudaStreamSynchronize(F->csr->ctx->stream));
+    return JB_OK;
+}
+int32_t jb_ilu0_info(jb_ilu* F, int64_t* info) {
+    if (!F || !info) return JB_ERR_ARG;
+    info[0] = F->nlevF; info[1] = F->nlevB; info[2] = F->nL; info[3] = F->nU;
+    return JB_OK;
+}
+// Dump in the reference's layout: L and U as CSR over all rows (ascending row), 1-based.
+int32_t jb_ilu0_get(jb_ilu* F, int64_t* Lptr, int64_t* Lcol, double* L, int64_t* Uptr, int64_t* Ucol, double* U, double* Dinv) {
+    if (!F) return JB_ERR_ARG;
+    jb_ctx* ctx = F->csr->ctx;
+    const int b2 = F->bs * F->bs;
+    std::vector<double> fv((size_t)(F->nL + F->n + F->nU) * b2);
+    JB_CUDA(ctx, cudaMemcpyAsync(fv.data(), F->d_fv.p, fv.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (Dinv) JB_CUDA(ctx, cudaMemcpyAsync(Dinv, F->d_dinv.p, (size_t)F->n * b2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    i64 ol = 0, ou = 0;
+    for (i64 r = 0; r < F->n; r++) {
+        if (Lptr) Lptr[r] = ol + 1;
+        if (Uptr) Uptr[r] = ou + 1;
+        for (int32_t k = F->h_Lstart[r]; k < F->h_Lend[r]; k++, ol++) {
+            if (Lcol) Lcol[ol] = F->h_Lcol[k] + 1;
+            if (L) memcpy(L + ol * b2, &fv[(size_t)k * b2], sizeof(double) * b2);
+        }
+        for (int32_t k = F->h_Ustart[r]; k < F->h_Uend[r]; k++, ou++) {
+            if (Ucol) Ucol[ou] = F->h_Ucol[k] + 1;
+            if (U) memcpy(U + ou * b2, &fv[(size_t)(F->nL + F->n + k) * b2], sizeof(double) * b2);
+        }
+    }
+    if (Lptr) Lptr[F->n] = ol + 1;
+    if (Uptr) Uptr[F->n] = ou + 1;
+    return JB_OK;
+}
+
+}  // extern "C"

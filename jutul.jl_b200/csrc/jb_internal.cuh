@@ -1,0 +1,257 @@
+// Internal declarations shared by the translation units of libjutul_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jutul_b200.h"
+
+typedef int64_t i64;
+
+#define JB_SM_COUNT_DEFAULT 148
+
+void jb_set_global_error(const std::string& s);
+
+struct jb_ctx {
+    int device = 0;
+    int sm_count = JB_SM_COUNT_DEFAULT;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    i64 launches = 0;
+    // reduction workspace: per-CTA partials + completion counters
+    double* d_partials = nullptr;   // JB_MAX_PARTIALS * JB_MAX_RED doubles
+    unsigned int* d_counters = nullptr;
+    double* d_scalars = nullptr;    // small device scalar scratch (64 doubles)
+    double* h_pinned = nullptr;     // pinned host scratch (>= 4096 doubles)
+};
+
+#define JB_MAX_PARTIALS 2048
+#define JB_MAX_RED 4
+
+#define JB_CUDA(ctx, call)                                                                       \
+    do {                                                                                         \
+        cudaError_t _e = (call);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            std::string _m = std::string(#call) + ": " + cudaGetErrorString(_e);                 \
+            if (ctx) (ctx)->err = _m;                                                            \
+            jb_set_global_error(_m);                                                             \
+            return JB_ERR_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+#define JB_FAIL(ctx, code, msg)                  \
+    do {                                         \
+        std::string _m = (msg);                  \
+        if (ctx) (ctx)->err = _m;                \
+        jb_set_global_error(_m);                 \
+        return (code);                           \
+    } while (0)
+
+#define JB_CHECK_LAUNCH(ctx)                                   \
+    do {                                                       \
+        (ctx)->launches++;                                     \
+        JB_CUDA(ctx, cudaGetLastError());                      \
+    } while (0)
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DBuf() {}
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    ~DBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& h, cudaStream_t s) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        e = cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return e;
+        return cudaStreamSynchronize(s);
+    }
+};
+
+struct jb_mesh {
+    jb_ctx* ctx;
+    i64 nc, nf, nhf;
+    std::vector<int32_t> h_left, h_right;                 // per face, 0-based
+    std::vector<int32_t> h_hf_pos, h_hf_face, h_hf_other; // half-face CSR, 0-based
+    std::vector<int8_t> h_hf_sign;
+    DBuf<int32_t> d_left, d_right, d_hf_pos, d_hf_face, d_hf_other;
+    DBuf<int8_t> d_hf_sign;
+};
+
+struct jb_csr {
+    jb_ctx* ctx;
+    i64 n, nnzb;
+    int bs;
+    std::vector<int32_t> h_rowptr, h_colidx, h_diag;  // 0-based
+    DBuf<int32_t> d_rowptr, d_colidx, d_diag;
+    DBuf<double> d_val;
+};
+
+struct jb_tpfa {
+    jb_mesh* mesh;
+    jb_csr* csr;
+    std::vector<int32_t> h_diag_pos;    // block index of (c,c)
+    std::vector<int32_t> h_hf_pos;      // block index of (other,self)  [reference's table]
+    std::vector<int32_t> h_hf_rowpos;   // block index of (self,other)  [row-owner writes]
+    DBuf<int32_t> d_hf_pos, d_hf_rowpos;
+};
+
+struct jb_twophase {
+    jb_tpfa* t;
+    double params[7];
+    DBuf<double> d_hf_T, d_hf_sgdz;   // per half-face: T_f and sign*gdz_f
+    DBuf<double> d_face_T, d_face_gdz;  // per face (variant B)
+    DBuf<int32_t> d_pos_lr, d_pos_rl;   // per face: block index of (l,r) and (r,l) (variant B)
+    DBuf<double> d_pv;
+    DBuf<double> d_rec;               // per cell {p, sw, rho_w, rho_o}
+    DBuf<double> d_src;               // dense 2 x nc source buffer (only if nsrc > 0)
+    DBuf<int32_t> d_src_cells;
+    DBuf<double> d_src_vals;
+    i64 nsrc = 0;
+    // resident state for the host-facing perform_step
+    DBuf<double> d_p, d_s, d_M0, d_r, d_dx;
+};
+
+struct jb_ilu {
+    jb_csr* csr;
+    i64 n, nL, nU;
+    int bs;
+    int nlevF, nlevB;
+    // host symbolic data (0-based)
+    std::vector<int32_t> h_forder, h_border, h_levF_ptr, h_levB_ptr;
+    std::vector<int32_t> h_Lstart, h_Lend, h_Ustart, h_Uend;      // per row, offsets into L / U storage
+    std::vector<int32_t> h_Lcol, h_Ucol, h_Lmap, h_Umap, h_Dmap;  // storage order
+    std::vector<int32_t> h_upd_ptr, h_upd_tgt, h_upd_src;
+    // device
+    DBuf<int32_t> d_forder, d_border, d_Lstart, d_Lend, d_Ustart, d_Uend, d_Lcol, d_Ucol, d_Lmap, d_Umap, d_Dmap;
+    DBuf<int32_t> d_upd_ptr, d_upd_tgt, d_upd_src;
+    DBuf<double> d_fv;     // [L | D | U] blocks
+    DBuf<double> d_dinv;   // inverted diagonal blocks
+    DBuf<int32_t> d_status;
+    cudaGraphExec_t apply_graph = nullptr;
+    const double* graph_b = nullptr;
+    double* graph_x = nullptr;
+};
+
+struct KrylovScalars;  // device-side scalar block (krylov.cu)
+
+struct jb_krylov {
+    jb_csr* csr;
+    jb_ilu* ilu;
+    int kind;
+    i64 m;  // n*bs
+    DBuf<double> r, p, v, s, y, z, t, x, q, c;
+    DBuf<double> d_sc;      // scalar block
+    DBuf<double> d_hist;
+    double* h_flags = nullptr;  // pinned
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int hist_cap = 0;
+    // gmres
+    DBuf<double> V;  // (mem+1) x m basis
+    int gm_mem = 0;
+};
+
+// ---- launchers implemented in the kernel translation units (all enqueue on ctx->stream) ----
+enum { JB_DOT_NONE = 0, JB_DOT_CV = 1, JB_DOT_TS_TT = 2 };
+
+int jb_launch_spmv(jb_csr* A, double alpha, const double* d_x, double beta, double* d_y);
+// y = A*x fused with dot products; results accumulated by the finalizer into sc (see krylov.cu)
+int jb_launch_spmv_dots(jb_csr* A, const double* d_x, double* d_y, int mode, const double* d_u, double* d_sc);
+
+int jb_ilu_symbolic(jb_ilu* F, const int64_t* partition);
+int jb_ilu_upload(jb_ilu* F);
+int jb_launch_ilu_factor(jb_ilu* F);
+int jb_launch_ilu_apply(jb_ilu* F, const double* d_b, double* d_x);
+
+int jb_launch_twophase_state(jb_twophase* m, const double* d_p, const double* d_s);
+int jb_launch_twophase_assemble(jb_twophase* m, const double* d_M0, double dt, double* d_r, bool jac);
+int jb_launch_twophase_assemble_faces(jb_twophase* m, const double* d_M0, double dt, double* d_r);
+int jb_launch_twophase_mass(jb_twophase* m, const double* d_p, const double* d_s, double* d_M);
+
+// small dense block helpers usable on host and device
+#ifdef __CUDACC__
+#define JB_HD __host__ __device__ __forceinline__
+#else
+#define JB_HD inline
+#endif
+
+template <int BS>
+JB_HD void blk_inv(const double* A, double* B) {
+    if (BS == 1) {
+        B[0] = 1.0 / A[0];
+    } else if (BS == 2) {
+        double det = A[0] * A[3] - A[2] * A[1];
+        double idet = 1.0 / det;
+        B[0] = A[3] * idet; B[1] = -(A[1] * idet); B[2] = -(A[2] * idet); B[3] = A[0] * idet;
+    } else {
+        double M[BS * BS], I[BS * BS];
+        for (int i = 0; i < BS * BS; i++) { M[i] = A[i]; I[i] = 0.0; }
+        for (int i = 0; i < BS; i++) I[i * BS + i] = 1.0;
+        for (int c = 0; c < BS; c++) {
+            int piv = c;
+            for (int r = c + 1; r < BS; r++) if (fabs(M[c * BS + r]) > fabs(M[c * BS + piv])) piv = r;
+            if (piv != c) for (int k = 0; k < BS; k++) {
+                double a = M[k * BS + c]; M[k * BS + c] = M[k * BS + piv]; M[k * BS + piv] = a;
+                a = I[k * BS + c]; I[k * BS + c] = I[k * BS + piv]; I[k * BS + piv] = a;
+            }
+            double ip = 1.0 / M[c * BS + c];
+            for (int k = 0; k < BS; k++) { M[k * BS + c] *= ip; I[k * BS + c] *= ip; }
+            for (int r = 0; r < BS; r++) if (r != c) {
+                double f = M[c * BS + r];
+                for (int k = 0; k < BS; k++) { M[k * BS + r] -= f * M[k * BS + c]; I[k * BS + r] -= f * I[k * BS + c]; }
+            }
+        }
+        for (int i = 0; i < BS * BS; i++) B[i] = I[i];
+    }
+}
+// C = A*B, column-major
+template <int BS>
+JB_HD void blk_mul(const double* A, const double* B, double* C) {
+#pragma unroll
+    for (int j = 0; j < BS; j++)
+#pragma unroll
+        for (int i = 0; i < BS; i++) {
+            double s = A[i] * B[j * BS];
+#pragma unroll
+            for (int p = 1; p < BS; p++) s += A[p * BS + i] * B[j * BS + p];
+            C[j * BS + i] = s;
+        }
+}
+// y -= A*x
+template <int BS>
+JB_HD void blk_submulvec(const double* A, const double* x, double* y) {
+#pragma unroll
+    for (int i = 0; i < BS; i++) {
+        double s = A[i] * x[0];
+#pragma unroll
+        for (int p = 1; p < BS; p++) s += A[p * BS + i] * x[p];
+        y[i] -= s;
+    }
+}
+template <int BS>
+JB_HD void blk_mulvec(const double* A, const double* x, double* y) {
+#pragma unroll
+    for (int i = 0; i < BS; i++) {
+        double s = A[i] * x[0];
+#pragma unroll
+        for (int p = 1; p < BS; p++) s += A[p * BS + i] * x[p];
+        y[i] = s;
+    }
+}

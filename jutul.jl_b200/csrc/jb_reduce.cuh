@@ -1,0 +1,71 @@
+// Deterministic grid-wide reductions: every CTA writes its partial sums, the last
+// CTA to finish (ticket counter) adds the partials in a fixed order and runs a
+// finaliser with the totals. No floating-point atomics, so results are bitwise
+// reproducible for a fixed grid size.
+#pragma once
+#include "jb_internal.cuh"
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+struct OpSum { __device__ static double ident() { return 0.0; } __device__ static double warp(double v) { return warp_sum(v); } __device__ static double comb(double a, double b) { return a + b; } };
+struct OpMax { __device__ static double ident() { return 0.0; } __device__ static double warp(double v) { return warp_max(v); } __device__ static double comb(double a, double b) { return fmax(a, b); } };
+
+// Reduce NR values over the CTA; result valid in thread 0. BLOCK must be a multiple of 32, <= 1024.
+template <int NR, class Op>
+__device__ __forceinline__ void block_reduce(double (&v)[NR], double* smem /* NR*32 */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int r = 0; r < NR; r++) v[r] = Op::warp(v[r]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) smem[r * 32 + wid] = v[r];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            double x = (lane < nw) ? smem[r * 32 + lane] : Op::ident();
+            v[r] = Op::warp(x);
+        }
+    }
+}
+
+// Grid reduction. All threads of all CTAs must call. `fin(totals)` runs on thread 0 of the
+// last CTA. partials: gridDim.x*NR doubles; counter: one unsigned, zero before first use
+// (atomicInc wraps it back to zero).
+template <int NR, class Op, class Fin>
+__device__ __forceinline__ void grid_reduce(double (&v)[NR], double* partials, unsigned int* counter, Fin fin) {
+    __shared__ double smem[NR * 32];
+    __shared__ bool is_last;
+    block_reduce<NR, Op>(v, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) partials[(size_t)blockIdx.x * NR + r] = v[r];
+        __threadfence();
+        unsigned int ticket = atomicInc(counter, gridDim.x - 1);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double acc[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) acc[r] = Op::ident();
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+            for (int r = 0; r < NR; r++) acc[r] = Op::comb(acc[r], __ldcg(&partials[(size_t)b * NR + r]));
+        }
+        block_reduce<NR, Op>(acc, smem);
+        if (threadIdx.x == 0) fin(acc);
+    }
+}

@@ -1,0 +1,275 @@
+// ILU(0)-preconditioned BiCGStab for sm_100a, in the operation order of Krylov.jl
+// 0.9 `bicgstab!` as Jutul calls it (src/linsolve/krylov.jl:71-182,212-238):
+// x0 = 0, c = b, right preconditioning by default (src/linsolve/utils.jl:25),
+// left for the distributed path (ext/JutulPartitionedArraysExt/krylov.jl:60).
+//
+// B200 design: the whole iteration lives on the device. The 19 vector streams
+// of an iteration are fused into three update kernels; the five inner products
+// are fused into the kernels that produce their operands (<c,v> and <t,s>,<t,t>
+// into the SpMV, <c,r>,<r,r> into the residual update) and reduced
+// deterministically; alpha, omega, beta, |r| and the termination flags are
+// device-resident scalars written by the last CTA of the reducing kernel, so no
+// host round trip sits between kernels. The host enqueues one iteration ahead
+// and polls a pinned copy of the flags; once `done` is set all later kernels of
+// the solve return immediately.
+#include "jb_internal.cuh"
+#include "jb_krylov_scalars.cuh"
+#include "jb_reduce.cuh"
+
+int jb_launch_ilu_apply_sc(jb_ilu* F, const double* d_b, double* d_x, const double* d_sc);
+
+__global__ void __launch_bounds__(256) bicg_init_kernel(i64 m, const double* __restrict__ b, const double* rin, double* r, double* __restrict__ p,
+                                                        double* __restrict__ x, double* __restrict__ v, double* __restrict__ s, double* sc,
+                                                        double* hist, double* partials, unsigned int* counter) {
+    double d[2] = {0.0, 0.0};
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
+        const double ri = rin[i];
+        r[i] = ri; p[i] = ri; x[i] = 0.0; v[i] = 0.0; s[i] = 0.0;
+        d[0] = fma(ri, ri, d[0]);
+        d[1] = fma(__ldg(b + i), ri, d[1]);
+    }
+    grid_reduce<2, OpSum>(d, partials, counter, [=](double(&t)[2]) {
+        const double rnorm = sqrt(t[0]);
+        sc[KS_RNORM] = rnorm; sc[KS_R0] = rnorm;
+        sc[KS_EPS] = sc[KS_ATOL] + sc[KS_RTOL] * rnorm;
+        sc[KS_RHO] = t[1];
+        sc[KS_ALPHA] = 1.0; sc[KS_OMEGA] = 1.0; sc[KS_BETA] = 0.0;
+        sc[KS_ITER] = 0.0;
+        hist[0] = rnorm;
+        double done = 0.0, status = 1.0;
+        if (rnorm == 0.0) { done = 1.0; status = 0.0; }            // x = 0 is the solution
+        else if (t[1] == 0.0) { done = 1.0; status = 2.0; }        // "Breakdown b'c = 0"
+        else if (rnorm <= sc[KS_EPS]) { done = 1.0; status = 0.0; }
+        else if (sc[KS_ITMAX] <= 0.0) { done = 1.0; status = 1.0; }
+        sc[KS_DONE] = done; sc[KS_STATUS] = status;
+    });
+}
+
+// s = r - alpha v ; x += alpha y
+__global__ void __launch_bounds__(256) bicg_update1_kernel(i64 m, const double* sc, const double* __restrict__ r, const double* __restrict__ v,
+                                                           const double* __restrict__ y, double* __restrict__ s, double* __restrict__ x) {
+    if (sc[KS_DONE] != 0.0) return;
+    const double alpha = sc[KS_ALPHA];
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
+        s[i] = fma(-alpha, __ldg(v + i), __ldg(r + i));
+        x[i] = fma(alpha, __ldg(y + i), x[i]);
+    }
+}
+
+// x += omega z ; r = s - omega t ; rho' = <c,r>, |r| ; beta ; termination
+__global__ void __launch_bounds__(256) bicg_update2_kernel(i64 m, double* sc, const double* __restrict__ s, const double* __restrict__ t,
+                                                           const double* __restrict__ z, const double* __restrict__ c, double* __restrict__ x,
+                                                           double* __restrict__ r, double* hist, int hist_cap, double* partials,
+                                                           unsigned int* counter) {
+    if (sc[KS_DONE] != 0.0) return;
+    const double omega = sc[KS_OMEGA];
+    double d[2] = {0.0, 0.0};
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
+        x[i] = fma(omega, __ldg(z + i), x[i]);
+        const double ri = fma(-omega, __ldg(t + i), __ldg(s + i));
+        r[i] = ri;
+        d[0] = fma(__ldg(c + i), ri, d[0]);
+        d[1] = fma(ri, ri, d[1]);
+    }
+    grid_reduce<2, OpSum>(d, partials, counter, [=](double(&tt)[2]) {
+        const double alpha = sc[KS_ALPHA], om = sc[KS_OMEGA], rho = sc[KS_RHO];
+        const double next_rho = tt[0];
+        sc[KS_BETA] = (next_rho / rho) * (alpha / om);
+        sc[KS_RHO] = next_rho;
+        const double rnorm = sqrt(tt[1]);
+        sc[KS_RNORM] = rnorm;
+        const double iter = sc[KS_ITER] + 1.0;
+        sc[KS_ITER] = iter;
+        if ((int)iter < hist_cap) hist[(int)iter] = rnorm;
+        const bool mach = (rnorm + 1.0 <= 1.0);
+        bool solved = (rnorm <= sc[KS_EPS]) || mach;
+        bool user_exit = false;
+        if (sc[KS_MANUAL] != 0.0)   // krylov_termination_criterion (src/linsolve/krylov.jl:198-205)
+            user_exit = (rnorm <= sc[KS_ABS_TOL] + sc[KS_REL_TOL] * sc[KS_R0]) && (iter + 1.0 > sc[KS_MIN_IT]);
+        const bool tired = iter >= sc[KS_ITMAX];
+        const bool breakdown = (alpha == 0.0) || isnan(alpha);
+        if (solved || user_exit) { sc[KS_DONE] = 1.0; sc[KS_STATUS] = 0.0; }
+        else if (breakdown) { sc[KS_DONE] = 1.0; sc[KS_STATUS] = 2.0; }
+        else if (tired) { sc[KS_DONE] = 1.0; sc[KS_STATUS] = 1.0; }
+    });
+}
+
+// p = r + beta (p - omega v)
+__global__ void __launch_bounds__(256) bicg_update3_kernel(i64 m, const double* sc, const double* __restrict__ r, const double* __restrict__ v,
+                                                           double* __restrict__ p) {
+    if (sc[KS_DONE] != 0.0) return;
+    const double beta = sc[KS_BETA], omega = sc[KS_OMEGA];
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
+        const double pa = fma(-omega, __ldg(v + i), p[i]);
+        p[i] = fma(beta, pa, __ldg(r + i));
+    }
+}
+
+// stand-alone dots for the left-preconditioned / unfused paths
+template <int MODE>
+__global__ void __launch_bounds__(256) bicg_dot_kernel(i64 m, double* sc, const double* __restrict__ a, const double* __restrict__ b,
+                                                       double* partials, unsigned int* counter) {
+    if (sc[KS_DONE] != 0.0) return;
+    double d[2] = {0.0, 0.0};
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
+        const double ai = __ldg(a + i);
+        d[0] = fma(ai, __ldg(b + i), d[0]);
+        if (MODE == JB_DOT_TS_TT) d[1] = fma(ai, ai, d[1]);
+    }
+    grid_reduce<2, OpSum>(d, partials, counter, [=](double(&t)[2]) {
+        if (MODE == JB_DOT_CV) sc[KS_ALPHA] = sc[KS_RHO] / t[0];
+        else sc[KS_OMEGA] = t[0] / t[1];
+    });
+}
+
+__global__ void __launch_bounds__(256) negate_kernel(i64 m, const double* __restrict__ x, double* __restrict__ dx) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) dx[i] = -__ldg(x + i);
+}
+
+static int vec_grid(jb_ctx* ctx, i64 m) {
+    i64 want = (m + 255) / 256;
+    i64 cap = std::min<i64>((i64)ctx->sm_count * 8, JB_MAX_PARTIALS);
+    return (int)std::max<i64>(1, std::min(want, cap));
+}
+
+extern "C" {
+
+int32_t jb_krylov_create(jb_csr* A, jb_ilu* ilu, int32_t kind, jb_krylov** out) {
+    if (!A || !out) return JB_ERR_ARG;
+    jb_ctx* ctx = A->ctx;
+    if (kind != 0) JB_FAIL(ctx, JB_ERR_UNSUPPORTED, "jb_krylov_create: only kind 0 (bicgstab) is implemented in this build");
+    jb_krylov* K = new jb_krylov();
+    K->csr = A; K->ilu = ilu; K->kind = kind; K->m = A->n * A->bs;
+    const size_t m = (size_t)K->m;
+    bool ok = K->r.alloc(m) == cudaSuccess && K->p.alloc(m) == cudaSuccess && K->v.alloc(m) == cudaSuccess && K->s.alloc(m) == cudaSuccess &&
+              K->y.alloc(m) == cudaSuccess && K->z.alloc(m) == cudaSuccess && K->t.alloc(m) == cudaSuccess && K->x.alloc(m) == cudaSuccess &&
+              K->q.alloc(m) == cudaSuccess && K->d_sc.alloc(KS_SIZE) == cudaSuccess;
+    K->hist_cap = 1026;
+    ok = ok && K->d_hist.alloc(K->hist_cap) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&K->h_flags, 4 * KS_SIZE * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&K->ev[0], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&K->ev[1], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { delete K; JB_FAIL(ctx, JB_ERR_ALLOC, "jb_krylov_create: allocation failed"); }
+    *out = K;
+    return JB_OK;
+}
+int32_t jb_krylov_destroy(jb_krylov* K) {
+    if (K) {
+        if (K->h_flags) cudaFreeHost(K->h_flags);
+        if (K->ev[0]) cudaEventDestroy(K->ev[0]);
+        if (K->ev[1]) cudaEventDestroy(K->ev[1]);
+    }
+    delete K;
+    return JB_OK;
+}
+
+}  // extern "C"
+
+// Enqueue-only solve; the caller synchronises. Returns the status through *status_out after a
+// final sync inside (the flags have to be read anyway).
+int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double rtol, double atol, int itmax, int min_it, int side,
+                         int* iters, double* hist, int hist_cap, int* status_out) {
+    jb_csr* A = K->csr;
+    jb_ctx* ctx = A->ctx;
+    cudaStream_t st = ctx->stream;
+    const i64 m = K->m;
+    const int g = vec_grid(ctx, m);
+    jb_ilu* F = K->ilu;
+    const bool right = (side == 0 && F), left = (side == 1 && F);
+    if (itmax > K->hist_cap - 2) itmax = K->hist_cap - 2;
+    double* sc = K->d_sc.p;
+
+    double h_sc[KS_SIZE];
+    memset(h_sc, 0, sizeof(h_sc));
+    const bool manual = min_it > 1;
+    h_sc[KS_MANUAL] = manual ? 1.0 : 0.0;
+    h_sc[KS_ABS_TOL] = atol; h_sc[KS_REL_TOL] = rtol; h_sc[KS_MIN_IT] = (double)min_it;
+    h_sc[KS_ATOL] = manual ? 1e-20 : atol;
+    h_sc[KS_RTOL] = manual ? 1e-20 : rtol;
+    h_sc[KS_ITMAX] = (double)itmax;
+    memcpy(K->h_flags + 2 * KS_SIZE, h_sc, sizeof(h_sc));
+    JB_CUDA(ctx, cudaMemcpyAsync(sc, K->h_flags + 2 * KS_SIZE, sizeof(h_sc), cudaMemcpyHostToDevice, st));
+
+    const double* rin = d_b;
+    if (left) {
+        int rc = jb_launch_ilu_apply_sc(F, d_b, K->r.p, nullptr);
+        if (rc != JB_OK) return rc;
+        rin = K->r.p;
+    }
+    bicg_init_kernel<<<g, 256, 0, st>>>(m, d_b, rin, K->r.p, K->p.p, K->x.p, K->v.p, K->s.p, sc, K->d_hist.p, ctx->d_partials, ctx->d_counters);
+    JB_CHECK_LAUNCH(ctx);
+    JB_CUDA(ctx, cudaMemcpyAsync(K->h_flags, sc, KS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
+    JB_CUDA(ctx, cudaEventRecord(K->ev[0], st));
+
+    int enq = 0;
+    bool done = false;
+    // it = index of the iteration being enqueued; flags of iteration it-1 (slot (it) & 1) are awaited before enqueuing it+1
+    for (int it = 1; it <= itmax && !done; it++) {
+        // keep one iteration in flight ahead of the host: before enqueuing iteration `it`, make sure the
+        // flags written after iteration it-2 (same pinned slot this iteration will reuse) are not `done`.
+        if (it >= 2) {
+            const int slot_prev = it & 1;
+            JB_CUDA(ctx, cudaEventSynchronize(K->ev[slot_prev]));
+            if (K->h_flags[slot_prev * KS_SIZE + KS_DONE] != 0.0) { done = true; break; }
+        }
+        int rc;
+        const double* yv = K->p.p;
+        if (right) { rc = jb_launch_ilu_apply_sc(F, K->p.p, K->y.p, sc); if (rc != JB_OK) return rc; yv = K->y.p; }
+        if (!left) {
+            rc = jb_launch_spmv_dots(A, yv, K->v.p, JB_DOT_CV, d_b, sc);      // v = A y, alpha = rho/<c,v>
+            if (rc != JB_OK) return rc;
+        } else {
+            rc = jb_launch_spmv_dots(A, yv, K->q.p, JB_DOT_NONE, nullptr, nullptr); if (rc != JB_OK) return rc;
+            rc = jb_launch_ilu_apply_sc(F, K->q.p, K->v.p, sc); if (rc != JB_OK) return rc;
+            bicg_dot_kernel<JB_DOT_CV><<<g, 256, 0, st>>>(m, sc, K->v.p, d_b, ctx->d_partials, ctx->d_counters);
+            JB_CHECK_LAUNCH(ctx);
+        }
+        bicg_update1_kernel<<<g, 256, 0, st>>>(m, sc, K->r.p, K->v.p, yv, K->s.p, K->x.p);
+        JB_CHECK_LAUNCH(ctx);
+        const double* zv = K->s.p;
+        if (right) { rc = jb_launch_ilu_apply_sc(F, K->s.p, K->z.p, sc); if (rc != JB_OK) return rc; zv = K->z.p; }
+        if (!left) {
+            rc = jb_launch_spmv_dots(A, zv, K->t.p, JB_DOT_TS_TT, K->s.p, sc);  // t = A z, omega = <t,s>/<t,t>
+            if (rc != JB_OK) return rc;
+        } else {
+            rc = jb_launch_spmv_dots(A, zv, K->q.p, JB_DOT_NONE, nullptr, nullptr); if (rc != JB_OK) return rc;
+            rc = jb_launch_ilu_apply_sc(F, K->q.p, K->t.p, sc); if (rc != JB_OK) return rc;
+            bicg_dot_kernel<JB_DOT_TS_TT><<<g, 256, 0, st>>>(m, sc, K->t.p, K->s.p, ctx->d_partials, ctx->d_counters);
+            JB_CHECK_LAUNCH(ctx);
+        }
+        bicg_update2_kernel<<<g, 256, 0, st>>>(m, sc, K->s.p, K->t.p, zv, d_b, K->x.p, K->r.p, K->d_hist.p, K->hist_cap, ctx->d_partials,
+                                               ctx->d_counters);
+        JB_CHECK_LAUNCH(ctx);
+        bicg_update3_kernel<<<g, 256, 0, st>>>(m, sc, K->r.p, K->v.p, K->p.p);
+        JB_CHECK_LAUNCH(ctx);
+        const int slot = it & 1;
+        JB_CUDA(ctx, cudaMemcpyAsync(K->h_flags + slot * KS_SIZE, sc, KS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
+        JB_CUDA(ctx, cudaEventRecord(K->ev[slot], st));
+        enq = it;
+    }
+    (void)enq;
+    negate_kernel<<<g, 256, 0, st>>>(m, K->x.p, d_dx);   // dx = -x (update_dx_from_vector!)
+    JB_CHECK_LAUNCH(ctx);
+    JB_CUDA(ctx, cudaMemcpyAsync(K->h_flags + 3 * KS_SIZE, sc, KS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
+    JB_CUDA(ctx, cudaStreamSynchronize(st));
+    const double* f = K->h_flags + 3 * KS_SIZE;
+    const int niter = (int)f[KS_ITER];
+    if (iters) *iters = niter;
+    if (hist && hist_cap > 0) {
+        const int nh = std::min(hist_cap, niter + 1);
+        JB_CUDA(ctx, cudaMemcpy(hist, K->d_hist.p, nh * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    int status = (int)f[KS_STATUS];
+    if (f[KS_DONE] == 0.0) status = JB_NOT_CONVERGED;
+    *status_out = status;
+    return JB_OK;
+}
+
+extern "C" int32_t jb_krylov_solve(jb_krylov* K, const double* d_r, double* d_dx, double rtol, double atol, int32_t itmax, int32_t min_it,
+                                   int32_t side, int32_t* iters, double* hist, int32_t hist_cap) {
+    if (!K || !d_r || !d_dx || itmax < 0) return JB_ERR_ARG;
+    int status = 0;
+    int rc = jb_krylov_solve_impl(K, d_r, d_dx, rtol, atol, itmax, min_it, side, iters, hist, hist_cap, &status);
+    if (rc != JB_OK) return rc;
+    return status;
+}

@@ -1,0 +1,335 @@
+// Newton glue kernels (streaming, one pass each) and the two in-tree test systems.
+//   update_jutul_variable_internal!/choose_increment  src/variables/utils.jl:117-174
+//   unit_update_pairs!                                 src/variables/utils.jl:471-482
+//   increment_norm                                     src/models.jl:955-965
+//   convergence_criterion                              src/equations.jl:619-629
+//   apply_scaling_to_linearized_system!                src/linsolve/default.jl:325-385
+//   unit_diagonalize!                                  ext/JutulPartitionedArraysExt/linalg.jl:1-35
+//   SimpleHeatEquation                                 src/applications/test_systems/heat_2d/heat_2d.jl:7-49
+//   VariablePoissonEquation                            src/applications/test_systems/variable_poisson/variable_poisson.jl:90-133
+#include "jb_internal.cuh"
+#include "jb_reduce.cuh"
+
+__device__ __forceinline__ double sgn(double x) { return (double)((x > 0.0) - (x < 0.0)); }
+__device__ __forceinline__ double choose_increment(double v, double dv, double abs_max, double rel_max, double minv, double maxv, double scale) {
+    if (!isnan(scale)) dv = dv * scale;
+    if (!isnan(abs_max)) dv = sgn(dv) * fmin(fabs(dv), abs_max);
+    if (!isnan(rel_max)) dv = sgn(dv) * fmin(fabs(dv), rel_max * fabs(v));
+    if (!isnan(minv)) dv = fmax(dv, minv - v);
+    if (!isnan(maxv)) dv = fmin(dv, maxv - v);
+    return dv;
+}
+
+__global__ void __launch_bounds__(256) update_scalar_kernel(i64 n, double* __restrict__ v, const double* __restrict__ dx, i64 stride, double w,
+                                                            double abs_max, double rel_max, double minv, double maxv, double scale) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const double vi = v[i];
+        v[i] = vi + choose_increment(vi, w * __ldg(dx + i * stride), abs_max, rel_max, minv, maxv, scale);
+    }
+}
+__global__ void __launch_bounds__(256) update_pair_kernel(i64 n, double* __restrict__ s, const double* __restrict__ dx, i64 stride, double w,
+                                                          double abs_max, double minval, double maxval) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        double2 sv = reinterpret_cast<double2*>(s)[i];
+        const double dv = w * choose_increment(sv.x, __ldg(dx + i * stride), abs_max, NAN, minval, maxval, NAN);
+        sv.x += dv; sv.y -= dv;
+        reinterpret_cast<double2*>(s)[i] = sv;
+    }
+}
+__global__ void __launch_bounds__(256) increment_norm_kernel(i64 n, const double* __restrict__ dx, i64 stride, double* out, double* partials,
+                                                             unsigned int* counter) {
+    double a[1] = {0.0}, b[1] = {0.0};
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const double x = fabs(__ldg(dx + i * stride));
+        a[0] += x; b[0] = fmax(b[0], x);
+    }
+    // two reductions with different operators share the workspace through disjoint halves
+    grid_reduce<1, OpSum>(a, partials, counter, [=](double(&t)[1]) { out[0] = t[0]; });
+    grid_reduce<1, OpMax>(b, partials + JB_MAX_PARTIALS, counter + 1, [=](double(&t)[1]) { out[1] = t[0]; });
+}
+template <int BS>
+__global__ void __launch_bounds__(256) maxabs_rows_kernel(i64 n, const double* __restrict__ r, double* out, double* partials, unsigned int* counter) {
+    double m[BS];
+#pragma unroll
+    for (int e = 0; e < BS; e++) m[e] = 0.0;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int e = 0; e < BS; e++) {
+            const double x = fabs(__ldg(r + i * BS + e));
+            // NaN must surface as an error, not vanish in fmax
+            m[e] = (x != x) ? x : fmax(m[e], x);
+        }
+    }
+    grid_reduce<BS, OpMax>(m, partials, counter, [=](double(&t)[BS]) {
+#pragma unroll
+        for (int e = 0; e < BS; e++) out[e] = t[e];
+    });
+}
+
+__global__ void __launch_bounds__(256) scale_kernel(i64 n, double a, double* __restrict__ x) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) x[i] *= a;
+}
+template <int BS>
+__global__ void __launch_bounds__(256) scale_diag_kernel(i64 n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ diag,
+                                                         double* __restrict__ val, double* __restrict__ r) {
+    constexpr int B2 = BS * BS;
+    for (i64 row = (i64)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (i64)gridDim.x * blockDim.x) {
+        double D[B2], Di[B2], a[B2], o[B2], rv[BS], ro[BS];
+        const int32_t dp = __ldg(diag + row);
+#pragma unroll
+        for (int q = 0; q < B2; q++) D[q] = val[(size_t)dp * B2 + q];
+        blk_inv<BS>(D, Di);
+        for (int32_t k = __ldg(rowptr + row); k < __ldg(rowptr + row + 1); k++) {
+#pragma unroll
+            for (int q = 0; q < B2; q++) a[q] = val[(size_t)k * B2 + q];
+            blk_mul<BS>(Di, a, o);
+#pragma unroll
+            for (int q = 0; q < B2; q++) val[(size_t)k * B2 + q] = o[q];
+        }
+#pragma unroll
+        for (int e = 0; e < BS; e++) rv[e] = r[row * BS + e];
+        blk_mulvec<BS>(Di, rv, ro);
+#pragma unroll
+        for (int e = 0; e < BS; e++) r[row * BS + e] = ro[e];
+    }
+}
+template <int BS>
+__global__ void __launch_bounds__(256) unit_diag_kernel(i64 n_owned, i64 n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                        double* __restrict__ val, double* __restrict__ r) {
+    constexpr int B2 = BS * BS;
+    for (i64 row = n_owned + (i64)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (i64)gridDim.x * blockDim.x) {
+        for (int32_t k = __ldg(rowptr + row); k < __ldg(rowptr + row + 1); k++) {
+            const bool dg = __ldg(colidx + k) == row;
+#pragma unroll
+            for (int q = 0; q < B2; q++) val[(size_t)k * B2 + q] = (dg && (q % (BS + 1) == 0)) ? -1.0 : 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < BS; e++) r[row * BS + e] = 0.0;
+    }
+}
+
+// ---- heat: one thread per cell writes its 5-entry row and residual ----
+__global__ void __launch_bounds__(256) heat_assemble_kernel(i64 nx, i64 ny, double hx, double hy, double dt, const double* __restrict__ T,
+                                                            const double* __restrict__ T0, const int32_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ colidx, double* __restrict__ nz, double* __restrict__ r) {
+    const i64 nc = nx * ny;
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (i64)gridDim.x * blockDim.x) {
+        const i64 i = c % nx, j = c / nx;
+        const i64 L = j * nx + (i == 0 ? nx - 1 : i - 1), R = j * nx + (i == nx - 1 ? 0 : i + 1);
+        const i64 U = (j == 0 ? ny - 1 : j - 1) * nx + i, D = (j == ny - 1 ? 0 : j + 1) * nx + i;
+        const double Tc = __ldg(T + c);
+        const double dtt = (Tc - __ldg(T0 + c)) / dt;
+        const double d2x = (__ldg(T + L) - 2 * Tc + __ldg(T + R)) / (hx * hx);
+        const double d2y = (__ldg(T + U) - 2 * Tc + __ldg(T + D)) / (hy * hy);
+        r[c] = dtt - (d2x + d2y);
+        const double cx = -(1.0 / (hx * hx)), cy = -(1.0 / (hy * hy));
+        const double cd = 1.0 / dt - ((-2.0) / (hx * hx) + (-2.0) / (hy * hy));
+        for (int32_t k = __ldg(rowptr + c); k < __ldg(rowptr + c + 1); k++) {
+            const i64 col = __ldg(colidx + k);
+            double v = 0.0;   // aliasing neighbours on tiny periodic grids accumulate
+            if (col == c) v += cd;
+            if (col == L) v += cx;
+            if (col == R) v += cx;
+            if (col == U) v += cy;
+            if (col == D) v += cy;
+            nz[k] = v;
+        }
+    }
+}
+
+// ---- Poisson: row-owner over the half-face map ----
+__global__ void __launch_bounds__(256) poisson_assemble_kernel(i64 nc, const int32_t* __restrict__ hf_pos, const int32_t* __restrict__ hf_other,
+                                                               const int32_t* __restrict__ hf_face, const int32_t* __restrict__ hf_rowpos,
+                                                               const int32_t* __restrict__ diag, const double* __restrict__ K,
+                                                               const double* __restrict__ U, const double* __restrict__ U0, int time_dependent,
+                                                               double dt, const double* __restrict__ src, double* __restrict__ nz,
+                                                               double* __restrict__ r) {
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (i64)gridDim.x * blockDim.x) {
+        const double Uc = __ldg(U + c);
+        double val = 0.0, dself = 0.0, div = 0.0, ddiv = 0.0;
+        if (time_dependent) { val = (Uc - __ldg(U0 + c)) / dt; dself = 1.0 / dt; }
+        // zero the row first: several half-faces may connect the same pair of cells
+        for (int32_t i = __ldg(hf_pos + c); i < __ldg(hf_pos + c + 1); i++) nz[__ldg(hf_rowpos + i)] = 0.0;
+        for (int32_t i = __ldg(hf_pos + c); i < __ldg(hf_pos + c + 1); i++) {
+            const double Kf = __ldg(K + __ldg(hf_face + i));
+            const double q = -Kf * (__ldg(U + __ldg(hf_other + i)) - Uc);
+            div = div + q; ddiv = ddiv + Kf;
+            nz[__ldg(hf_rowpos + i)] += -Kf;
+        }
+        val = time_dependent ? val + div : div;
+        dself += ddiv;
+        if (!time_dependent && c == 0) { val = val + 1e-10 * Uc; dself += 1e-10; }
+        if (src) val += __ldg(src + c);
+        r[c] = val;
+        nz[__ldg(diag + c)] = dself;
+    }
+}
+__global__ void scatter_scalar_sources_kernel(i64 nsrc, const int32_t* __restrict__ cells, const double* __restrict__ vals, double* __restrict__ src) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) for (i64 k = 0; k < nsrc; k++) src[cells[k]] += vals[k];
+}
+
+static int sgrid(jb_ctx* ctx, i64 n) {
+    i64 want = (n + 255) / 256;
+    i64 cap = std::min<i64>((i64)ctx->sm_count * 8, JB_MAX_PARTIALS);
+    return (int)std::max<i64>(1, std::min(want, cap));
+}
+
+int jb_launch_update_scalar(jb_ctx* ctx, double* d_v, const double* d_dx, i64 stride, i64 n, double w, double abs_max, double rel_max,
+                            double minv, double maxv, double scale) {
+    update_scalar_kernel<<<sgrid(ctx, n), 256, 0, ctx->stream>>>(n, d_v, d_dx, stride, w, abs_max, rel_max, minv, maxv, scale);
+    JB_CHECK_LAUNCH(ctx);
+    return JB_OK;
+}
+int jb_launch_update_pair(jb_ctx* ctx, double* d_s, const double* d_dx, i64 stride, i64 n, double w, double abs_max, double minval, double maxval) {
+    // unit_sum_update! (src/variables/utils.jl:393-413): maxval - nf*minval, then unit_update_pairs! clamps
+    maxval = maxval - 2 * minval;
+    maxval = fmin(1 - minval, maxval);
+    minval = fmax(minval, maxval - 1);
+    update_pair_kernel<<<sgrid(ctx, n), 256, 0, ctx->stream>>>(n, d_s, d_dx, stride, w, abs_max, minval, maxval);
+    JB_CHECK_LAUNCH(ctx);
+    return JB_OK;
+}
+int jb_launch_maxabs_rows(jb_ctx* ctx, const double* d_r, int bs, i64 n, double* d_out) {
+    const int g = sgrid(ctx, n);
+    switch (bs) {
+        case 1: maxabs_rows_kernel<1><<<g, 256, 0, ctx->stream>>>(n, d_r, d_out, ctx->d_partials, ctx->d_counters); break;
+        case 2: maxabs_rows_kernel<2><<<g, 256, 0, ctx->stream>>>(n, d_r, d_out, ctx->d_partials, ctx->d_counters); break;
+        case 3: maxabs_rows_kernel<3><<<g, 256, 0, ctx->stream>>>(n, d_r, d_out, ctx->d_partials, ctx->d_counters); break;
+        case 4: maxabs_rows_kernel<4><<<g, 256, 0, ctx->stream>>>(n, d_r, d_out, ctx->d_partials, ctx->d_counters); break;
+        default: return JB_ERR_UNSUPPORTED;
+    }
+    JB_CHECK_LAUNCH(ctx);
+    return JB_OK;
+}
+
+extern "C" {
+
+int32_t jb_update_scalar(jb_ctx* ctx, double* d_v, const double* d_dx, int64_t dx_stride, int64_t n, double w, double abs_max, double rel_max,
+                         double minv, double maxv, double scale) {
+    if (!ctx || !d_v || !d_dx || n < 0 || dx_stride < 1) return JB_ERR_ARG;
+    if (n == 0) return JB_OK;
+    int rc = jb_launch_update_scalar(ctx, d_v, d_dx, dx_stride, n, w, abs_max, rel_max, minv, maxv, scale);
+    if (rc != JB_OK) return rc;
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+int32_t jb_update_fraction_pair(jb_ctx* ctx, double* d_s, const double* d_dx, int64_t dx_stride, int64_t n, double w, double abs_max,
+                                double minval, double maxval) {
+    if (!ctx || !d_s || !d_dx || n < 0 || dx_stride < 1) return JB_ERR_ARG;
+    if (n == 0) return JB_OK;
+    int rc = jb_launch_update_pair(ctx, d_s, d_dx, dx_stride, n, w, abs_max, minval, maxval);
+    if (rc != JB_OK) return rc;
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+int32_t jb_increment_norm(jb_ctx* ctx, const double* d_dx, int64_t stride, int64_t n, double* sum_abs, double* max_abs) {
+    if (!ctx || !d_dx || n < 0 || stride < 1) return JB_ERR_ARG;
+    if (n == 0) { if (sum_abs) *sum_abs = 0; if (max_abs) *max_abs = 0; return JB_OK; }
+    increment_norm_kernel<<<sgrid(ctx, n), 256, 0, ctx->stream>>>(n, d_dx, stride, ctx->d_scalars, ctx->d_partials, ctx->d_counters);
+    JB_CHECK_LAUNCH(ctx);
+    JB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scalars, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (sum_abs) *sum_abs = ctx->h_pinned[0];
+    if (max_abs) *max_abs = ctx->h_pinned[1];
+    return JB_OK;
+}
+int32_t jb_maxabs_rows(jb_ctx* ctx, const double* d_r, int32_t bs, int64_t n, double* out) {
+    if (!ctx || !d_r || !out || n < 0 || bs < 1 || bs > 4) return JB_ERR_ARG;
+    if (n == 0) { for (int e = 0; e < bs; e++) out[e] = 0; return JB_OK; }
+    int rc = jb_launch_maxabs_rows(ctx, d_r, bs, n, ctx->d_scalars);
+    if (rc != JB_OK) return rc;
+    JB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_scalars, bs * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int e = 0; e < bs; e++) out[e] = ctx->h_pinned[e];
+    return JB_OK;
+}
+
+int32_t jb_scale_system(jb_csr* A, double* d_r, int32_t kind, double dt) {
+    if (!A || !d_r) return JB_ERR_ARG;
+    jb_ctx* ctx = A->ctx;
+    if (kind == 0) return JB_OK;
+    if (kind == 2) {
+        const i64 nv = A->nnzb * A->bs * A->bs, nr = A->n * A->bs;
+        scale_kernel<<<sgrid(ctx, nv), 256, 0, ctx->stream>>>(nv, dt, A->d_val.p); JB_CHECK_LAUNCH(ctx);
+        scale_kernel<<<sgrid(ctx, nr), 256, 0, ctx->stream>>>(nr, dt, d_r); JB_CHECK_LAUNCH(ctx);
+    } else if (kind == 1) {
+        const int g = sgrid(ctx, A->n);
+        switch (A->bs) {
+            case 1: scale_diag_kernel<1><<<g, 256, 0, ctx->stream>>>(A->n, A->d_rowptr.p, A->d_diag.p, A->d_val.p, d_r); break;
+            case 2: scale_diag_kernel<2><<<g, 256, 0, ctx->stream>>>(A->n, A->d_rowptr.p, A->d_diag.p, A->d_val.p, d_r); break;
+            case 3: scale_diag_kernel<3><<<g, 256, 0, ctx->stream>>>(A->n, A->d_rowptr.p, A->d_diag.p, A->d_val.p, d_r); break;
+            case 4: scale_diag_kernel<4><<<g, 256, 0, ctx->stream>>>(A->n, A->d_rowptr.p, A->d_diag.p, A->d_val.p, d_r); break;
+        }
+        JB_CHECK_LAUNCH(ctx);
+    } else return JB_ERR_ARG;
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+
+int32_t jb_unit_diagonalize_ghosts(jb_csr* A, double* d_r, int64_t n_owned) {
+    if (!A || !d_r || n_owned < 0 || n_owned > A->n) return JB_ERR_ARG;
+    jb_ctx* ctx = A->ctx;
+    const i64 ng = A->n - n_owned;
+    if (ng == 0) return JB_OK;
+    const int g = sgrid(ctx, ng);
+    switch (A->bs) {
+        case 1: unit_diag_kernel<1><<<g, 256, 0, ctx->stream>>>(n_owned, A->n, A->d_rowptr.p, A->d_colidx.p, A->d_val.p, d_r); break;
+        case 2: unit_diag_kernel<2><<<g, 256, 0, ctx->stream>>>(n_owned, A->n, A->d_rowptr.p, A->d_colidx.p, A->d_val.p, d_r); break;
+        case 3: unit_diag_kernel<3><<<g, 256, 0, ctx->stream>>>(n_owned, A->n, A->d_rowptr.p, A->d_colidx.p, A->d_val.p, d_r); break;
+        case 4: unit_diag_kernel<4><<<g, 256, 0, ctx->stream>>>(n_owned, A->n, A->d_rowptr.p, A->d_colidx.p, A->d_val.p, d_r); break;
+    }
+    JB_CHECK_LAUNCH(ctx);
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+
+int32_t jb_heat_pattern(jb_ctx* ctx, int64_t nx, int64_t ny, jb_csr** out) {
+    if (!ctx || !out || nx < 1 || ny < 1) return JB_ERR_ARG;
+    const i64 nc = nx * ny;
+    std::vector<int64_t> I(5 * nc), J(5 * nc);
+    i64 k = 0;
+    for (i64 c = 0; c < nc; c++) {
+        const i64 i = c % nx, j = c / nx;
+        const i64 nb[5] = {c, j * nx + (i == 0 ? nx - 1 : i - 1), j * nx + (i == nx - 1 ? 0 : i + 1), (j == 0 ? ny - 1 : j - 1) * nx + i,
+                           (j == ny - 1 ? 0 : j + 1) * nx + i};
+        for (int w = 0; w < 5; w++) { I[k] = c + 1; J[k++] = nb[w] + 1; }
+    }
+    return jb_csr_create_from_coo(ctx, I.data(), J.data(), 5 * nc, nc, 1, out);
+}
+int32_t jb_heat_assemble(jb_csr* A, int64_t nx, int64_t ny, double hx, double hy, double dt, const double* d_T, const double* d_T0, double* d_r) {
+    if (!A || !d_T || !d_T0 || !d_r || A->bs != 1 || A->n != nx * ny || !(dt > 0)) return JB_ERR_ARG;
+    jb_ctx* ctx = A->ctx;
+    heat_assemble_kernel<<<sgrid(ctx, A->n), 256, 0, ctx->stream>>>(nx, ny, hx, hy, dt, d_T, d_T0, A->d_rowptr.p, A->d_colidx.p, A->d_val.p, d_r);
+    JB_CHECK_LAUNCH(ctx);
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+int32_t jb_poisson_assemble(jb_tpfa* t, const double* d_K, const double* d_U, const double* d_U0, int32_t time_dependent, double dt,
+                            int64_t nsrc, const int64_t* src_cells, const double* src_vals, double* d_r) {
+    if (!t || !d_K || !d_U || !d_r || t->csr->bs != 1 || (time_dependent && (!d_U0 || !(dt > 0)))) return JB_ERR_ARG;
+    jb_ctx* ctx = t->mesh->ctx;
+    const i64 nc = t->mesh->nc;
+    DBuf<double> src, sv;
+    DBuf<int32_t> scell;
+    if (nsrc > 0) {
+        std::vector<int32_t> hc(nsrc);
+        for (i64 k = 0; k < nsrc; k++) {
+            if (src_cells[k] < 1 || src_cells[k] > nc) JB_FAIL(ctx, JB_ERR_ARG, "jb_poisson_assemble: source cell out of range");
+            hc[k] = (int32_t)(src_cells[k] - 1);
+        }
+        std::vector<double> hv(src_vals, src_vals + nsrc);
+        if (src.alloc(nc) != cudaSuccess || scell.upload(hc, ctx->stream) != cudaSuccess || sv.upload(hv, ctx->stream) != cudaSuccess)
+            JB_FAIL(ctx, JB_ERR_ALLOC, "jb_poisson_assemble: allocation failed");
+        JB_CUDA(ctx, cudaMemsetAsync(src.p, 0, nc * sizeof(double), ctx->stream));
+        scatter_scalar_sources_kernel<<<1, 32, 0, ctx->stream>>>(nsrc, scell.p, sv.p, src.p);
+        JB_CHECK_LAUNCH(ctx);
+    }
+    poisson_assemble_kernel<<<sgrid(ctx, nc), 256, 0, ctx->stream>>>(nc, t->mesh->d_hf_pos.p, t->mesh->d_hf_other.p, t->mesh->d_hf_face.p,
+                                                                     t->d_hf_rowpos.p, t->csr->d_diag.p, d_K, d_U, d_U0, time_dependent, dt,
+                                                                     nsrc > 0 ? src.p : nullptr, t->csr->d_val.p, d_r);
+    JB_CHECK_LAUNCH(ctx);
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+// Block-CSR SpMV for sm_100a: y = alpha*A*x + beta*y  (csr_mul_add!,
+// src/StaticCSR/mat.jl:41-61; block_mul! src/linsolve/block_cpu.jl:1-9).
+//
+// HBM-bound: per row the kernel streams the row's blocks (8*bs^2 B each) and
+// column indices (4 B) once, gathers x blocks (L2-resident for local numberings)
+// and writes y. LPR lanes cooperate on a row so that a warp's loads of colidx /
+// values cover contiguous memory (4 rows x ~7 blocks x 32 B for bs = 2); the
+// partial sums are combined with LPR-wide shuffles. Optionally the Krylov dot
+// products that consume y are fused in (<c,y>, or <y,u> and <y,y>), reduced
+// deterministically (jb_reduce.cuh) and turned into alpha / omega by the last CTA.
+#include "jb_internal.cuh"
+#include "jb_krylov_scalars.cuh"
+#include "jb_reduce.cuh"
+
+template <int BS> struct BlockLoad;
+template <> struct BlockLoad<1> {
+    __device__ static void mat(const double* __restrict__ v, size_t k, double (&a)[1]) { a[0] = __ldg(v + k); }
+    __device__ static void vec(const double* __restrict__ x, int c, double (&o)[1]) { o[0] = __ldg(x + c); }
+};
+template <> struct BlockLoad<2> {
+    __device__ static void mat(const double* __restrict__ v, size_t k, double (&a)[4]) {
+        const double2* p = reinterpret_cast<const double2*>(v + 4 * k);
+        double2 a0 = __ldg(p), a1 = __ldg(p + 1);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y;
+    }
+    __device__ static void vec(const double* __restrict__ x, int c, double (&o)[2]) {
+        double2 t = __ldg(reinterpret_cast<const double2*>(x) + c);
+        o[0] = t.x; o[1] = t.y;
+    }
+};
+template <int BS> struct BlockLoadN {
+    __device__ static void mat(const double* __restrict__ v, size_t k, double (&a)[BS * BS]) {
+#pragma unroll
+        for (int i = 0; i < BS * BS; i++) a[i] = __ldg(v + k * BS * BS + i);
+    }
+    __device__ static void vec(const double* __restrict__ x, int c, double (&o)[BS]) {
+#pragma unroll
+        for (int i = 0; i < BS; i++) o[i] = __ldg(x + (size_t)c * BS + i);
+    }
+};
+template <> struct BlockLoad<3> : BlockLoadN<3> {};
+template <> struct BlockLoad<4> : BlockLoadN<4> {};
+
+template <int BS, int LPR, int MODE>
+__global__ void __launch_bounds__(256) spmv_kernel(i64 n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                                   const double* __restrict__ val, const double* __restrict__ x,
+                                                   double* __restrict__ y, double alpha, double beta,
+                                                   const double* __restrict__ u, double* sc, double* partials,
+                                                   unsigned int* counter) {
+    if (MODE != JB_DOT_NONE) {
+        if (sc[KS_DONE] != 0.0) return;
+    }
+    const int lane = threadIdx.x % LPR;
+    constexpr int ROWS_PER_WARP = 32 / LPR;
+    const i64 warps_per_cta = blockDim.x >> 5;
+    const i64 stride = (i64)gridDim.x * warps_per_cta * ROWS_PER_WARP;
+    double d0 = 0.0, d1 = 0.0;
+    // warp-uniform loop bound: every lane of a warp takes part in the shuffles
+    for (i64 base = ((i64)blockIdx.x * warps_per_cta + (threadIdx.x >> 5)) * ROWS_PER_WARP; base < n; base += stride) {
+        const i64 row = base + (threadIdx.x & 31) / LPR;
+        const bool live = row < n;
+        double acc[BS];
+#pragma unroll
+        for (int e = 0; e < BS; e++) acc[e] = 0.0;
+        if (live) {
+            const int32_t k0 = __ldg(rowptr + row), k1 = __ldg(rowptr + row + 1);
+            for (int32_t k = k0 + lane; k < k1; k += LPR) {
+                const int32_t c = __ldg(colidx + k);
+                double a[BS * BS], xv[BS];
+                BlockLoad<BS>::mat(val, (size_t)k, a);
+                BlockLoad<BS>::vec(x, c, xv);
+#pragma unroll
+                for (int p = 0; p < BS; p++)
+#pragma unroll
+                    for (int e = 0; e < BS; e++) acc[e] = fma(a[p * BS + e], xv[p], acc[e]);
+            }
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+            for (int e = 0; e < BS; e++) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+        if (live && lane == 0) {
+#pragma unroll
+            for (int e = 0; e < BS; e++) {
+                double v = alpha * acc[e];
+                if (beta != 0.0) v += beta * y[row * BS + e];
+                y[row * BS + e] = v;
+                if (MODE == JB_DOT_CV) d0 = fma(__ldg(u + row * BS + e), v, d0);
+                if (MODE == JB_DOT_TS_TT) { d0 = fma(v, __ldg(u + row * BS + e), d0); d1 = fma(v, v, d1); }
+            }
+        }
+    }
+    if (MODE == JB_DOT_CV) {
+        double r[1] = {d0};
+        grid_reduce<1, OpSum>(r, partials, counter, [=](double(&t)[1]) {
+            sc[KS_ALPHA] = sc[KS_RHO] / t[0];   // alpha_k = rho_k / <c, v_k>
+        });
+    } else if (MODE == JB_DOT_TS_TT) {
+        double r[2] = {d0, d1};
+        grid_reduce<2, OpSum>(r, partials, counter, [=](double(&t)[2]) {
+            sc[KS_OMEGA] = t[0] / t[1];         // omega_k = <t,s>/<t,t>
+        });
+    }
+}
+
+template <int BS, int LPR, int MODE>
+static int launch_spmv_t(jb_csr* A, double alpha, const double* x, double beta, double* y, const double* u, double* sc) {
+    jb_ctx* ctx = A->ctx;
+    const int threads = 256;
+    const i64 rows_per_cta = threads / LPR;
+    i64 want = (A->n + rows_per_cta - 1) / rows_per_cta;
+    i64 cap = (MODE == JB_DOT_NONE) ? want : (i64)ctx->sm_count * 8;   // fused dots: bounded grid for the partials buffer
+    if (cap > JB_MAX_PARTIALS && MODE != JB_DOT_NONE) cap = JB_MAX_PARTIALS;
+    int grid = (int)std::max<i64>(1, std::min(want, cap));
+    spmv_kernel<BS, LPR, MODE><<<grid, threads, 0, ctx->stream>>>(A->n, A->d_rowptr.p, A->d_colidx.p, A->d_val.p, x, y, alpha, beta, u,
+                                                                  sc, ctx->d_partials, ctx->d_counters);
+    JB_CHECK_LAUNCH(ctx);
+    return JB_OK;
+}
+
+template <int MODE>
+static int launch_spmv_mode(jb_csr* A, double alpha, const double* x, double beta, double* y, const double* u, double* sc) {
+    // lanes per row from the average row length (7 for a hex-like TPFA stencil)
+    const double avg = (double)A->nnzb / (double)A->n;
+    const int lpr = avg <= 2.5 ? 2 : (avg <= 5.0 ? 4 : (avg <= 12.0 ? 8 : 16));
+#define JB_SPMV_CASE(BS)                                                                   \
+    case BS:                                                                               \
+        if (lpr == 2) return launch_spmv_t<BS, 2, MODE>(A, alpha, x, beta, y, u, sc);      \
+        if (lpr == 4) return launch_spmv_t<BS, 4, MODE>(A, alpha, x, beta, y, u, sc);      \
+        if (lpr == 8) return launch_spmv_t<BS, 8, MODE>(A, alpha, x, beta, y, u, sc);      \
+        return launch_spmv_t<BS, 16, MODE>(A, alpha, x, beta, y, u, sc);
+    switch (A->bs) {
+        JB_SPMV_CASE(1)
+        JB_SPMV_CASE(2)
+        JB_SPMV_CASE(3)
+        JB_SPMV_CASE(4)
+    }
+#undef JB_SPMV_CASE
+    return JB_ERR_UNSUPPORTED;
+}
+
+int jb_launch_spmv(jb_csr* A, double alpha, const double* d_x, double beta, double* d_y) {
+    return launch_spmv_mode<JB_DOT_NONE>(A, alpha, d_x, beta, d_y, nullptr, nullptr);
+}
+int jb_launch_spmv_dots(jb_csr* A, const double* d_x, double* d_y, int mode, const double* d_u, double* d_sc) {
+    if (mode == JB_DOT_CV) return launch_spmv_mode<JB_DOT_CV>(A, 1.0, d_x, 0.0, d_y, d_u, d_sc);
+    if (mode == JB_DOT_TS_TT) return launch_spmv_mode<JB_DOT_TS_TT>(A, 1.0, d_x, 0.0, d_y, d_u, d_sc);
+    return launch_spmv_mode<JB_DOT_NONE>(A, 1.0, d_x, 0.0, d_y, nullptr, nullptr);
+}
+
+extern "C" int32_t jb_spmv(jb_csr* A, double alpha, const double* d_x, double beta, double* d_y) {
+    if (!A || !d_x || !d_y) return JB_ERR_ARG;
+    int rc = jb_launch_spmv(A, alpha, d_x, beta, d_y);
+    if (rc != JB_OK) return rc;
+    JB_CUDA(A->ctx, cudaStreamSynchronize(A->ctx->stream));
+    return JB_OK;
+}

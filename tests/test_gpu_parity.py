@@ -1,0 +1,388 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Tolerances (FP64): integer/index work bit-exact; assembly |dJ|,|dr| <= 1e-11 * scale (exp and FMA
+contraction differ in the last bits, accumulation cancels); SpMV 1e-13 relative to the row scale;
+ILU factors 1e-10 relative to the factor scale; Krylov: same iteration count +-1 and
+|x_gpu - x_cpu| <= 10 * rtol * |x|."""
+import numpy as np
+import pytest
+
+from conftest import oracle_system, to_scipy
+
+pytestmark = pytest.mark.gpu
+
+MESHES = [((3, 1, 1), False), ((4, 3, 1), False), ((6, 5, 4), False), ((6, 5, 4), True), ((13, 11, 7), True)]
+
+
+def _setup(J, O, ctx, dims, permute, seed=None):
+    kw = {} if seed is None else {"seed": seed}
+    w = J.workloads.unstructured_hex(*dims, permute=permute, **kw)
+    s = oracle_system(O, w)
+    return w, s
+
+
+@pytest.mark.parametrize("dims,permute", MESHES)
+def test_topology_pattern_alignment_bit_exact(J, O, ctx, dims, permute):
+    w, s = _setup(J, O, ctx, dims, permute)
+    disc = J.TwoPointPotentialFlowHardCoded(ctx, w["N"], w["nc"])
+    hf = disc.half_face_map()
+    for k in ("faces", "face_pos", "cells", "face_sign"):
+        assert np.array_equal(hf[k], s["hf"][k]), k
+    for bs in (1, 2):
+        jac = J.tpfa_jacobian(disc, bs)
+        rowptr, colidx = jac.pattern()
+        assert np.array_equal(rowptr, s["rowptr"]) and np.array_equal(colidx, s["colidx"])
+        st = J.ConservationLawTPFAStorage(disc, jac)
+        d, h = st.jacobian_positions()
+        assert np.array_equal(d, s["diag_pos"]) and np.array_equal(h, s["hf_pos"])
+    # build_sparse_matrix from the COO triplets gives the same canonical pattern (duplicates merged)
+    I, Jc = O.tpfa_pattern(s["hf"])
+    I2 = np.concatenate([I, I[:5]]); J2 = np.concatenate([Jc, Jc[:5]])
+    jac2 = J.build_sparse_matrix(ctx, I2, J2, w["nc"], 2)
+    rowptr, colidx = jac2.pattern()
+    assert np.array_equal(rowptr, s["rowptr"]) and np.array_equal(colidx, s["colidx"])
+
+
+def _assemble_both(J, O, ctx, w, s, variant="cells", sources=True, perturb=1e-3):
+    sim = J.TwoPhaseSimulator(ctx, w["N"], w["nc"], w["Tf"], w["gdz"], w["pv"], w["params"])
+    if sources:
+        sim.set_forces(w["src_cells"], w["src_vals"])
+    sim.set_state(w["p0"], w["sw0"])
+    M0 = O.mass_2ph(w["pv"], w["params"], w["p0"], w["sw0"])
+    assert np.allclose(sim.M0.get(), M0, rtol=1e-14)
+    rng = np.random.default_rng(11)
+    p = w["p0"] * (1 + perturb * rng.standard_normal(w["nc"]))
+    sw = np.clip(w["sw0"] + 0.05 * rng.standard_normal(w["nc"]), 0.0, 1.0)
+    s2 = np.stack([sw, 1 - sw], axis=1).ravel()
+    sim.p.set(p); sim.s.set(s2)
+    sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r, variant=variant)
+    nz, r = O.assemble_2ph(s["hf"], s["diag_pos"], s["hf_pos"], w["Tf"], w["gdz"], w["pv"], w["params"], p, sw, M0, w["dt"],
+                           s["colidx"].shape[0], w["src_cells"] if sources else None, w["src_vals"] if sources else None)
+    return sim, nz, r, p, sw, M0
+
+
+@pytest.mark.parametrize("dims,permute", MESHES)
+@pytest.mark.parametrize("variant", ["cells", "faces"])
+def test_twophase_assembly_matches_oracle(J, O, ctx, dims, permute, variant):
+    w, s = _setup(J, O, ctx, dims, permute)
+    sim, nz, r, p, sw, M0 = _assemble_both(J, O, ctx, w, s, variant)
+    nz_g, r_g = sim.jac.nonzeros(), sim.r.get()
+    # scale per block row: the diagonal block magnitude bounds the cancellation in that row
+    assert np.abs(r_g - r).max() <= 1e-11 * max(np.abs(r).max(), 1e-30)
+    nb = s["colidx"].shape[0]
+    rowscale = np.repeat(np.abs(nz.reshape(nb, 4)).max(axis=1), 4)
+    rows = np.repeat(np.arange(w["nc"]), np.diff(s["rowptr"]))
+    rs = np.zeros(w["nc"]); np.maximum.at(rs, rows, np.abs(nz.reshape(nb, 4)).max(axis=1))
+    tol = 1e-11 * np.repeat(rs[rows], 4)
+    assert np.all(np.abs(nz_g - nz) <= tol + 1e-300)
+
+
+def test_twophase_residual_hook_and_no_sources(J, O, ctx):
+    w, s = _setup(J, O, ctx, (6, 5, 4), True)
+    sim, nz, r, p, sw, M0 = _assemble_both(J, O, ctx, w, s, "cells", sources=False)
+    r_asm = sim.r.get()
+    sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r, variant="residual")
+    assert np.array_equal(sim.r.get(), r_asm)      # float-only residual == AD-assembly residual (helper.jl:3-18)
+    assert np.abs(r_asm - r).max() <= 1e-11 * np.abs(r).max()
+
+
+def test_assembly_deterministic(J, O, ctx):
+    w, s = _setup(J, O, ctx, (13, 11, 7), True)
+    sim, *_ = _assemble_both(J, O, ctx, w, s)
+    a, b = sim.jac.nonzeros(), sim.r.get()
+    sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r)
+    assert np.array_equal(a, sim.jac.nonzeros()) and np.array_equal(b, sim.r.get())
+
+
+@pytest.mark.parametrize("bs", [1, 2, 3])
+def test_spmv_matches_oracle(J, O, ctx, bs):
+    w, s = _setup(J, O, ctx, (9, 8, 5), True)
+    n = w["nc"]
+    disc = J.TwoPointPotentialFlowHardCoded(ctx, w["N"], n)
+    jac = J.tpfa_jacobian(disc, bs)
+    rng = np.random.default_rng(bs)
+    nz = rng.standard_normal(jac.nnz * bs * bs)
+    jac.set_nonzeros(nz)
+    x = rng.standard_normal(n * bs); y0 = rng.standard_normal(n * bs)
+    dx, dy = ctx.transfer(x), ctx.transfer(y0)
+    jac.mul(dy, dx)
+    ref = O.spmv(n, bs, s["rowptr"], s["colidx"], nz, x)
+    absA = O.spmv(n, bs, s["rowptr"], s["colidx"], np.abs(nz), np.abs(x))
+    assert np.all(np.abs(dy.get() - ref) <= 1e-13 * absA + 1e-300)
+    dy.set(y0)
+    jac.mul(dy, dx, alpha=-2.0, beta=0.5)
+    ref2 = O.spmv(n, bs, s["rowptr"], s["colidx"], nz, x, alpha=-2.0, beta=0.5, y=y0.copy())
+    assert np.all(np.abs(dy.get() - ref2) <= 1e-13 * (2 * absA + np.abs(y0)) + 1e-300)
+
+
+def _jacobian_on_gpu(J, O, ctx, dims=(9, 8, 5), permute=True):
+    w, s = _setup(J, O, ctx, dims, permute)
+    sim, nz, r, p, sw, M0 = _assemble_both(J, O, ctx, w, s)
+    return w, s, sim, nz, r
+
+
+@pytest.mark.parametrize("nparts", [None, 3, 16])
+@pytest.mark.parametrize("permute", [False, True])
+def test_ilu0_factor_and_apply_match_oracle(J, O, ctx, nparts, permute):
+    w, s, sim, nz, r = _jacobian_on_gpu(J, O, ctx, permute=permute)
+    n = w["nc"]
+    nz = sim.jac.nonzeros()      # factor exactly what the GPU holds
+    part = None if nparts is None else np.random.default_rng(nparts).integers(1, nparts + 1, n)
+    ilu_g = J.ILUZeroPreconditioner(sim.jac, part)
+    assert ilu_g.update_preconditioner() == 0
+    ilu_o = O.ILU0(n, 2, s["rowptr"], s["colidx"], part)
+    assert ilu_o.factor(nz) == 0
+    fg, fo = ilu_g.factors(), ilu_o.get()
+    for k in ("Lptr", "Lcol", "Uptr", "Ucol"):
+        assert np.array_equal(fg[k], fo[k]), k
+    for k in ("L", "U", "D"):
+        scale = np.abs(fo[k]).max() if fo[k].size else 1.0
+        assert np.abs(fg[k] - fo[k]).max() <= 1e-10 * scale, k
+    b = np.random.default_rng(2).standard_normal(2 * n)
+    db, dx = ctx.transfer(b), ctx.zeros(2 * n)
+    ilu_g.apply(dx, db)
+    xo = ilu_o.solve(b)
+    assert np.abs(dx.get() - xo).max() <= 1e-9 * np.abs(xo).max()
+    info = ilu_g.info()
+    assert info["nnz_l"] == fo["Lcol"].shape[0] and info["forward_levels"] >= 1
+
+
+def test_ilu0_scalar_and_bs3(J, O, ctx):
+    w, s = _setup(J, O, ctx, (7, 6, 5), True)
+    n = w["nc"]
+    disc = J.TwoPointPotentialFlowHardCoded(ctx, w["N"], n)
+    for bs in (1, 3):
+        jac = J.tpfa_jacobian(disc, bs)
+        rng = np.random.default_rng(bs)
+        nz = 0.2 * rng.standard_normal(jac.nnz * bs * bs)
+        for row in range(n):
+            k = s["diag_pos"][row] - 1
+            nz[k * bs * bs:(k + 1) * bs * bs] += (4 * np.eye(bs)).ravel()
+        jac.set_nonzeros(nz)
+        ig = J.ILUZeroPreconditioner(jac); assert ig.update_preconditioner() == 0
+        io = O.ILU0(n, bs, s["rowptr"], s["colidx"]); io.factor(nz)
+        b = rng.standard_normal(n * bs)
+        dx = ctx.zeros(n * bs)
+        ig.apply(dx, ctx.transfer(b))
+        assert np.abs(dx.get() - io.solve(b)).max() <= 1e-11
+
+
+def test_ilu0_bad_pivot_reported(J, O, ctx):
+    w, s = _setup(J, O, ctx, (4, 3, 2), False)
+    disc = J.TwoPointPotentialFlowHardCoded(ctx, w["N"], w["nc"])
+    jac = J.tpfa_jacobian(disc, 1)
+    jac.set_nonzeros(np.zeros(jac.nnz))
+    assert J.ILUZeroPreconditioner(jac).update_preconditioner() == J.JB_BAD_PIVOT
+
+
+@pytest.mark.parametrize("side", ["right", "left"])
+@pytest.mark.parametrize("rtol", [1e-3, 1e-8])
+def test_bicgstab_matches_oracle(J, O, ctx, side, rtol):
+    w, s, sim, nz, r = _jacobian_on_gpu(J, O, ctx, dims=(13, 11, 7))
+    n = w["nc"]
+    nz = sim.jac.nonzeros(); r = sim.r.get()
+    kry = J.GenericKrylov(sim.jac, "bicgstab", sim.prec, relative_tolerance=rtol, precond_side=side, max_iterations=200)
+    ok, its, hist, st = J.linear_solve(kry, sim.r, sim.dx)
+    ilu = O.ILU0(n, 2, s["rowptr"], s["colidx"]); ilu.factor(nz)
+    x, st_o, its_o, hist_o = O.bicgstab(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, side=side, rtol=rtol, itmax=200)
+    assert ok and st == 0 and st_o == 0
+    assert abs(its - its_o) <= 1
+    m = min(len(hist), len(hist_o)) - 1
+    assert np.allclose(hist[0], hist_o[0], rtol=1e-12)
+    assert np.allclose(hist[:m], hist_o[:m], rtol=1e-3)     # iteration-by-iteration residual history
+    dx = sim.dx.get()
+    assert np.linalg.norm(dx + x) <= 10 * rtol * np.linalg.norm(x)
+    # direct-solve cross-check of the GPU answer itself
+    import scipy.sparse.linalg as spla
+    A = to_scipy(n, 2, s["rowptr"], s["colidx"], nz)
+    xd = spla.spsolve(A.tocsc(), r)
+    assert np.linalg.norm(dx + xd) <= 50 * rtol * np.linalg.norm(xd)
+
+
+def test_bicgstab_edge_cases(J, O, ctx):
+    w, s, sim, nz, r = _jacobian_on_gpu(J, O, ctx, dims=(6, 5, 4))
+    n = w["nc"]
+    zero = ctx.zeros(2 * n)
+    kry = J.GenericKrylov(sim.jac, "bicgstab", sim.prec)
+    ok, its, hist, st = J.linear_solve(kry, zero, sim.dx)
+    assert ok and its == 0 and np.all(sim.dx.get() == 0)
+    kry2 = J.GenericKrylov(sim.jac, "bicgstab", None, relative_tolerance=1e-14, max_iterations=2)
+    ok, its, hist, st = J.linear_solve(kry2, sim.r, sim.dx)
+    assert (not ok) and st == J.JB_NOT_CONVERGED and its == 2 and len(hist) == 3
+    kry3 = J.GenericKrylov(sim.jac, "bicgstab", sim.prec, relative_tolerance=1e-1, min_iterations=6)
+    ok, its, hist, st = J.linear_solve(kry3, sim.r, sim.dx)
+    assert ok and its >= 5
+
+
+def test_update_and_convergence_kernels(J, O, ctx):
+    rng = np.random.default_rng(4)
+    n = 10007
+    v = rng.random(n) * 2; dx = rng.standard_normal(2 * n)
+    dv, ddx = ctx.transfer(v), ctx.transfer(dx)
+    J.update_primary_variable(ctx, dv, ddx, n, dx_stride=2, w=0.9, abs_max=0.5, rel_max=0.2, minimum=0.0, maximum=1.5, scale=1.1)
+    ref = O.update_scalar(v.copy(), dx, w=0.9, abs_max=0.5, rel_max=0.2, minv=0.0, maxv=1.5, scale=1.1, dx_stride=2)
+    assert np.array_equal(dv.get(), ref)
+    sw = rng.random(n); s = np.stack([sw, 1 - sw], axis=1).ravel()
+    ds = ctx.transfer(s)
+    J.unit_update_pairs(ctx, ds, ddx.offset(1), n, dx_stride=2, abs_max=0.2)
+    ref = O.update_fraction_pair(s.copy(), dx[1:], abs_max=0.2, dx_stride=2)
+    assert np.array_equal(ds.get(), ref)
+    a, b = J.increment_norm(ctx, ddx, n, stride=2)
+    ao, bo = O.increment_norm(dx, stride=2, n=n)
+    assert abs(a - ao) <= 1e-12 * ao and b == bo
+    e = J.convergence_criterion(ctx, ddx, 2, n)
+    assert np.array_equal(e, O.maxabs_rows(dx, 2))
+    dx[17] = np.nan
+    assert np.isnan(J.convergence_criterion(ctx, ctx.transfer(dx), 2, n)[1])
+
+
+def test_scaling_and_ghost_rows(J, O, ctx):
+    w, s, sim, nz, r = _jacobian_on_gpu(J, O, ctx, dims=(6, 5, 4))
+    n = w["nc"]
+    nz = sim.jac.nonzeros(); r = sim.r.get()
+    sim.jac.scale(sim.r, "dt", 3.0)
+    assert np.allclose(sim.jac.nonzeros(), 3.0 * nz, rtol=1e-15) and np.allclose(sim.r.get(), 3.0 * r, rtol=1e-15)
+    sim.jac.set_nonzeros(nz); sim.r.set(r)
+    sim.jac.scale(sim.r, "diagonal")
+    nz2, r2 = nz.copy(), r.copy()
+    O.scale_diagonal(n, 2, s["rowptr"], s["colidx"], nz2, r2)
+    assert np.allclose(sim.jac.nonzeros(), nz2, rtol=1e-9, atol=1e-9 * np.abs(nz2).max())
+    assert np.allclose(sim.r.get(), r2, rtol=1e-9, atol=1e-9 * np.abs(r2).max())
+    sim.jac.set_nonzeros(nz); sim.r.set(r)
+    n_owned = n - 7
+    sim.jac.unit_diagonalize_ghosts(sim.r, n_owned)
+    A = to_scipy(n, 2, s["rowptr"], s["colidx"], sim.jac.nonzeros()).toarray()
+    assert np.array_equal(A[2 * n_owned:, :], np.hstack([np.zeros((14, 2 * n_owned)), -np.eye(14)]))
+    assert np.array_equal(sim.r.get()[2 * n_owned:], np.zeros(14)) and np.array_equal(sim.r.get()[:2 * n_owned], r[:2 * n_owned])
+
+
+def test_heat_config1(J, O, ctx):
+    """Config 1: 100x100 heat equation, one implicit step; Newton iterate vs the oracle's direct solve."""
+    import scipy.sparse.linalg as spla
+    nx = ny = 100
+    T0 = J.workloads.heat_initial_condition(nx, ny)
+    sim = J.HeatSimulator(ctx, nx, ny, 100.0, 100.0, rtol=1e-10)
+    sim.set_state(T0)
+    sim.assemble(1.0)
+    I, Jc = O.heat_pattern(nx, ny)
+    rowptr, colidx = O.csr_from_coo(I, Jc, nx * ny)
+    nz, r = O.assemble_heat(nx, ny, 1.0, 1.0, 1.0, T0, T0, rowptr, colidx)
+    rp, ci = sim.jac.pattern()
+    assert np.array_equal(rp, rowptr) and np.array_equal(ci, colidx) and colidx.shape[0] == 50000
+    assert np.array_equal(sim.jac.nonzeros(), nz) and np.array_equal(sim.r.get(), r)
+    ok, info = sim.step(1.0)
+    assert ok and len(info) == 1          # linear problem: 2 assemblies + 1 solve
+    A = to_scipy(nx * ny, 1, rowptr, colidx, nz)
+    T1 = np.maximum(T0 - spla.spsolve(A.tocsc(), r), 0.0)
+    assert np.abs(sim.T.get() - T1).max() <= 1e-7
+    assert abs(sim.T.get().sum() - T0.sum()) <= 1e-6 * T0.sum()    # periodic: heat is conserved
+
+
+def test_heat_tiny_periodic_aliasing(J, O, ctx):
+    for nx, ny in [(4, 4), (2, 3), (1, 5)]:
+        sim = J.HeatSimulator(ctx, nx, ny, 1.0, 1.0)
+        rng = np.random.default_rng(nx * 10 + ny)
+        T0 = rng.random(nx * ny); T = rng.random(nx * ny)
+        sim.T.set(T); sim.T0.set(T0)
+        sim.assemble(0.1)
+        I, Jc = O.heat_pattern(nx, ny)
+        rowptr, colidx = O.csr_from_coo(I, Jc, nx * ny)
+        nz, r = O.assemble_heat(nx, ny, 1.0 / nx, 1.0 / ny, 0.1, T, T0, rowptr, colidx)
+        assert np.allclose(sim.jac.nonzeros(), nz, rtol=1e-14) and np.allclose(sim.r.get(), r, rtol=1e-13, atol=1e-12)
+
+
+def test_poisson_known_answer(J, O, ctx):
+    # test/test_systems/variable_poisson.jl:28-35 through assemble -> ILU0-BiCGStab -> update
+    N = O.cart_neighbors(3, 1, 1)
+    sim = J.PoissonSimulator(ctx, N, 3, np.full(2, 3.0))
+    sim.set_state(np.ones(3))
+    sim.set_forces([1, 3], [1.0, -1.0])
+    assert sim.step(1.0)
+    U = sim.U.get()
+    assert np.allclose(U - U[0], [0.0, 1.0 / 3.0, 2.0 / 3.0], atol=1e-8)
+    # assembly parity on a bigger permuted grid, stationary and time-dependent
+    w, s = _setup(J, O, ctx, (6, 5, 4), True)
+    for td in (False, True):
+        ps = J.PoissonSimulator(ctx, w["N"], w["nc"], w["Tf"] * 1e12, time_dependent=td)
+        rng = np.random.default_rng(8)
+        U0 = rng.random(w["nc"]); U1 = rng.random(w["nc"])
+        ps.U.set(U1); ps.U0.set(U0)
+        ps.set_forces([2, 5], [0.3, -0.1])
+        ps.assemble(0.5)
+        nz, r = O.assemble_poisson(s["hf"], s["rowptr"], s["colidx"], w["Tf"] * 1e12, U1, U0, td, 0.5, [2, 5], [0.3, -0.1])
+        assert np.allclose(ps.jac.nonzeros(), nz, rtol=1e-14, atol=1e-14)
+        assert np.allclose(ps.r.get(), r, rtol=1e-12, atol=1e-12 * np.abs(r).max())
+
+
+def test_newton_step_matches_oracle(J, O, ctx):
+    """Config 3 in miniature: full Newton loop to convergence with ILU(0)-BiCGStab to 1e-8; iterate parity 1e-8."""
+    w, s = _setup(J, O, ctx, (10, 9, 6), True)
+    n = w["nc"]
+    sim = J.TwoPhaseSimulator(ctx, w["N"], n, w["Tf"], w["gdz"], w["pv"], w["params"], rtol=1e-8, tolerance=1e-5, max_linear_iterations=200)
+    sim.set_forces(w["src_cells"], w["src_vals"])
+    sim.set_state(w["p0"], w["sw0"])
+    ok, reps = sim.solve_ministep(w["dt"])
+    assert ok
+    # oracle Newton loop
+    p, sw = w["p0"].copy(), w["sw0"].copy()
+    M0 = O.mass_2ph(w["pv"], w["params"], p, sw)
+    ilu = O.ILU0(n, 2, s["rowptr"], s["colidx"])
+    sat = np.stack([sw, 1 - sw], axis=1).ravel()
+    n_solves = 0
+    for it in range(16):
+        nz, r = O.assemble_2ph(s["hf"], s["diag_pos"], s["hf_pos"], w["Tf"], w["gdz"], w["pv"], w["params"], p, sat[0::2].copy(), M0, w["dt"],
+                               s["colidx"].shape[0], w["src_cells"], w["src_vals"])
+        if np.all(O.maxabs_rows(r, 2) <= 1e-5):
+            break
+        ilu.factor(nz)
+        x, st, its, hist = O.bicgstab(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, rtol=1e-8, itmax=200)
+        dx = -x
+        O.update_scalar(p, dx, dx_stride=2)
+        O.update_fraction_pair(sat, dx[1:], abs_max=0.2, dx_stride=2)
+        n_solves += 1
+    assert len(reps) == n_solves + 1            # n+1 assemblies for n solves (check_before_solve)
+    pg, swg = sim.get_state()
+    assert np.abs(pg - p).max() <= 1e-8 * np.abs(p).max()
+    assert np.abs(swg - sat[0::2]).max() <= 1e-8
+
+
+def test_perform_step_host_end_to_end(J, O, ctx):
+    w, s = _setup(J, O, ctx, (10, 9, 6), True)
+    n = w["nc"]
+    sim = J.TwoPhaseSimulator(ctx, w["N"], n, w["Tf"], w["gdz"], w["pv"], w["params"], rtol=1e-8)
+    sim.set_forces(w["src_cells"], w["src_vals"])
+    sim.set_state(w["p0"], w["sw0"])
+    p = w["p0"].copy(); sat = np.stack([w["sw0"], 1 - w["sw0"]], axis=1).ravel().copy()
+    M0 = O.mass_2ph(w["pv"], w["params"], w["p0"], w["sw0"])
+    st, conv, its, err = sim.perform_step_host(p, sat, M0, w["dt"])
+    conv2, err2, rep = sim.perform_step(w["dt"])
+    assert st == 0 and not conv and its == rep["linear_iterations"] and np.array_equal(err, err2)
+    pg, swg = sim.get_state()
+    assert np.array_equal(pg, p) and np.array_equal(swg, sat[0::2])
+
+
+def test_full_size_properties(J, O, ctx):
+    """Size-independent properties at a size the oracle is not run at (1M cells, config 2):
+    linearity of SpMV, L*U*x == A*x restricted identity via ILU apply of A*e for block-diagonal dominance,
+    conservation: column sums of the flux part of the Jacobian vanish, residual sums to accumulation + sources."""
+    w = J.workloads.unstructured_hex(100, 100, 100)
+    n = w["nc"]
+    sim = J.TwoPhaseSimulator(ctx, w["N"], n, w["Tf"], w["gdz"], w["pv"], w["params"], rtol=1e-6)
+    sim.set_forces(w["src_cells"], w["src_vals"])
+    sim.set_state(w["p0"], w["sw0"])
+    sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r)
+    r = sim.r.get()
+    # fluxes cancel pairwise: sum of residual = sum of accumulation (0 at state0) + sources
+    tot = r.reshape(n, 2).sum(axis=0)
+    assert np.allclose(tot, w["src_vals"].sum(axis=0), atol=1e-6 * np.abs(r).max())
+    rng = np.random.default_rng(0)
+    x1, x2 = rng.standard_normal(2 * n), rng.standard_normal(2 * n)
+    d1, d2, d3 = ctx.transfer(x1), ctx.transfer(x2), ctx.transfer(2.0 * x1 - 3.0 * x2)
+    y1, y2, y3 = ctx.zeros(2 * n), ctx.zeros(2 * n), ctx.zeros(2 * n)
+    sim.jac.mul(y1, d1); sim.jac.mul(y2, d2); sim.jac.mul(y3, d3)
+    a, b, c = y1.get(), y2.get(), y3.get()
+    assert np.abs(c - (2.0 * a - 3.0 * b)).max() <= 1e-12 * (np.abs(a).max() + np.abs(b).max())
+    ok, its, hist, st = J.linear_solve(sim.krylov, sim.r, sim.dx)
+    assert ok and hist[-1] <= 1e-6 * hist[0] + 1e-12
+    # true residual of the returned increment: |r + J dx| small
+    sim.jac.mul(y1, sim.dx)
+    assert np.linalg.norm(y1.get() + r) <= 1e-5 * np.linalg.norm(r)

@@ -1,0 +1,180 @@
+"""Oracle self-checks where the reference holds no golden vector ("parity unpinned" items):
+dense-algebra identities, scipy direct solves, finite differences. No GPU."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from conftest import oracle_system, to_scipy
+
+
+def _twophase_system(O, J, dims=(6, 5, 4), permute=True, perturb=True):
+    w = J.workloads.unstructured_hex(*dims, permute=permute)
+    s = oracle_system(O, w)
+    M0 = O.mass_2ph(w["pv"], w["params"], w["p0"], w["sw0"])
+    p = w["p0"] * (1 + (1e-3 * np.sin(np.arange(w["nc"])) if perturb else 0))
+    nz, r = O.assemble_2ph(s["hf"], s["diag_pos"], s["hf_pos"], w["Tf"], w["gdz"], w["pv"], w["params"], p, w["sw0"], M0, w["dt"],
+                           s["colidx"].shape[0], w["src_cells"], w["src_vals"])
+    return w, s, M0, p, nz, r
+
+
+def test_spmv_matches_scipy(O, J):
+    w, s, M0, p, nz, r = _twophase_system(O, J)
+    A = to_scipy(w["nc"], 2, s["rowptr"], s["colidx"], nz)
+    x = np.random.default_rng(0).standard_normal(2 * w["nc"])
+    y = O.spmv(w["nc"], 2, s["rowptr"], s["colidx"], nz, x)
+    assert np.allclose(y, A @ x, rtol=1e-13, atol=1e-13 * np.abs(y).max())
+    y2 = O.spmv(w["nc"], 2, s["rowptr"], s["colidx"], nz, x, alpha=2.0, beta=0.5, y=y.copy())
+    assert np.allclose(y2, 2.0 * (A @ x) + 0.5 * y, rtol=1e-13, atol=1e-13 * np.abs(y).max())
+
+
+def test_jacobian_finite_differences(O, J):
+    """The AD Jacobian (local-perspective partials scattered as the reference does) equals dR/dx."""
+    w, s, M0, p, nz, r = _twophase_system(O, J, dims=(4, 3, 3))
+    A = to_scipy(w["nc"], 2, s["rowptr"], s["colidx"], nz).toarray()
+    nc = w["nc"]
+    rng = np.random.default_rng(3)
+    for c in rng.choice(nc, 8, replace=False):
+        for var, h in ((0, 10.0), (1, 1e-7)):
+            pp, ss = p.copy(), w["sw0"].copy()
+            pm, sm = p.copy(), w["sw0"].copy()
+            if var == 0:
+                pp[c] += h; pm[c] -= h
+            else:
+                ss[c] += h; sm[c] -= h
+            rp = O.residual_2ph(s["hf"], w["Tf"], w["gdz"], w["pv"], w["params"], pp, ss, M0, w["dt"])
+            rm = O.residual_2ph(s["hf"], w["Tf"], w["gdz"], w["pv"], w["params"], pm, sm, M0, w["dt"])
+            fd = (rp - rm) / (2 * h)
+            col = A[:, 2 * c + var]
+            assert np.allclose(fd, col, rtol=2e-5, atol=1e-6 * np.abs(col).max())
+
+
+def test_residual_identity(O, J):
+    # test/test_systems/helper.jl:3-18: model_residual (no AD) == LinearizedSystem.r
+    w, s, M0, p, nz, r = _twophase_system(O, J)
+    r2 = O.residual_2ph(s["hf"], w["Tf"], w["gdz"], w["pv"], w["params"], p, w["sw0"], M0, w["dt"])
+    src = np.zeros_like(r2)
+    for c, v in zip(w["src_cells"], w["src_vals"]):
+        src[2 * (c - 1):2 * c] += v
+    assert np.allclose(r, r2 + src, rtol=1e-14, atol=1e-14 * np.abs(r).max())
+
+
+@pytest.mark.parametrize("bs", [1, 2, 3])
+def test_ilu0_exact_on_tridiagonal(O, bs):
+    """ILU(0) of a (block) tridiagonal matrix has no dropped fill: L*U == A and the solve is exact."""
+    n = 40
+    rng = np.random.default_rng(bs)
+    I = np.concatenate([np.arange(1, n + 1), np.arange(2, n + 1), np.arange(1, n)])
+    Jc = np.concatenate([np.arange(1, n + 1), np.arange(1, n), np.arange(2, n + 1)])
+    rowptr, colidx = O.csr_from_coo(I, Jc, n)
+    nz = rng.standard_normal(colidx.shape[0] * bs * bs) * 0.3
+    for row in range(n):   # diagonally dominant blocks
+        for k in range(rowptr[row] - 1, rowptr[row + 1] - 1):
+            if colidx[k] - 1 == row:
+                blk = nz[k * bs * bs:(k + 1) * bs * bs].reshape(bs, bs)
+                blk += 4 * np.eye(bs)
+    A = to_scipy(n, bs, rowptr, colidx, nz)
+    ilu = O.ILU0(n, bs, rowptr, colidx)
+    assert ilu.factor(nz) == 0
+    b = rng.standard_normal(n * bs)
+    x = ilu.solve(b)
+    assert np.allclose(A @ x, b, rtol=1e-11, atol=1e-11)
+
+
+def test_ilu0_residual_zero_on_pattern(O, J):
+    """Defining property of ILU(0): (L*U - A) vanishes on the sparsity pattern of A."""
+    w, s, M0, p, nz, r = _twophase_system(O, J, dims=(5, 4, 3))
+    n, bs = w["nc"], 2
+    ilu = O.ILU0(n, bs, s["rowptr"], s["colidx"])
+    assert ilu.factor(nz) == 0
+    f = ilu.get()
+    import scipy.sparse as sp
+    L = to_scipy(n, bs, f["Lptr"], f["Lcol"], f["L"]) + sp.identity(n * bs)
+    U = to_scipy(n, bs, f["Uptr"], f["Ucol"], f["U"])
+    Dinv = f["D"].reshape(n, bs, bs).transpose(0, 2, 1)
+    D = sp.block_diag([sp.coo_matrix(np.linalg.inv(d)) for d in Dinv])
+    A = to_scipy(n, bs, s["rowptr"], s["colidx"], nz)
+    E = (L @ (D + U) - A).toarray()
+    mask = (to_scipy(n, bs, s["rowptr"], s["colidx"], np.ones_like(nz)).toarray() != 0)
+    assert np.abs(E[mask]).max() <= 1e-12 * np.abs(A).max()
+
+
+def test_block_jacobi_ilu_equals_per_block(O, J):
+    """ilu0_csr(A, partition): each block is the ILU(0) of its own diagonal sub-matrix (par_ilu0.jl:47-87)."""
+    w, s, M0, p, nz, r = _twophase_system(O, J, dims=(5, 4, 3))
+    n, bs = w["nc"], 2
+    part = O.partition_linear(3, n)
+    ilu = O.ILU0(n, bs, s["rowptr"], s["colidx"], part)
+    ilu.factor(nz)
+    b = np.random.default_rng(5).standard_normal(n * bs)
+    x = ilu.solve(b)
+    A = to_scipy(n, bs, s["rowptr"], s["colidx"], nz).tocsr()
+    for blk in range(1, 4):
+        rows = np.where(part == blk)[0]
+        dof = (rows[:, None] * bs + np.arange(bs)[None, :]).ravel()
+        sub = A[dof][:, dof].tocoo()
+        # sub-matrix as its own block CSR
+        Ib = sub.row // bs + 1; Jb = sub.col // bs + 1
+        rp, ci = O.csr_from_coo(Ib, Jb, rows.shape[0])
+        dense = sub.toarray()
+        nzb = np.concatenate([dense[(r_ * bs):(r_ * bs + bs), ((c_ - 1) * bs):((c_ - 1) * bs + bs)].T.ravel()
+                              for r_ in range(rows.shape[0]) for c_ in ci[rp[r_] - 1:rp[r_ + 1] - 1]])
+        sub_ilu = O.ILU0(rows.shape[0], bs, rp, ci)
+        sub_ilu.factor(nzb)
+        assert np.allclose(sub_ilu.solve(b[dof]), x[dof], rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("side", ["right", "left", "none"])
+def test_bicgstab_solves(O, J, side):
+    w, s, M0, p, nz, r = _twophase_system(O, J)
+    n = w["nc"]
+    O.scale_diagonal(n, 2, s["rowptr"], s["colidx"], nz, r)   # krylov scaling = :diagonal, keeps the unpreconditioned case solvable
+    A = to_scipy(n, 2, s["rowptr"], s["colidx"], nz)
+    ilu = O.ILU0(n, 2, s["rowptr"], s["colidx"]); ilu.factor(nz)
+    x, st, its, hist = O.bicgstab(n, 2, s["rowptr"], s["colidx"], nz, r, ilu if side != "none" else None, side=side,
+                                  rtol=1e-10, itmax=2000)
+    assert st == 0 and its >= 1 and hist.shape[0] == its + 1
+    xd = spla.spsolve(A.tocsc(), r)
+    assert np.linalg.norm(x - xd) <= 1e-6 * np.linalg.norm(xd)
+    if side != "left":   # history is the true residual norm for right/no preconditioning
+        assert abs(np.linalg.norm(r - A @ x) - hist[-1]) <= 1e-6 * hist[0]
+
+
+def test_bicgstab_min_iterations_and_itmax(O, J):
+    w, s, M0, p, nz, r = _twophase_system(O, J)
+    n = w["nc"]
+    ilu = O.ILU0(n, 2, s["rowptr"], s["colidx"]); ilu.factor(nz)
+    _, st, its, _ = O.bicgstab(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, rtol=1e-1, min_it=1)
+    _, st2, its2, _ = O.bicgstab(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, rtol=1e-1, min_it=its + 3)
+    assert st == 0 and st2 == 0 and its2 >= its + 3 - 1
+    _, st3, its3, _ = O.bicgstab(n, 2, s["rowptr"], s["colidx"], nz, r, None, side="none", rtol=1e-14, itmax=2)
+    assert st3 == 1 and its3 == 2
+    x, st4, its4, h4 = O.bicgstab(n, 2, s["rowptr"], s["colidx"], nz, np.zeros_like(r), ilu)
+    assert st4 == 0 and its4 == 0 and np.all(x == 0)
+
+
+def test_update_rules(O):
+    # choose_increment order: scale, abs, rel, lower, upper (src/variables/utils.jl:146-156)
+    v = np.array([1.0, 1.0, 1.0, 0.05, 0.95])
+    dx = np.array([10.0, -10.0, 0.3, -1.0, 1.0])
+    out = O.update_scalar(v.copy(), dx, abs_max=0.5, rel_max=0.2, minv=0.0, maxv=1.0)
+    assert np.allclose(out, [1.0, 0.8, 1.0, 0.04, 1.0])
+    # unit_update_pairs!: w applied after limiting; s2 mirrors s1
+    s = np.array([0.5, 0.5, 0.1, 0.9, 0.9, 0.1])
+    O.update_fraction_pair(s, np.array([0.4, -0.5, 0.5]), abs_max=0.2)
+    assert np.allclose(s, [0.7, 0.3, 0.0, 1.0, 1.0, 0.0])
+    assert O.increment_norm(np.array([1.0, -3.0, 2.0])) == (6.0, 3.0)
+    assert O.maxabs_rows(np.array([1.0, -2.0, -5.0, 0.5]), 2).tolist() == [5.0, 2.0]
+
+
+def test_scaling(O, J):
+    w, s, M0, p, nz, r = _twophase_system(O, J, dims=(4, 3, 2))
+    n = w["nc"]
+    A = to_scipy(n, 2, s["rowptr"], s["colidx"], nz)
+    x = spla.spsolve(A.tocsc(), r)
+    nz2, r2 = nz.copy(), r.copy()
+    O.scale_diagonal(n, 2, s["rowptr"], s["colidx"], nz2, r2)
+    A2 = to_scipy(n, 2, s["rowptr"], s["colidx"], nz2)
+    assert np.allclose(spla.spsolve(A2.tocsc(), r2), x, rtol=1e-8)
+    d = A2.toarray()
+    for c in range(n):
+        assert np.allclose(d[2 * c:2 * c + 2, 2 * c:2 * c + 2], np.eye(2), atol=1e-8)
