@@ -118,6 +118,11 @@ class DeviceArray:
             check(self.ctx.lib.jb_d2h(self.ctx.h, out.ctypes.data_as(C.c_void_p), self.ptr, self.n * 8), self.ctx.h, "jb_d2h")
         return out
 
+    def copy_from(self, other):
+        assert other.n == self.n
+        check(self.ctx.lib.jb_d2d(self.ctx.h, self.ptr, other.ptr, self.n * 8), self.ctx.h, "jb_d2d")
+        return self
+
     def offset(self, k):
         """Device pointer to element k (for strided views such as dx[1::2])."""
         return C.c_void_p((self.ptr.value or 0) + 8 * int(k))
@@ -383,6 +388,53 @@ def convergence_criterion(ctx, r, bs, n):
     out = np.zeros(bs)
     check(ctx.lib.jb_maxabs_rows(ctx.h, _dp(r), bs, n, _pd(out)), ctx.h, "jb_maxabs_rows")
     return out
+
+
+def partition(N, num_coarse, weights=None, nc=None, partitioner="metis"):
+    """partition(N, num_coarse, weights; partitioner = MetisPartitioner()) (src/partitioning.jl:244-307).
+    Host-side setup call; returns 1-based block labels per cell."""
+    lib = _lib.load()
+    N = np.ascontiguousarray(N, dtype=i64)
+    nc = int(N.max()) if nc is None else int(nc)
+    part = np.zeros(nc, dtype=i64)
+    if partitioner == "linear":
+        rc = lib.jb_partition_linear(int(num_coarse), nc, _pi(part))
+    else:
+        w = None if weights is None else np.ascontiguousarray(weights, dtype=f64)
+        rc = lib.jb_partition_metis(nc, N.shape[0], _pi(N), _pd(w), int(num_coarse), _pi(part))
+    check(rc, None, "partition")
+    return part
+
+
+class DeviceProfile:
+    """Per-kernel-class device times (CUDA events on the context's stream)."""
+
+    CLASSES = ("state", "assembly", "spmv", "ilu_factor", "ilu_apply", "vector", "newton", "other")
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def __enter__(self):
+        check(self.ctx.lib.jb_prof_enable(self.ctx.h, 1), self.ctx.h, "jb_prof_enable")
+        return self
+
+    def __exit__(self, *a):
+        self.ctx.lib.jb_prof_enable(self.ctx.h, 0)
+
+    def collect(self):
+        ms = np.zeros(8); cnt = np.zeros(8, dtype=i64)
+        check(self.ctx.lib.jb_prof_collect(self.ctx.h, _pd(ms), _pi(cnt)), self.ctx.h, "jb_prof_collect")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.CLASSES)}
+
+
+def timer_start(ctx):
+    check(ctx.lib.jb_timer_start(ctx.h), ctx.h, "jb_timer_start")
+
+
+def timer_stop(ctx):
+    ms = C.c_double(0)
+    check(ctx.lib.jb_timer_stop(ctx.h, C.byref(ms)), ctx.h, "jb_timer_stop")
+    return ms.value
 
 
 from .simulator import HeatSimulator, PoissonSimulator, TwoPhaseSimulator  # noqa: E402

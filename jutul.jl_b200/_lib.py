@@ -26,10 +26,15 @@ PROTOTYPES = {
     "jb_last_error": (C.c_char_p, [P]),
     "jb_launch_count": (I64, [P]),
     "jb_stream": (P, [P]),
+    "jb_timer_start": (I32, [P]),
+    "jb_timer_stop": (I32, [P, PF64]),
+    "jb_prof_enable": (I32, [P, I32]),
+    "jb_prof_collect": (I32, [P, PF64, PI64]),
     "jb_malloc": (I32, [P, I64, PP]),
     "jb_free": (I32, [P, P]),
     "jb_h2d": (I32, [P, P, P, I64]),
     "jb_d2h": (I32, [P, P, P, I64]),
+    "jb_d2d": (I32, [P, P, P, I64]),
     "jb_pinned_alloc": (I32, [I64, PP]),
     "jb_pinned_free": (I32, [P]),
     "jb_mesh_create": (I32, [P, I64, I64, PI64, PP]),
@@ -74,6 +79,8 @@ PROTOTYPES = {
     "jb_update_fraction_pair": (I32, [P, P, P, I64, I64, F64, F64, F64, F64]),
     "jb_increment_norm": (I32, [P, P, I64, I64, PF64, PF64]),
     "jb_maxabs_rows": (I32, [P, P, I32, I64, PF64]),
+    "jb_partition_metis": (I32, [I64, I64, PI64, PF64, I64, PI64]),
+    "jb_partition_linear": (I32, [I64, I64, PI64]),
     "jb_twophase_perform_step_host": (I32, [P, P, P, PF64, PF64, PF64, F64, F64, F64, F64, I32, F64, F64, PF64, PI32, PI32]),
 }
 

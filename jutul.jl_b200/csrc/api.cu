@@ -9,9 +9,60 @@ int jb_launch_update_scalar(jb_ctx* ctx, double* d_v, const double* d_dx, i64 st
 int jb_launch_update_pair(jb_ctx* ctx, double* d_s, const double* d_dx, i64 stride, i64 n, double w, double abs_max, double minval, double maxval);
 int jb_launch_maxabs_rows(jb_ctx* ctx, const double* d_r, int bs, i64 n, double* d_out);
 
+static cudaEvent_t prof_event(jb_ctx* ctx) {
+    if (!ctx->prof_pool.empty()) { cudaEvent_t e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void jb_prof_begin(jb_ctx* ctx, int cls) {
+    jb_ctx::ProfRec r;
+    r.cls = cls; r.a = prof_event(ctx); r.b = prof_event(ctx);
+    cudaEventRecord(r.a, ctx->stream);
+    ctx->prof_recs.push_back(r);
+}
+void jb_prof_end(jb_ctx* ctx) {
+    if (!ctx->prof_recs.empty()) cudaEventRecord(ctx->prof_recs.back().b, ctx->stream);
+}
+
 extern "C" {
 
 int32_t jb_version(void) { return 100; }
+
+int32_t jb_prof_enable(jb_ctx* ctx, int32_t on) {
+    if (!ctx) return JB_ERR_ARG;
+    ctx->prof_on = on != 0;
+    return JB_OK;
+}
+// Sums the recorded per-class kernel times (ms) and launch-group counts since the last call, then clears them.
+int32_t jb_prof_collect(jb_ctx* ctx, double* ms /*8*/, int64_t* counts /*8*/) {
+    if (!ctx || !ms || !counts) return JB_ERR_ARG;
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < JB_PROF_NCLASS; i++) { ms[i] = 0.0; counts[i] = 0; }
+    for (auto& r : ctx->prof_recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cls] += (double)t; counts[r.cls]++; }
+        ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof_recs.clear();
+    return JB_OK;
+}
+int32_t jb_timer_start(jb_ctx* ctx) {
+    if (!ctx) return JB_ERR_ARG;
+    if (!ctx->timer_a) { JB_CUDA(ctx, cudaEventCreate(&ctx->timer_a)); JB_CUDA(ctx, cudaEventCreate(&ctx->timer_b)); }
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    JB_CUDA(ctx, cudaEventRecord(ctx->timer_a, ctx->stream));
+    return JB_OK;
+}
+int32_t jb_timer_stop(jb_ctx* ctx, double* ms) {
+    if (!ctx || !ms || !ctx->timer_a) return JB_ERR_ARG;
+    JB_CUDA(ctx, cudaEventRecord(ctx->timer_b, ctx->stream));
+    JB_CUDA(ctx, cudaEventSynchronize(ctx->timer_b));
+    float t = 0.f;
+    JB_CUDA(ctx, cudaEventElapsedTime(&t, ctx->timer_a, ctx->timer_b));
+    *ms = (double)t;
+    return JB_OK;
+}
 
 int32_t jb_ctx_create(int32_t device, jb_ctx** out) {
     if (!out) return JB_ERR_ARG;
@@ -44,6 +95,9 @@ int32_t jb_ctx_destroy(jb_ctx* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_scalars) cudaFree(ctx->d_scalars);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (auto& r : ctx->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->prof_pool) cudaEventDestroy(e);
+    if (ctx->timer_a) { cudaEventDestroy(ctx->timer_a); cudaEventDestroy(ctx->timer_b); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return JB_OK;
@@ -81,6 +135,12 @@ int32_t jb_d2h(jb_ctx* ctx, void* dst, const void* d_src, int64_t bytes) {
     if (bytes == 0) return JB_OK;
     JB_CUDA(ctx, cudaMemcpyAsync(dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
     JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+int32_t jb_d2d(jb_ctx* ctx, void* d_dst, const void* d_src, int64_t bytes) {
+    if (!ctx || bytes < 0) return JB_ERR_ARG;
+    if (bytes == 0) return JB_OK;
+    JB_CUDA(ctx, cudaMemcpyAsync(d_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return JB_OK;
 }
 int32_t jb_pinned_alloc(int64_t bytes, void** out) {

@@ -32,7 +32,8 @@
 #include "jb_internal.cuh"
 #include "jb_reduce.cuh"
 
-struct TPParams { double rho0[2], c[2], mu[2], p0; };
+// inv_mu: the kernels multiply by 1/mu instead of dividing (FP64 division is a ~30-instruction sequence)
+struct TPParams { double rho0[2], c[2], mu[2], p0, inv_mu[2]; };
 
 __global__ void __launch_bounds__(256) twophase_state_kernel(i64 nc, TPParams P, const double* __restrict__ p, const double* __restrict__ s,
                                                              double4* __restrict__ rec) {
@@ -65,9 +66,9 @@ __device__ __forceinline__ CellP cell_props(const TPParams& P, const double4 r) 
 #pragma unroll
     for (int a = 0; a < 2; a++) {
         const double kr = S[a] * S[a];
-        o.mob[a] = (o.rho[a] * kr) / P.mu[a];
-        o.dmob_dp[a] = (P.c[a] * o.rho[a] * kr) / P.mu[a];
-        o.dmob_ds[a] = (o.rho[a] * (2.0 * S[a] * dS[a])) / P.mu[a];
+        o.mob[a] = (o.rho[a] * kr) * P.inv_mu[a];
+        o.dmob_dp[a] = P.c[a] * o.mob[a];
+        o.dmob_ds[a] = (o.rho[a] * (2.0 * S[a] * dS[a])) * P.inv_mu[a];
     }
     return o;
 }
@@ -91,12 +92,12 @@ __device__ __forceinline__ void flux_phase(const TPParams& P, const CellP& self,
 }
 
 template <int LPC, bool JAC>
-__global__ void __launch_bounds__(256) twophase_assemble_kernel(i64 nc, TPParams P, const int32_t* __restrict__ hf_pos,
+__global__ void __launch_bounds__(256, 4) twophase_assemble_kernel(i64 nc, TPParams P, const int32_t* __restrict__ hf_pos,
                                                                 const int32_t* __restrict__ hf_other, const int32_t* __restrict__ hf_rowpos,
                                                                 const double* __restrict__ hf_T, const double* __restrict__ hf_sgdz,
                                                                 const int32_t* __restrict__ diag_pos, const double4* __restrict__ rec,
                                                                 const double* __restrict__ pv, const double* __restrict__ M0,
-                                                                const double* __restrict__ src, double inv_dt_unused, double dt,
+                                                                const double* __restrict__ src, double inv_dt, double dt,
                                                                 double* __restrict__ nz, double* __restrict__ r) {
     constexpr int CELLS_PER_WARP = 32 / LPC;
     const int lane = threadIdx.x % LPC;
@@ -147,11 +148,11 @@ __global__ void __launch_bounds__(256) twophase_assemble_kernel(i64 nc, TPParams
 #pragma unroll
                 for (int a = 0; a < 2; a++) {
                     const double mass = pvc * (self.rho[a] * S[a]);
-                    double acc = (mass - __ldg(M0 + 2 * c + a)) / dt;
+                    double acc = (mass - __ldg(M0 + 2 * c + a)) * inv_dt;
                     if (src) acc += __ldg(src + 2 * c + a);
                     racc[a] += acc;
-                    dacc[a] += (pvc * (P.c[a] * self.rho[a] * S[a])) / dt;
-                    dacc[2 + a] += (pvc * (self.rho[a] * dS[a])) / dt;
+                    dacc[a] += (pvc * (P.c[a] * self.rho[a] * S[a])) * inv_dt;
+                    dacc[2 + a] += (pvc * (self.rho[a] * dS[a])) * inv_dt;
                 }
             }
         }
@@ -251,6 +252,7 @@ static TPParams make_params(const jb_twophase* m) {
     TPParams P;
     P.rho0[0] = m->params[0]; P.rho0[1] = m->params[1]; P.c[0] = m->params[2]; P.c[1] = m->params[3];
     P.mu[0] = m->params[4]; P.mu[1] = m->params[5]; P.p0 = m->params[6];
+    P.inv_mu[0] = 1.0 / P.mu[0]; P.inv_mu[1] = 1.0 / P.mu[1];
     return P;
 }
 static int grid_for(jb_ctx* ctx, i64 n, int threads, int per_sm) {
@@ -261,6 +263,7 @@ static int grid_for(jb_ctx* ctx, i64 n, int threads, int per_sm) {
 int jb_launch_twophase_state(jb_twophase* m, const double* d_p, const double* d_s) {
     jb_ctx* ctx = m->t->mesh->ctx;
     const i64 nc = m->t->mesh->nc;
+    ProfScope _ps(ctx, JB_PROF_STATE);
     twophase_state_kernel<<<grid_for(ctx, nc, 256, 16), 256, 0, ctx->stream>>>(nc, make_params(m), d_p, d_s, reinterpret_cast<double4*>(m->d_rec.p));
     JB_CHECK_LAUNCH(ctx);
     return JB_OK;
@@ -271,6 +274,7 @@ int jb_launch_twophase_assemble(jb_twophase* m, const double* d_M0, double dt, d
     jb_ctx* ctx = t->mesh->ctx;
     const i64 nc = t->mesh->nc;
     constexpr int LPC = 8;
+    ProfScope _ps(ctx, JB_PROF_ASSEMBLY);
     const i64 cells_per_cta = 256 / LPC;
     const int grid = (int)std::max<i64>(1, (nc + cells_per_cta - 1) / cells_per_cta);
     const double* src = m->nsrc > 0 ? m->d_src.p : nullptr;
@@ -278,12 +282,12 @@ int jb_launch_twophase_assemble(jb_twophase* m, const double* d_M0, double dt, d
         twophase_assemble_kernel<LPC, true><<<grid, 256, 0, ctx->stream>>>(nc, make_params(m), t->mesh->d_hf_pos.p, t->mesh->d_hf_other.p,
                                                                            t->d_hf_rowpos.p, m->d_hf_T.p, m->d_hf_sgdz.p, t->csr->d_diag.p,
                                                                            reinterpret_cast<const double4*>(m->d_rec.p), m->d_pv.p, d_M0, src,
-                                                                           0.0, dt, t->csr->d_val.p, d_r);
+                                                                           1.0 / dt, dt, t->csr->d_val.p, d_r);
     else
         twophase_assemble_kernel<LPC, false><<<grid, 256, 0, ctx->stream>>>(nc, make_params(m), t->mesh->d_hf_pos.p, t->mesh->d_hf_other.p,
                                                                             t->d_hf_rowpos.p, m->d_hf_T.p, m->d_hf_sgdz.p, t->csr->d_diag.p,
                                                                             reinterpret_cast<const double4*>(m->d_rec.p), m->d_pv.p, d_M0, src,
-                                                                            0.0, dt, t->csr->d_val.p, d_r);
+                                                                            1.0 / dt, dt, t->csr->d_val.p, d_r);
     JB_CHECK_LAUNCH(ctx);
     return JB_OK;
 }
@@ -293,6 +297,7 @@ int jb_launch_twophase_assemble_faces(jb_twophase* m, const double* d_M0, double
     jb_ctx* ctx = t->mesh->ctx;
     const i64 nc = t->mesh->nc, nf = t->mesh->nf;
     const double* src = m->nsrc > 0 ? m->d_src.p : nullptr;
+    ProfScope _ps(ctx, JB_PROF_ASSEMBLY);
     twophase_acc_kernel<<<grid_for(ctx, nc, 256, 16), 256, 0, ctx->stream>>>(nc, make_params(m), reinterpret_cast<const double4*>(m->d_rec.p),
                                                                              m->d_pv.p, d_M0, src, dt, t->csr->d_diag.p, t->csr->d_val.p, d_r);
     JB_CHECK_LAUNCH(ctx);

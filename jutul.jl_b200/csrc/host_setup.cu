@@ -6,6 +6,7 @@
 #include <numeric>
 
 #include "jb_internal.cuh"
+#include "jb_stream.cuh"
 
 static std::string g_err;
 void jb_set_global_error(const std::string& s) { g_err = s; }
@@ -74,6 +75,10 @@ static int csr_finish(jb_ctx* ctx, jb_csr* A) {
         for (int32_t k = A->h_rowptr[r]; k < A->h_rowptr[r + 1]; k++)
             if (A->h_colidx[k] == r) { A->h_diag[r] = k; break; }
     cudaStream_t s = ctx->stream;
+    A->h_chunks.clear();
+    if (jb_cut_chunks(A->h_rowptr, 0, (int32_t)A->n, A->h_chunks)) A->h_chunks.push_back((int32_t)A->n);
+    else A->h_chunks.clear();
+    if (!A->h_chunks.empty() && A->d_chunks.upload(A->h_chunks, s) != cudaSuccess) return JB_ERR_ALLOC;
     if (A->d_rowptr.upload(A->h_rowptr, s) != cudaSuccess || A->d_colidx.upload(A->h_colidx, s) != cudaSuccess ||
         A->d_diag.upload(A->h_diag, s) != cudaSuccess || A->d_val.alloc((size_t)A->nnzb * A->bs * A->bs) != cudaSuccess)
         return JB_ERR_ALLOC;
@@ -306,18 +311,44 @@ int jb_ilu_symbolic(jb_ilu* F, const int64_t* partition) {
         }
     }
     if (!fits_i32((i64)F->h_upd_tgt.size()) || !fits_i32(F->nL + n + F->nU)) return JB_ERR_UNSUPPORTED;
+    // stored-row offsets (storage follows forder / border, so these are plain prefix sums) and stream chunks per level
+    F->h_LptrT.resize(n + 1); F->h_UptrT.resize(n + 1);
+    for (i64 t = 0; t < n; t++) { F->h_LptrT[t] = F->h_Lstart[F->h_forder[t]]; F->h_UptrT[t] = F->h_Ustart[F->h_border[t]]; }
+    F->h_LptrT[n] = (int32_t)F->nL; F->h_UptrT[n] = (int32_t)F->nU;
+    F->stream_ok = true;
+    auto cut = [&](const std::vector<int32_t>& ptrT, const std::vector<int32_t>& lev_ptr, int nlev, std::vector<int32_t>& chunks,
+                   std::vector<int32_t>& lev_chunk) {
+        chunks.clear(); lev_chunk.assign(nlev + 1, 0);
+        for (int l = 0; l < nlev; l++) {
+            lev_chunk[l] = (int32_t)chunks.size();
+            if (!jb_cut_chunks(ptrT, lev_ptr[l], lev_ptr[l + 1], chunks)) F->stream_ok = false;
+        }
+        lev_chunk[nlev] = (int32_t)chunks.size();
+        chunks.push_back((int32_t)n);
+    };
+    cut(F->h_LptrT, F->h_levF_ptr, F->nlevF, F->h_chunksF, F->h_levF_chunk);
+    cut(F->h_UptrT, F->h_levB_ptr, F->nlevB, F->h_chunksB, F->h_levB_chunk);
     return JB_OK;
 }
 
 int jb_ilu_upload(jb_ilu* F) {
     cudaStream_t s = F->csr->ctx->stream;
+    // device copies of the row extents are stored in level order (indexed by the position t in forder / border),
+    // so a level kernel reads them contiguously
+    std::vector<int32_t> ls(F->n), le(F->n), us(F->n), ue(F->n);
+    for (i64 t = 0; t < F->n; t++) {
+        ls[t] = F->h_Lstart[F->h_forder[t]]; le[t] = F->h_Lend[F->h_forder[t]];
+        us[t] = F->h_Ustart[F->h_border[t]]; ue[t] = F->h_Uend[F->h_border[t]];
+    }
     bool ok = F->d_forder.upload(F->h_forder, s) == cudaSuccess && F->d_border.upload(F->h_border, s) == cudaSuccess &&
-              F->d_Lstart.upload(F->h_Lstart, s) == cudaSuccess && F->d_Lend.upload(F->h_Lend, s) == cudaSuccess &&
-              F->d_Ustart.upload(F->h_Ustart, s) == cudaSuccess && F->d_Uend.upload(F->h_Uend, s) == cudaSuccess &&
+              F->d_Lstart.upload(ls, s) == cudaSuccess && F->d_Lend.upload(le, s) == cudaSuccess &&
+              F->d_Ustart.upload(us, s) == cudaSuccess && F->d_Uend.upload(ue, s) == cudaSuccess &&
               F->d_Lcol.upload(F->h_Lcol, s) == cudaSuccess && F->d_Ucol.upload(F->h_Ucol, s) == cudaSuccess &&
               F->d_Lmap.upload(F->h_Lmap, s) == cudaSuccess && F->d_Umap.upload(F->h_Umap, s) == cudaSuccess &&
               F->d_Dmap.upload(F->h_Dmap, s) == cudaSuccess && F->d_upd_ptr.upload(F->h_upd_ptr, s) == cudaSuccess &&
               F->d_upd_tgt.upload(F->h_upd_tgt, s) == cudaSuccess && F->d_upd_src.upload(F->h_upd_src, s) == cudaSuccess;
+    ok = ok && F->d_LptrT.upload(F->h_LptrT, s) == cudaSuccess && F->d_UptrT.upload(F->h_UptrT, s) == cudaSuccess &&
+         F->d_chunksF.upload(F->h_chunksF, s) == cudaSuccess && F->d_chunksB.upload(F->h_chunksB, s) == cudaSuccess;
     const size_t b2 = (size_t)F->bs * F->bs;
     ok = ok && F->d_fv.alloc((size_t)(F->nL + F->n + F->nU) * b2) == cudaSuccess && F->d_dinv.alloc((size_t)F->n * b2) == cudaSuccess &&
          F->d_status.alloc(1) == cudaSuccess;

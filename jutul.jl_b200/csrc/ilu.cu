@@ -13,6 +13,7 @@
 // L / U value arrays) so each level streams its part of the factor once.
 #include "jb_internal.cuh"
 #include "jb_krylov_scalars.cuh"
+#include "jb_stream.cuh"
 
 template <int BS>
 __global__ void __launch_bounds__(256) ilu_gather_kernel(i64 nL, i64 n, i64 nU, const int32_t* __restrict__ Lmap,
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(128) ilu_factor_level_kernel(int32_t t0, int32
     const int32_t t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= t1) return;
     const int32_t i = __ldg(forder + t);
-    const int32_t l0 = __ldg(Lstart + i), l1 = __ldg(Lend + i);
+    const int32_t l0 = __ldg(Lstart + t), l1 = __ldg(Lend + t);   // level-ordered copies: contiguous in t
     for (int32_t li = l0; li < l1; li++) {
         const int32_t k = __ldg(Lcol + li);
         double Lik[B2], Dk[B2], m[B2];
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(256) ilu_forward_level_kernel(int32_t t0, int3
     double v[BS];
 #pragma unroll
     for (int e = 0; e < BS; e++) v[e] = b[(size_t)i * BS + e];
-    const int32_t l0 = __ldg(Lstart + i), l1 = __ldg(Lend + i);
+    const int32_t l0 = __ldg(Lstart + t), l1 = __ldg(Lend + t);   // level-ordered copies: contiguous in t
     for (int32_t li = l0; li < l1; li++) {
         const int32_t j = __ldg(Lcol + li);
         double a[B2], xj[BS];
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) ilu_backward_level_kernel(int32_t t0, int
     double v[BS], out[BS], d[B2];
 #pragma unroll
     for (int e = 0; e < BS; e++) v[e] = x[(size_t)i * BS + e];
-    const int32_t u0 = __ldg(Ustart + i), u1 = __ldg(Uend + i);
+    const int32_t u0 = __ldg(Ustart + t), u1 = __ldg(Uend + t);
     for (int32_t ui = u0; ui < u1; ui++) {
         const int32_t j = __ldg(Ucol + ui);
         double a[B2], xj[BS];
@@ -131,9 +132,83 @@ __global__ void __launch_bounds__(256) ilu_backward_level_kernel(int32_t t0, int
     for (int e = 0; e < BS; e++) x[(size_t)i * BS + e] = out[e];
 }
 
+// ---- row-chunk stream form of the sweeps (default; see jb_stream.cuh). One launch per level; a CTA streams the
+//      L (or U) entries of its chunk with unit stride and gathers x of earlier levels. ----
+template <int BS, bool BACKWARD>
+__global__ void __launch_bounds__(256) ilu_sweep_stream_kernel(int c0, int c1, const int32_t* __restrict__ chunk_ptr,
+                                                               const int32_t* __restrict__ ptrT, const int32_t* __restrict__ col,
+                                                               const double* __restrict__ fv, size_t val_block_offset,
+                                                               const int32_t* __restrict__ order, const double* __restrict__ dinv,
+                                                               const double* b, double* x, const double* sc) {
+    if (sc && sc[KS_DONE] != 0.0) return;
+    __shared__ int32_t s_rp[JB_CHUNK_ROWS + 1];
+    extern __shared__ double s_prod[];
+    for (int c = c0 + blockIdx.x; c < c1; c += gridDim.x) {
+        const int t0 = __ldg(chunk_ptr + c), nr = __ldg(chunk_ptr + c + 1) - t0;
+        // own row ids and right-hand sides are independent of the products: issue them first
+        int i = 0;
+        double v[BS];
+        if ((int)threadIdx.x < nr) {
+            i = __ldg(order + t0 + threadIdx.x);
+#pragma unroll
+            for (int e = 0; e < BS; e++) v[e] = BACKWARD ? x[(size_t)i * BS + e] : b[(size_t)i * BS + e];
+        }
+        stream_chunk_products<BS, 4>(t0, nr, ptrT, col, fv, val_block_offset, x, s_rp, s_prod);
+        if ((int)threadIdx.x < nr) {
+            double acc[BS];
+            stream_row_sum<BS>(threadIdx.x, s_rp, s_prod, acc);
+#pragma unroll
+            for (int e = 0; e < BS; e++) v[e] -= acc[e];
+            if (BACKWARD) {
+                double d[BS * BS], out[BS];
+#pragma unroll
+                for (int q = 0; q < BS * BS; q++) d[q] = __ldg(dinv + (size_t)i * BS * BS + q);
+                blk_mulvec<BS>(d, v, out);
+#pragma unroll
+                for (int e = 0; e < BS; e++) x[(size_t)i * BS + e] = out[e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < BS; e++) x[(size_t)i * BS + e] = v[e];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int BS>
+static int ilu_apply_stream_t(jb_ilu* F, const double* b, double* x, const double* sc) {
+    jb_ctx* ctx = F->csr->ctx;
+    ProfScope _ps(ctx, JB_PROF_ILU_APPLY);
+    cudaStream_t s = ctx->stream;
+    const size_t smem = (size_t)JB_CHUNK_CAP * BS * sizeof(double);
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        cudaFuncSetAttribute(ilu_sweep_stream_kernel<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(ilu_sweep_stream_kernel<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ilu_sweep_stream_kernel<BS, true>, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    const int cap = ctx->sm_count * per_sm;
+    for (int l = 0; l < F->nlevF; l++) {
+        const int c0 = F->h_levF_chunk[l], c1 = F->h_levF_chunk[l + 1];
+        if (c1 <= c0) continue;
+        ilu_sweep_stream_kernel<BS, false><<<std::min(c1 - c0, cap), 256, smem, s>>>(c0, c1, F->d_chunksF.p, F->d_LptrT.p, F->d_Lcol.p, F->d_fv.p, 0,
+                                                                                     F->d_forder.p, F->d_dinv.p, b, x, sc);
+        JB_CHECK_LAUNCH(ctx);
+    }
+    for (int l = 0; l < F->nlevB; l++) {
+        const int c0 = F->h_levB_chunk[l], c1 = F->h_levB_chunk[l + 1];
+        if (c1 <= c0) continue;
+        ilu_sweep_stream_kernel<BS, true><<<std::min(c1 - c0, cap), 256, smem, s>>>(c0, c1, F->d_chunksB.p, F->d_UptrT.p, F->d_Ucol.p, F->d_fv.p,
+                                                                                    (size_t)(F->nL + F->n), F->d_border.p, F->d_dinv.p, b, x, sc);
+        JB_CHECK_LAUNCH(ctx);
+    }
+    return JB_OK;
+}
+
 template <int BS>
 static int ilu_factor_t(jb_ilu* F) {
     jb_ctx* ctx = F->csr->ctx;
+    ProfScope _ps(ctx, JB_PROF_ILU_FACTOR);
     cudaStream_t s = ctx->stream;
     JB_CUDA(ctx, cudaMemsetAsync(F->d_status.p, 0, sizeof(int32_t), s));
     const i64 total = (F->nL + F->n + F->nU) * BS * BS;
@@ -154,6 +229,7 @@ static int ilu_factor_t(jb_ilu* F) {
 template <int BS>
 static int ilu_apply_t(jb_ilu* F, const double* b, double* x, const double* sc) {
     jb_ctx* ctx = F->csr->ctx;
+    ProfScope _ps(ctx, JB_PROF_ILU_APPLY);
     cudaStream_t s = ctx->stream;
     for (int l = 0; l < F->nlevF; l++) {
         const int32_t t0 = F->h_levF_ptr[l], t1 = F->h_levF_ptr[l + 1];
@@ -182,7 +258,15 @@ int jb_launch_ilu_factor(jb_ilu* F) {
     return JB_ERR_UNSUPPORTED;
 }
 int jb_launch_ilu_apply_sc(jb_ilu* F, const double* d_b, double* d_x, const double* d_sc) {
-    switch (F->bs) {
+    if (F->stream_ok) {
+        switch (F->bs) {
+            case 1: return ilu_apply_stream_t<1>(F, d_b, d_x, d_sc);
+            case 2: return ilu_apply_stream_t<2>(F, d_b, d_x, d_sc);
+            case 3: return ilu_apply_stream_t<3>(F, d_b, d_x, d_sc);
+            case 4: return ilu_apply_stream_t<4>(F, d_b, d_x, d_sc);
+        }
+    }
+    switch (F->bs) {   // fallback: one thread per row (a row longer than the shared-memory tile)
         case 1: return ilu_apply_t<1>(F, d_b, d_x, d_sc);
         case 2: return ilu_apply_t<2>(F, d_b, d_x, d_sc);
         case 3: return ilu_apply_t<3>(F, d_b, d_x, d_sc);

@@ -28,6 +28,23 @@ struct jb_ctx {
     unsigned int* d_counters = nullptr;
     double* d_scalars = nullptr;    // small device scalar scratch (64 doubles)
     double* h_pinned = nullptr;     // pinned host scratch (>= 4096 doubles)
+    // optional per-kernel-class timing with CUDA events on `stream` (bench.py roofline pass)
+    bool prof_on = false;
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
+};
+
+enum { JB_PROF_STATE = 0, JB_PROF_ASSEMBLY = 1, JB_PROF_SPMV = 2, JB_PROF_ILU_FACTOR = 3, JB_PROF_ILU_APPLY = 4, JB_PROF_VECTOR = 5,
+       JB_PROF_NEWTON = 6, JB_PROF_OTHER = 7, JB_PROF_NCLASS = 8 };
+
+void jb_prof_begin(jb_ctx* ctx, int cls);
+void jb_prof_end(jb_ctx* ctx);
+struct ProfScope {
+    jb_ctx* c;
+    ProfScope(jb_ctx* ctx, int cls) : c(ctx) { if (c->prof_on) jb_prof_begin(c, cls); }
+    ~ProfScope() { if (c->prof_on) jb_prof_end(c); }
 };
 
 #define JB_MAX_PARTIALS 2048
@@ -100,7 +117,8 @@ struct jb_csr {
     i64 n, nnzb;
     int bs;
     std::vector<int32_t> h_rowptr, h_colidx, h_diag;  // 0-based
-    DBuf<int32_t> d_rowptr, d_colidx, d_diag;
+    std::vector<int32_t> h_chunks;                    // row-chunk boundaries for the stream kernels (empty: fallback)
+    DBuf<int32_t> d_rowptr, d_colidx, d_diag, d_chunks;
     DBuf<double> d_val;
 };
 
@@ -139,6 +157,11 @@ struct jb_ilu {
     std::vector<int32_t> h_Lstart, h_Lend, h_Ustart, h_Uend;      // per row, offsets into L / U storage
     std::vector<int32_t> h_Lcol, h_Ucol, h_Lmap, h_Umap, h_Dmap;  // storage order
     std::vector<int32_t> h_upd_ptr, h_upd_tgt, h_upd_src;
+    std::vector<int32_t> h_LptrT, h_UptrT;            // entry offsets per stored row (level order), n+1 each
+    std::vector<int32_t> h_chunksF, h_chunksB;        // stream-kernel chunks (stored-row boundaries), never across a level
+    std::vector<int32_t> h_levF_chunk, h_levB_chunk;  // first chunk of each level (nlev+1)
+    bool stream_ok = false;
+    DBuf<int32_t> d_LptrT, d_UptrT, d_chunksF, d_chunksB;
     // device
     DBuf<int32_t> d_forder, d_border, d_Lstart, d_Lend, d_Ustart, d_Uend, d_Lcol, d_Ucol, d_Lmap, d_Umap, d_Dmap;
     DBuf<int32_t> d_upd_ptr, d_upd_tgt, d_upd_src;

@@ -10,14 +10,16 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// NaN-propagating max: a non-finite residual must reach the host (fmax would drop the NaN)
+__device__ __forceinline__ double nan_max(double a, double b) { return (a != a) ? a : ((b != b) ? b : fmax(a, b)); }
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = nan_max(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 
 struct OpSum { __device__ static double ident() { return 0.0; } __device__ static double warp(double v) { return warp_sum(v); } __device__ static double comb(double a, double b) { return a + b; } };
-struct OpMax { __device__ static double ident() { return 0.0; } __device__ static double warp(double v) { return warp_max(v); } __device__ static double comb(double a, double b) { return fmax(a, b); } };
+struct OpMax { __device__ static double ident() { return 0.0; } __device__ static double warp(double v) { return warp_max(v); } __device__ static double comb(double a, double b) { return nan_max(a, b); } };
 
 // Reduce NR values over the CTA; result valid in thread 0. BLOCK must be a multiple of 32, <= 1024.
 template <int NR, class Op>

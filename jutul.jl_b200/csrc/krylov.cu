@@ -196,8 +196,10 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
         if (rc != JB_OK) return rc;
         rin = K->r.p;
     }
+    if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
     bicg_init_kernel<<<g, 256, 0, st>>>(m, d_b, rin, K->r.p, K->p.p, K->x.p, K->v.p, K->s.p, sc, K->d_hist.p, ctx->d_partials, ctx->d_counters);
     JB_CHECK_LAUNCH(ctx);
+    if (ctx->prof_on) jb_prof_end(ctx);
     JB_CUDA(ctx, cudaMemcpyAsync(K->h_flags, sc, KS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
     JB_CUDA(ctx, cudaEventRecord(K->ev[0], st));
 
@@ -221,11 +223,15 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
         } else {
             rc = jb_launch_spmv_dots(A, yv, K->q.p, JB_DOT_NONE, nullptr, nullptr); if (rc != JB_OK) return rc;
             rc = jb_launch_ilu_apply_sc(F, K->q.p, K->v.p, sc); if (rc != JB_OK) return rc;
+            if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
             bicg_dot_kernel<JB_DOT_CV><<<g, 256, 0, st>>>(m, sc, K->v.p, d_b, ctx->d_partials, ctx->d_counters);
             JB_CHECK_LAUNCH(ctx);
+            if (ctx->prof_on) jb_prof_end(ctx);
         }
+        if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
         bicg_update1_kernel<<<g, 256, 0, st>>>(m, sc, K->r.p, K->v.p, yv, K->s.p, K->x.p);
         JB_CHECK_LAUNCH(ctx);
+        if (ctx->prof_on) jb_prof_end(ctx);
         const double* zv = K->s.p;
         if (right) { rc = jb_launch_ilu_apply_sc(F, K->s.p, K->z.p, sc); if (rc != JB_OK) return rc; zv = K->z.p; }
         if (!left) {
@@ -234,22 +240,30 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
         } else {
             rc = jb_launch_spmv_dots(A, zv, K->q.p, JB_DOT_NONE, nullptr, nullptr); if (rc != JB_OK) return rc;
             rc = jb_launch_ilu_apply_sc(F, K->q.p, K->t.p, sc); if (rc != JB_OK) return rc;
+            if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
             bicg_dot_kernel<JB_DOT_TS_TT><<<g, 256, 0, st>>>(m, sc, K->t.p, K->s.p, ctx->d_partials, ctx->d_counters);
             JB_CHECK_LAUNCH(ctx);
+            if (ctx->prof_on) jb_prof_end(ctx);
         }
+        if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
         bicg_update2_kernel<<<g, 256, 0, st>>>(m, sc, K->s.p, K->t.p, zv, d_b, K->x.p, K->r.p, K->d_hist.p, K->hist_cap, ctx->d_partials,
                                                ctx->d_counters);
         JB_CHECK_LAUNCH(ctx);
+        if (ctx->prof_on) jb_prof_end(ctx);
+        if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
         bicg_update3_kernel<<<g, 256, 0, st>>>(m, sc, K->r.p, K->v.p, K->p.p);
         JB_CHECK_LAUNCH(ctx);
+        if (ctx->prof_on) jb_prof_end(ctx);
         const int slot = it & 1;
         JB_CUDA(ctx, cudaMemcpyAsync(K->h_flags + slot * KS_SIZE, sc, KS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
         JB_CUDA(ctx, cudaEventRecord(K->ev[slot], st));
         enq = it;
     }
     (void)enq;
+    if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
     negate_kernel<<<g, 256, 0, st>>>(m, K->x.p, d_dx);   // dx = -x (update_dx_from_vector!)
     JB_CHECK_LAUNCH(ctx);
+    if (ctx->prof_on) jb_prof_end(ctx);
     JB_CUDA(ctx, cudaMemcpyAsync(K->h_flags + 3 * KS_SIZE, sc, KS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
     JB_CUDA(ctx, cudaStreamSynchronize(st));
     const double* f = K->h_flags + 3 * KS_SIZE;

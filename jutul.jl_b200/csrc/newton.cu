@@ -176,6 +176,7 @@ static int sgrid(jb_ctx* ctx, i64 n) {
 
 int jb_launch_update_scalar(jb_ctx* ctx, double* d_v, const double* d_dx, i64 stride, i64 n, double w, double abs_max, double rel_max,
                             double minv, double maxv, double scale) {
+    ProfScope _ps(ctx, JB_PROF_NEWTON);
     update_scalar_kernel<<<sgrid(ctx, n), 256, 0, ctx->stream>>>(n, d_v, d_dx, stride, w, abs_max, rel_max, minv, maxv, scale);
     JB_CHECK_LAUNCH(ctx);
     return JB_OK;
@@ -185,12 +186,14 @@ int jb_launch_update_pair(jb_ctx* ctx, double* d_s, const double* d_dx, i64 stri
     maxval = maxval - 2 * minval;
     maxval = fmin(1 - minval, maxval);
     minval = fmax(minval, maxval - 1);
+    ProfScope _ps(ctx, JB_PROF_NEWTON);
     update_pair_kernel<<<sgrid(ctx, n), 256, 0, ctx->stream>>>(n, d_s, d_dx, stride, w, abs_max, minval, maxval);
     JB_CHECK_LAUNCH(ctx);
     return JB_OK;
 }
 int jb_launch_maxabs_rows(jb_ctx* ctx, const double* d_r, int bs, i64 n, double* d_out) {
     const int g = sgrid(ctx, n);
+    ProfScope _ps(ctx, JB_PROF_NEWTON);
     switch (bs) {
         case 1: maxabs_rows_kernel<1><<<g, 256, 0, ctx->stream>>>(n, d_r, d_out, ctx->d_partials, ctx->d_counters); break;
         case 2: maxabs_rows_kernel<2><<<g, 256, 0, ctx->stream>>>(n, d_r, d_out, ctx->d_partials, ctx->d_counters); break;

@@ -11,6 +11,7 @@
 #include "jb_internal.cuh"
 #include "jb_krylov_scalars.cuh"
 #include "jb_reduce.cuh"
+#include "jb_stream.cuh"
 
 template <int BS> struct BlockLoad;
 template <> struct BlockLoad<1> {
@@ -103,9 +104,69 @@ __global__ void __launch_bounds__(256) spmv_kernel(i64 n, const int32_t* __restr
     }
 }
 
+// ---- row-chunk stream form (default): see jb_stream.cuh -------------------------------------------------
+template <int BS, int MODE>
+__global__ void __launch_bounds__(256) spmv_stream_kernel(int nchunks, const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ rowptr,
+                                                          const int32_t* __restrict__ colidx, const double* __restrict__ val,
+                                                          const double* __restrict__ x, double* __restrict__ y, double alpha, double beta,
+                                                          const double* __restrict__ u, double* sc, double* partials, unsigned int* counter) {
+    if (MODE != JB_DOT_NONE) {
+        if (sc[KS_DONE] != 0.0) return;
+    }
+    __shared__ int32_t s_rp[JB_CHUNK_ROWS + 1];
+    extern __shared__ double s_prod[];
+    double d0 = 0.0, d1 = 0.0;
+    for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const int t0 = __ldg(chunk_ptr + c), nr = __ldg(chunk_ptr + c + 1) - t0;
+        stream_chunk_products<BS, 4>(t0, nr, rowptr, colidx, val, 0, x, s_rp, s_prod);
+        if ((int)threadIdx.x < nr) {
+            const size_t row = (size_t)t0 + threadIdx.x;
+            double acc[BS];
+            stream_row_sum<BS>(threadIdx.x, s_rp, s_prod, acc);
+#pragma unroll
+            for (int e = 0; e < BS; e++) {
+                double v = alpha * acc[e];
+                if (beta != 0.0) v += beta * y[row * BS + e];
+                y[row * BS + e] = v;
+                if (MODE == JB_DOT_CV) d0 = fma(__ldg(u + row * BS + e), v, d0);
+                if (MODE == JB_DOT_TS_TT) { d0 = fma(v, __ldg(u + row * BS + e), d0); d1 = fma(v, v, d1); }
+            }
+        }
+        __syncthreads();
+    }
+    if (MODE == JB_DOT_CV) {
+        double r[1] = {d0};
+        grid_reduce<1, OpSum>(r, partials, counter, [=](double(&t)[1]) { sc[KS_ALPHA] = sc[KS_RHO] / t[0]; });
+    } else if (MODE == JB_DOT_TS_TT) {
+        double r[2] = {d0, d1};
+        grid_reduce<2, OpSum>(r, partials, counter, [=](double(&t)[2]) { sc[KS_OMEGA] = t[0] / t[1]; });
+    }
+}
+
+template <int BS, int MODE>
+static int launch_spmv_stream(jb_csr* A, double alpha, const double* x, double beta, double* y, const double* u, double* sc) {
+    jb_ctx* ctx = A->ctx;
+    ProfScope _ps(ctx, JB_PROF_SPMV);
+    const int nchunks = (int)A->h_chunks.size() - 1;
+    const size_t smem = (size_t)JB_CHUNK_CAP * BS * sizeof(double);
+    static int per_sm = 0;   // resident CTAs per SM: the persistent grid is sized to exactly one wave
+    if (per_sm == 0) {
+        cudaFuncSetAttribute(spmv_stream_kernel<BS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_stream_kernel<BS, MODE>, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    int cap = ctx->sm_count * per_sm;
+    if (MODE != JB_DOT_NONE && cap > JB_MAX_PARTIALS) cap = JB_MAX_PARTIALS;
+    const int grid = std::max(1, std::min(nchunks, cap));
+    spmv_stream_kernel<BS, MODE><<<grid, 256, smem, ctx->stream>>>(nchunks, A->d_chunks.p, A->d_rowptr.p, A->d_colidx.p, A->d_val.p, x, y, alpha,
+                                                                  beta, u, sc, ctx->d_partials, ctx->d_counters);
+    JB_CHECK_LAUNCH(ctx);
+    return JB_OK;
+}
+
 template <int BS, int LPR, int MODE>
 static int launch_spmv_t(jb_csr* A, double alpha, const double* x, double beta, double* y, const double* u, double* sc) {
     jb_ctx* ctx = A->ctx;
+    ProfScope _ps(ctx, JB_PROF_SPMV);
     const int threads = 256;
     const i64 rows_per_cta = threads / LPR;
     i64 want = (A->n + rows_per_cta - 1) / rows_per_cta;
@@ -120,6 +181,15 @@ static int launch_spmv_t(jb_csr* A, double alpha, const double* x, double beta, 
 
 template <int MODE>
 static int launch_spmv_mode(jb_csr* A, double alpha, const double* x, double beta, double* y, const double* u, double* sc) {
+    if (!A->h_chunks.empty()) {
+        switch (A->bs) {
+            case 1: return launch_spmv_stream<1, MODE>(A, alpha, x, beta, y, u, sc);
+            case 2: return launch_spmv_stream<2, MODE>(A, alpha, x, beta, y, u, sc);
+            case 3: return launch_spmv_stream<3, MODE>(A, alpha, x, beta, y, u, sc);
+            case 4: return launch_spmv_stream<4, MODE>(A, alpha, x, beta, y, u, sc);
+        }
+    }
+    // fallback (a row longer than the shared-memory tile): lanes-per-row kernel,
     // lanes per row from the average row length (7 for a hex-like TPFA stencil)
     const double avg = (double)A->nnzb / (double)A->n;
     const int lpr = avg <= 2.5 ? 2 : (avg <= 5.0 ? 4 : (avg <= 12.0 ? 8 : 16));

@@ -77,7 +77,7 @@ def unstructured_hex(nx, ny, nz, cell_size=(10.0, 10.0, 2.0), seed=DEFAULT_SEED,
     pv = cells_to_new(poro * vol)
     inj = int(cell_perm[0]) + 1
     prod = int(cell_perm[nc - 1]) + 1
-    q = 0.5
+    q = 0.02   # kg/s: < 10 % of a cell's fluid mass per day, so the producer cell does not dry out within a step
     return dict(
         nx=nx, ny=ny, nz=nz, nc=nc, nf=nf, N=N, Tf=Tf, gdz=gdz, pv=pv, z=z_new,
         p0=cells_to_new(p_init), sw0=cells_to_new(sw), cell_perm=cell_perm, face_perm=face_perm,

@@ -81,7 +81,8 @@ def test_twophase_residual_hook_and_no_sources(J, O, ctx):
     sim, nz, r, p, sw, M0 = _assemble_both(J, O, ctx, w, s, "cells", sources=False)
     r_asm = sim.r.get()
     sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r, variant="residual")
-    assert np.array_equal(sim.r.get(), r_asm)      # float-only residual == AD-assembly residual (helper.jl:3-18)
+    # float-only residual ≈ AD-assembly residual (test/test_systems/helper.jl:3-18 uses ≈ as well)
+    assert np.allclose(sim.r.get(), r_asm, rtol=1e-12, atol=1e-13 * np.abs(r_asm).max())
     assert np.abs(r_asm - r).max() <= 1e-11 * np.abs(r).max()
 
 
@@ -185,17 +186,22 @@ def test_bicgstab_matches_oracle(J, O, ctx, side, rtol):
     ilu = O.ILU0(n, 2, s["rowptr"], s["colidx"]); ilu.factor(nz)
     x, st_o, its_o, hist_o = O.bicgstab(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, side=side, rtol=rtol, itmax=200)
     assert ok and st == 0 and st_o == 0
-    assert abs(its - its_o) <= 1
-    m = min(len(hist), len(hist_o)) - 1
+    # BiCGStab is not contractive: last-bit differences (FMA, reduction order) grow along the iteration, so the
+    # count agrees to a few iterations and the histories agree tightly early on, loosely later.
+    assert abs(its - its_o) <= max(2, its_o // 10)
     assert np.allclose(hist[0], hist_o[0], rtol=1e-12)
-    assert np.allclose(hist[:m], hist_o[:m], rtol=1e-3)     # iteration-by-iteration residual history
+    m = min(len(hist), len(hist_o), 8)
+    assert np.allclose(hist[:m], hist_o[:m], rtol=1e-6)     # iteration-by-iteration residual history
     dx = sim.dx.get()
-    assert np.linalg.norm(dx + x) <= 10 * rtol * np.linalg.norm(x)
-    # direct-solve cross-check of the GPU answer itself
-    import scipy.sparse.linalg as spla
     A = to_scipy(n, 2, s["rowptr"], s["colidx"], nz)
+    if side == "right":   # history = true residual: the GPU's final claim must hold for its own x
+        assert abs(np.linalg.norm(r + A @ dx) - hist[-1]) <= 1e-3 * hist[-1] + 1e-14 * hist[0]
+    assert np.linalg.norm(r + A @ dx) <= 50 * rtol * np.linalg.norm(r)
+    # both answers solve the same system: compare through a direct solve, error bounded by cond * rtol
+    import scipy.sparse.linalg as spla
     xd = spla.spsolve(A.tocsc(), r)
-    assert np.linalg.norm(dx + xd) <= 50 * rtol * np.linalg.norm(xd)
+    eg = np.linalg.norm(dx + xd) / np.linalg.norm(xd); eo = np.linalg.norm(x - xd) / np.linalg.norm(xd)
+    assert eg <= max(10 * eo, 1e3 * rtol)
 
 
 def test_bicgstab_edge_cases(J, O, ctx):
@@ -205,7 +211,7 @@ def test_bicgstab_edge_cases(J, O, ctx):
     kry = J.GenericKrylov(sim.jac, "bicgstab", sim.prec)
     ok, its, hist, st = J.linear_solve(kry, zero, sim.dx)
     assert ok and its == 0 and np.all(sim.dx.get() == 0)
-    kry2 = J.GenericKrylov(sim.jac, "bicgstab", None, relative_tolerance=1e-14, max_iterations=2)
+    kry2 = J.GenericKrylov(sim.jac, "bicgstab", sim.prec, relative_tolerance=1e-14, max_iterations=2)
     ok, its, hist, st = J.linear_solve(kry2, sim.r, sim.dx)
     assert (not ok) and st == J.JB_NOT_CONVERGED and its == 2 and len(hist) == 3
     kry3 = J.GenericKrylov(sim.jac, "bicgstab", sim.prec, relative_tolerance=1e-1, min_iterations=6)
@@ -366,14 +372,17 @@ def test_full_size_properties(J, O, ctx):
     conservation: column sums of the flux part of the Jacobian vanish, residual sums to accumulation + sources."""
     w = J.workloads.unstructured_hex(100, 100, 100)
     n = w["nc"]
-    sim = J.TwoPhaseSimulator(ctx, w["N"], n, w["Tf"], w["gdz"], w["pv"], w["params"], rtol=1e-6)
+    sim = J.TwoPhaseSimulator(ctx, w["N"], n, w["Tf"], w["gdz"], w["pv"], w["params"], rtol=1e-6, max_linear_iterations=600)
     sim.set_forces(w["src_cells"], w["src_vals"])
     sim.set_state(w["p0"], w["sw0"])
+    sim.p.set(w["p0"] * (1 + 1e-4 * np.sin(np.arange(n))))
     sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r)
     r = sim.r.get()
     # fluxes cancel pairwise: sum of residual = sum of accumulation (0 at state0) + sources
+    M1 = ctx.zeros(2 * n); sim.law.total_masses(sim.p, sim.s, M1)
+    acc = ((M1.get() - sim.M0.get()) / w["dt"]).reshape(n, 2).sum(axis=0)
     tot = r.reshape(n, 2).sum(axis=0)
-    assert np.allclose(tot, w["src_vals"].sum(axis=0), atol=1e-6 * np.abs(r).max())
+    assert np.allclose(tot, acc + w["src_vals"].sum(axis=0), atol=1e-9 * np.abs(r).sum())
     rng = np.random.default_rng(0)
     x1, x2 = rng.standard_normal(2 * n), rng.standard_normal(2 * n)
     d1, d2, d3 = ctx.transfer(x1), ctx.transfer(x2), ctx.transfer(2.0 * x1 - 3.0 * x2)
