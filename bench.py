@@ -111,7 +111,8 @@ def run_b200(args):
     ctx = J.B200Context(local_rank)
     t_setup = time.perf_counter()
     sim = J.TwoPhaseSimulator(ctx, w["N"], nc, w["Tf"], w["gdz"], w["pv"], w["params"], rtol=args.rtol,
-                              max_linear_iterations=args.max_linear_iterations, tolerance=args.tolerance)
+                              max_linear_iterations=args.max_linear_iterations, tolerance=args.tolerance,
+                              ordering=None if args.ordering == "given" else args.ordering)
     t_setup = time.perf_counter() - t_setup
     sim.set_forces(w["src_cells"], w["src_vals"])
     sim.set_state(w["p0"], w["sw0"])
@@ -171,7 +172,7 @@ def run_b200(args):
 
     # ---- e2e: the reference-facing perform_step call with HOST (pinned-size) buffers: H2D of p, s, M0 and D2H of p, s
     #      inside every Newton iteration
-    p0_h, s0_h, M0_h = p_init.get(), s_init.get(), sim.M0.get()
+    p0_h, s0_h, M0_h = sim.download(p_init), sim.download(s_init, 2), sim.download(sim.M0, 2)   # caller's numbering
     p_h, s_h = p0_h.copy(), s0_h.copy()
     h2d = d2h = 0
 
@@ -215,7 +216,9 @@ def run_b200(args):
                    "cells": nc, "faces": nf, "block_size": 2, "linear_rtol": args.rtol, "max_linear_iterations": args.max_linear_iterations,
                    "newton_tolerance": args.tolerance,
                    "l2_policy": "inputs larger than L2 (Jacobian values %.2f GB); no flush needed" % ((nc + 2 * nf) * 32 / 1e9),
-                   "parallelism": "1 GPU", "setup_seconds": t_setup},
+                   "parallelism": "1 GPU", "setup_seconds": t_setup,
+                   "cell_ordering": args.ordering + (f" ({sim.ncolors} colours = ILU levels)" if sim.ncolors else ""),
+                   "ilu": sim.prec.info()},
         "newton_iterations_per_step": n_newton / max(args.steps, 1), "converged": all(r[0] for r in results),
         "linear_iterations_per_newton": float(np.mean(lin_its)) if lin_its else None, "linear_iterations": results[0][2],
         "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "kernels": kernels,
@@ -347,6 +350,8 @@ def main():
     ap.add_argument("--rtol", type=float, default=1e-3, help="linear relative tolerance (Jutul default 1e-3)")
     ap.add_argument("--max-linear-iterations", type=int, default=100, help="Jutul default 100")
     ap.add_argument("--tolerance", type=float, default=1e-3, help="Newton max|r| tolerance (Jutul default 1e-3)")
+    ap.add_argument("--ordering", default="multicolor", choices=["multicolor", "given"],
+                    help="device cell numbering: multicolor (internal renumbering, default) or given (the mesh's own numbering)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reference-budget", type=float, default=150.0, help="wall-clock budget (s) of the --impl reference timed region")
     args = ap.parse_args()

@@ -406,6 +406,39 @@ def partition(N, num_coarse, weights=None, nc=None, partitioner="metis"):
     return part
 
 
+def multicolor_ordering(N, nc):
+    """B200-friendly cell renumbering (setup, host): Cuthill-McKee locality + greedy colouring, numbered colour
+    by colour. Returns (perm, ncolors) with perm[c] = new 1-based label of (1-based) cell c+1."""
+    lib = _lib.load()
+    N = np.ascontiguousarray(N, dtype=i64)
+    perm = np.zeros(int(nc), dtype=i64)
+    ncol = C.c_int64(0)
+    check(lib.jb_order_multicolor(int(nc), N.shape[0], _pi(N), _pi(perm), C.byref(ncol)), None, "jb_order_multicolor")
+    return perm, ncol.value
+
+
+class CellPermutation(_Handle):
+    """Caller <-> device cell numbering, applied on the device."""
+
+    _destroy = "jb_perm_destroy"
+
+    def __init__(self, ctx, perm):
+        self.ctx = ctx
+        self.perm = np.ascontiguousarray(perm, dtype=i64)
+        self.n = self.perm.shape[0]
+        h = C.c_void_p()
+        check(ctx.lib.jb_perm_create(ctx.h, _pi(self.perm), self.n, C.byref(h)), ctx.h, "jb_perm_create")
+        self.h = h
+
+    def to_device(self, src, dst, bs=1):
+        check(self.ctx.lib.jb_perm_apply(self.h, _dp(src), _dp(dst), bs, 0), self.ctx.h, "jb_perm_apply")
+        return dst
+
+    def to_caller(self, src, dst, bs=1):
+        check(self.ctx.lib.jb_perm_apply(self.h, _dp(src), _dp(dst), bs, 1), self.ctx.h, "jb_perm_apply")
+        return dst
+
+
 class DeviceProfile:
     """Per-kernel-class device times (CUDA events on the context's stream)."""
 

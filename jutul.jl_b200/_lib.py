@@ -81,6 +81,11 @@ PROTOTYPES = {
     "jb_maxabs_rows": (I32, [P, P, I32, I64, PF64]),
     "jb_partition_metis": (I32, [I64, I64, PI64, PF64, I64, PI64]),
     "jb_partition_linear": (I32, [I64, I64, PI64]),
+    "jb_order_multicolor": (I32, [I64, I64, PI64, PI64, PI64]),
+    "jb_perm_create": (I32, [P, PI64, I64, PP]),
+    "jb_perm_destroy": (I32, [P]),
+    "jb_perm_apply": (I32, [P, P, P, I32, I32]),
+    "jb_twophase_set_permutation": (I32, [P, P]),
     "jb_twophase_perform_step_host": (I32, [P, P, P, PF64, PF64, PF64, F64, F64, F64, F64, I32, F64, F64, PF64, PI32, PI32]),
 }
 

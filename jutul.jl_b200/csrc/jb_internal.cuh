@@ -131,8 +131,16 @@ struct jb_tpfa {
     DBuf<int32_t> d_hf_pos, d_hf_rowpos;
 };
 
+struct jb_perm {
+    jb_ctx* ctx;
+    i64 n;
+    DBuf<int32_t> d_perm;   // device label (0-based) of caller cell i
+};
+
 struct jb_twophase {
     jb_tpfa* t;
+    jb_perm* perm = nullptr;          // optional caller <-> device renumbering for the host-buffer entry points
+    DBuf<double> d_stage;             // staging for permuted host transfers (2 x nc)
     double params[7];
     DBuf<double> d_hf_T, d_hf_sgdz;   // per half-face: T_f and sign*gdz_f
     DBuf<double> d_face_T, d_face_gdz;  // per face (variant B)

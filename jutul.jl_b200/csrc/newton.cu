@@ -336,3 +336,59 @@ int32_t jb_poisson_assemble(jb_tpfa* t, const double* d_K, const double* d_U, co
 }
 
 }  // extern "C"
+
+// ---- cell renumbering between the caller's numbering and the device numbering (jb_order_multicolor) ----
+template <int BS>
+__global__ void __launch_bounds__(256) permute_kernel(i64 n, const int32_t* __restrict__ perm, const double* __restrict__ src,
+                                                      double* __restrict__ dst, int to_caller) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) {
+        const size_t j = (size_t)__ldg(perm + i);
+#pragma unroll
+        for (int e = 0; e < BS; e++) {
+            if (to_caller) dst[(size_t)i * BS + e] = __ldg(src + j * BS + e);   // caller[i] = device[perm[i]]
+            else dst[j * BS + e] = __ldg(src + (size_t)i * BS + e);             // device[perm[i]] = caller[i]
+        }
+    }
+}
+
+int jb_launch_permute(jb_ctx* ctx, const int32_t* d_perm, i64 n, int bs, const double* d_src, double* d_dst, int to_caller) {
+    ProfScope _ps(ctx, JB_PROF_NEWTON);
+    const int g = sgrid(ctx, n);
+    switch (bs) {
+        case 1: permute_kernel<1><<<g, 256, 0, ctx->stream>>>(n, d_perm, d_src, d_dst, to_caller); break;
+        case 2: permute_kernel<2><<<g, 256, 0, ctx->stream>>>(n, d_perm, d_src, d_dst, to_caller); break;
+        case 3: permute_kernel<3><<<g, 256, 0, ctx->stream>>>(n, d_perm, d_src, d_dst, to_caller); break;
+        case 4: permute_kernel<4><<<g, 256, 0, ctx->stream>>>(n, d_perm, d_src, d_dst, to_caller); break;
+        default: return JB_ERR_UNSUPPORTED;
+    }
+    JB_CHECK_LAUNCH(ctx);
+    return JB_OK;
+}
+
+extern "C" {
+
+int32_t jb_perm_create(jb_ctx* ctx, const int64_t* perm, int64_t n, jb_perm** out) {
+    if (!ctx || !perm || !out || n < 1) return JB_ERR_ARG;
+    jb_perm* P = new jb_perm();
+    P->ctx = ctx; P->n = n;
+    std::vector<int32_t> h(n);
+    std::vector<char> seen(n, 0);
+    for (i64 i = 0; i < n; i++) {
+        if (perm[i] < 1 || perm[i] > n || seen[perm[i] - 1]) { delete P; JB_FAIL(ctx, JB_ERR_ARG, "jb_perm_create: not a permutation of 1..n"); }
+        seen[perm[i] - 1] = 1;
+        h[i] = (int32_t)(perm[i] - 1);
+    }
+    if (P->d_perm.upload(h, ctx->stream) != cudaSuccess) { delete P; JB_FAIL(ctx, JB_ERR_ALLOC, "jb_perm_create: allocation failed"); }
+    *out = P;
+    return JB_OK;
+}
+int32_t jb_perm_destroy(jb_perm* P) { delete P; return JB_OK; }
+int32_t jb_perm_apply(jb_perm* P, const double* d_src, double* d_dst, int32_t bs, int32_t to_caller) {
+    if (!P || !d_src || !d_dst || d_src == d_dst) return JB_ERR_ARG;
+    int rc = jb_launch_permute(P->ctx, P->d_perm.p, P->n, bs, d_src, d_dst, to_caller);
+    if (rc != JB_OK) return rc;
+    JB_CUDA(P->ctx, cudaStreamSynchronize(P->ctx->stream));
+    return JB_OK;
+}
+
+}  // extern "C"

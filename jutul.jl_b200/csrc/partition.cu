@@ -73,3 +73,75 @@ int32_t jb_partition_metis(int64_t nc, int64_t nf, const int64_t* N, const doubl
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Multicolour cell ordering for the GPU ILU(0) sweeps (setup-time, host). The reference lets the user renumber
+// the local system before factorising (SymRCM option of the distributed path,
+// ext/JutulPartitionedArraysExt/utils.jl:58-89); ILU(0) then eliminates in the new natural order. Here the
+// order is chosen for the B200: cells are visited breadth-first from a pseudo-peripheral cell (Cuthill-McKee
+// locality), greedily coloured in that order, and numbered colour by colour, breadth-first rank inside a colour.
+// Rows of one colour are mutually independent, so the triangular sweeps have as many levels as colours (2 on
+// bipartite hex-like grids) and every level is one contiguous, locality-ordered range of rows.
+// perm[c_old] (1-based) = new label (1-based).
+extern "C" int32_t jb_order_multicolor(int64_t nc, int64_t nf, const int64_t* N, int64_t* perm, int64_t* ncolors) {
+    if (!N || !perm || nc < 1 || nf < 0) return JB_ERR_ARG;
+    std::vector<i64> xadj(nc + 1, 0);
+    for (i64 f = 0; f < nf; f++) {
+        i64 l = N[2 * f] - 1, r = N[2 * f + 1] - 1;
+        if (l < 0 || l >= nc || r < 0 || r >= nc) return JB_ERR_ARG;
+        if (l == r) continue;
+        xadj[l + 1]++; xadj[r + 1]++;
+    }
+    for (i64 c = 0; c < nc; c++) xadj[c + 1] += xadj[c];
+    std::vector<int32_t> adj(xadj[nc]);
+    {
+        std::vector<i64> cur(xadj.begin(), xadj.end() - 1);
+        for (i64 f = 0; f < nf; f++) {
+            i64 l = N[2 * f] - 1, r = N[2 * f + 1] - 1;
+            if (l == r) continue;
+            adj[cur[l]++] = (int32_t)r; adj[cur[r]++] = (int32_t)l;
+        }
+    }
+    std::vector<int32_t> order; order.reserve(nc);
+    std::vector<int32_t> dist(nc, -1);
+    auto bfs = [&](int32_t root, std::vector<int32_t>& out) {   // appends the component of root in BFS order
+        size_t head = out.size();
+        out.push_back(root); dist[root] = 0;
+        while (head < out.size()) {
+            int32_t v = out[head++];
+            for (i64 e = xadj[v]; e < xadj[v + 1]; e++) {
+                int32_t u = adj[e];
+                if (dist[u] < 0) { dist[u] = dist[v] + 1; out.push_back(u); }
+            }
+        }
+    };
+    for (i64 s = 0; s < nc; s++) {
+        if (dist[s] >= 0) continue;
+        // pseudo-peripheral start: farthest cell of a first sweep
+        std::vector<int32_t> comp;
+        bfs((int32_t)s, comp);
+        int32_t far = comp.back();
+        for (int32_t v : comp) dist[v] = -1;
+        bfs(far, order);
+    }
+    std::vector<int32_t> color(nc, -1);
+    int32_t ncol = 0;
+    std::vector<char> used;
+    for (int32_t v : order) {
+        used.assign(ncol + 1, 0);
+        for (i64 e = xadj[v]; e < xadj[v + 1]; e++) {
+            int32_t cu = color[adj[e]];
+            if (cu >= 0) used[cu] = 1;
+        }
+        int32_t c = 0;
+        while (c < ncol && used[c]) c++;
+        color[v] = c;
+        if (c == ncol) ncol++;
+    }
+    std::vector<i64> start(ncol + 1, 0);
+    for (i64 v = 0; v < nc; v++) start[color[v] + 1]++;
+    for (int32_t c = 0; c < ncol; c++) start[c + 1] += start[c];
+    for (int32_t v : order) perm[v] = ++start[color[v]];     // BFS rank inside the colour, 1-based
+    if (ncolors) *ncolors = ncol;
+    return JB_OK;
+}

@@ -24,14 +24,34 @@ class TwoPhaseSimulator:
 
     def __init__(self, ctx, N, nc, Tf, gdz, pv, params=None, partition=None, linear_solver="bicgstab",
                  rtol=1e-3, atol=None, max_linear_iterations=100, tolerance=1e-3,
-                 max_nonlinear_iterations=15, dp_abs_max=None, ds_abs_max=0.2, precond_side="right"):
+                 max_nonlinear_iterations=15, dp_abs_max=None, ds_abs_max=0.2, precond_side="right", ordering=None):
+        """ordering: None keeps the caller's cell numbering on the device (ILU(0) eliminates in the caller's order,
+        the reference's semantics for the mesh as given); "multicolor" renumbers internally (jb_order_multicolor) —
+        all arrays crossing this class stay in the caller's numbering; an explicit permutation (new 1-based label per
+        cell) is accepted too."""
         J = _pkg()
         self.ctx, self.nc = ctx, int(nc)
+        self.perm = None
+        self.ncolors = None
+        N = np.ascontiguousarray(N, dtype=np.int64)
+        if ordering is not None:
+            if isinstance(ordering, str):
+                assert ordering == "multicolor"
+                perm, self.ncolors = J.multicolor_ordering(N, nc)
+            else:
+                perm = np.ascontiguousarray(ordering, dtype=np.int64)
+            self.perm = J.CellPermutation(ctx, perm)
+            N = perm[N - 1]                                   # relabel the neighbourship (faces keep their numbers)
+            pv = self._cells_to_device_host(pv)
+            if partition is not None:
+                partition = self._cells_to_device_host(np.asarray(partition))
         self.disc = J.TwoPointPotentialFlowHardCoded(ctx, N, nc)
         self.jac = J.tpfa_jacobian(self.disc, 2)
         self.storage = J.ConservationLawTPFAStorage(self.disc, self.jac)
         self.params = J.params_array() if params is None else np.asarray(params, dtype=np.float64)
         self.law = J.TwoPhaseConservationLaw(self.storage, Tf, gdz, pv, self.params)
+        if self.perm is not None:
+            _lib.check(ctx.lib.jb_twophase_set_permutation(self.law.h, self.perm.h), ctx.h, "jb_twophase_set_permutation")
         self.prec = J.ILUZeroPreconditioner(self.jac, partition)
         self.krylov = J.GenericKrylov(self.jac, linear_solver, self.prec, relative_tolerance=rtol, absolute_tolerance=atol,
                                       max_iterations=max_linear_iterations, precond_side=precond_side)
@@ -42,11 +62,38 @@ class TwoPhaseSimulator:
         self.p_prev = ctx.empty(nc); self.s_prev = ctx.empty(2 * nc)
         self.r = ctx.empty(2 * nc); self.dx = ctx.zeros(2 * nc)
 
+    # -- numbering ------------------------------------------------------------------------------
+    def _cells_to_device_host(self, a):
+        """Host-side renumbering of a per-cell array (setup data): out[perm[c]] = a[c]."""
+        a = np.asarray(a)
+        out = np.empty_like(a)
+        out[self.perm.perm - 1] = a
+        return out
+
+    def upload(self, dev, host, bs=1):
+        """Caller-numbered host array -> device array in device numbering."""
+        if self.perm is None:
+            return dev.set(host)
+        tmp = self.ctx.transfer(host)
+        self.perm.to_device(tmp, dev, bs)
+        tmp.free()
+        return dev
+
+    def download(self, dev, bs=1):
+        """Device array -> host array in the caller's numbering."""
+        if self.perm is None:
+            return dev.get()
+        tmp = self.ctx.empty(dev.n)
+        self.perm.to_caller(dev, tmp, bs)
+        out = tmp.get()
+        tmp.free()
+        return out
+
     # -- state handling -------------------------------------------------------------------------
     def set_state(self, p, sw):
         sw = np.asarray(sw, dtype=np.float64)
         s = np.empty((self.nc, 2)); s[:, 0] = sw; s[:, 1] = 1.0 - sw
-        self.p.set(p); self.s.set(s.ravel())
+        self.upload(self.p, p); self.upload(self.s, s.ravel(), 2)
         self.update_before_step()
 
     def update_before_step(self):
@@ -54,9 +101,11 @@ class TwoPhaseSimulator:
         self.law.total_masses(self.p, self.s, self.M0)
 
     def get_state(self):
-        return self.p.get(), self.s.get().reshape(self.nc, 2)[:, 0].copy()
+        return self.download(self.p), self.download(self.s, 2).reshape(self.nc, 2)[:, 0].copy()
 
     def set_forces(self, cells, values):
+        if self.perm is not None and cells is not None and len(cells):
+            cells = self.perm.perm[np.asarray(cells, dtype=np.int64) - 1]
         self.law.apply_forces(cells, values)
 
     # -- one Newton iteration -------------------------------------------------------------------

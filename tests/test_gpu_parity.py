@@ -395,3 +395,85 @@ def test_full_size_properties(J, O, ctx):
     # true residual of the returned increment: |r + J dx| small
     sim.jac.mul(y1, sim.dx)
     assert np.linalg.norm(y1.get() + r) <= 1e-5 * np.linalg.norm(r)
+
+
+# ---------------------------------------------------------------- internal cell renumbering
+def test_multicolor_ordering_properties(J, O, ctx):
+    w, s = _setup(J, O, ctx, (9, 8, 7), True)
+    perm, ncol = J.multicolor_ordering(w["N"], w["nc"])
+    assert sorted(perm.tolist()) == list(range(1, w["nc"] + 1))
+    assert ncol == 2                                   # hex-like grids are bipartite
+    # colours are contiguous label ranges and no face joins two cells of one colour
+    N2 = perm[w["N"] - 1]
+    n0 = int((perm <= 0).sum())
+    sim = J.TwoPhaseSimulator(ctx, w["N"], w["nc"], w["Tf"], w["gdz"], w["pv"], w["params"], ordering="multicolor")
+    info = sim.prec.info()
+    assert info["forward_levels"] == ncol and info["backward_levels"] == ncol
+    lo = np.minimum(N2[:, 0], N2[:, 1]); hi = np.maximum(N2[:, 0], N2[:, 1])
+    split = np.sort(lo)[-1]
+    assert np.all(hi > split) or ncol > 2
+    # device-side permutation round trip
+    x = np.random.default_rng(0).standard_normal(2 * w["nc"])
+    a, b, c = ctx.transfer(x), ctx.zeros(2 * w["nc"]), ctx.zeros(2 * w["nc"])
+    sim.perm.to_device(a, b, 2); sim.perm.to_caller(b, c, 2)
+    assert np.array_equal(c.get(), x)
+    xb = b.get().reshape(-1, 2)
+    assert np.array_equal(xb[perm - 1], x.reshape(-1, 2))
+
+
+def test_reordered_system_matches_oracle_on_renumbered_mesh(J, O, ctx):
+    """Ordering is an input (like the partition): the GPU on the internally renumbered mesh must equal the oracle run on
+    the same renumbered mesh — pattern bit-exact, assembly / ILU / Krylov within the usual tolerances."""
+    w, _ = _setup(J, O, ctx, (9, 8, 7), True)
+    n = w["nc"]
+    perm, ncol = J.multicolor_ordering(w["N"], n)
+    w2 = dict(w)
+    w2["N"] = perm[w["N"] - 1]
+    for k in ("pv", "p0", "sw0"):
+        a = np.empty_like(w[k]); a[perm - 1] = w[k]; w2[k] = a
+    w2["src_cells"] = perm[w["src_cells"] - 1]
+    s2 = oracle_system(O, w2)
+    sim = J.TwoPhaseSimulator(ctx, w["N"], n, w["Tf"], w["gdz"], w["pv"], w["params"], ordering="multicolor", rtol=1e-8,
+                              max_linear_iterations=300)
+    sim.set_forces(w["src_cells"], w["src_vals"])
+    sim.set_state(w["p0"], w["sw0"])
+    rp, ci = sim.jac.pattern()
+    assert np.array_equal(rp, s2["rowptr"]) and np.array_equal(ci, s2["colidx"])
+    conv, err, rep = sim.perform_step(w["dt"])
+    M0 = O.mass_2ph(w2["pv"], w2["params"], w2["p0"], w2["sw0"])
+    nz, r = O.assemble_2ph(s2["hf"], s2["diag_pos"], s2["hf_pos"], w2["Tf"], w2["gdz"], w2["pv"], w2["params"], w2["p0"], w2["sw0"], M0,
+                           w2["dt"], s2["colidx"].shape[0], w2["src_cells"], w2["src_vals"])
+    assert np.abs(sim.r.get() - r).max() <= 1e-11 * np.abs(r).max()
+    assert np.abs(sim.jac.nonzeros() - nz).max() <= 1e-11 * np.abs(nz).max()
+    ilu = O.ILU0(n, 2, s2["rowptr"], s2["colidx"]); ilu.factor(sim.jac.nonzeros())
+    fg, fo = sim.prec.factors(), ilu.get()
+    for k in ("L", "U", "D"):
+        assert np.abs(fg[k] - fo[k]).max() <= 1e-10 * np.abs(fo[k]).max()
+    x, st, its, hist = O.bicgstab(n, 2, s2["rowptr"], s2["colidx"], sim.jac.nonzeros(), sim.r.get(), ilu, rtol=1e-8, itmax=300)
+    assert abs(rep["linear_iterations"] - its) <= max(2, its // 10)
+    assert np.allclose(rep["linear_residuals"][:6], hist[:6], rtol=1e-6)
+
+
+def test_reordering_does_not_change_the_physics(J, O, ctx):
+    """The converged timestep is the same cell by cell with and without the internal renumbering (solver tolerance)."""
+    w, _ = _setup(J, O, ctx, (10, 9, 6), True)
+    out = []
+    for ordering in (None, "multicolor"):
+        sim = J.TwoPhaseSimulator(ctx, w["N"], w["nc"], w["Tf"], w["gdz"], w["pv"], w["params"], rtol=1e-10, tolerance=1e-7,
+                                  max_linear_iterations=400, ordering=ordering)
+        sim.set_forces(w["src_cells"], w["src_vals"])
+        sim.set_state(w["p0"], w["sw0"])
+        ok, reps = sim.solve_ministep(w["dt"])
+        assert ok
+        out.append(sim.get_state())
+    assert np.abs(out[0][0] - out[1][0]).max() <= 1e-8 * np.abs(out[0][0]).max()
+    assert np.abs(out[0][1] - out[1][1]).max() <= 1e-8
+    # host-buffer entry point in the caller's numbering, reordered inside
+    sim.set_state(w["p0"], w["sw0"])
+    p = w["p0"].copy(); sat = np.stack([w["sw0"], 1 - w["sw0"]], axis=1).ravel().copy()
+    M0 = O.mass_2ph(w["pv"], w["params"], w["p0"], w["sw0"])
+    st, conv, its, err = sim.perform_step_host(p, sat, M0, w["dt"])
+    conv2, err2, rep = sim.perform_step(w["dt"])
+    pg, swg = sim.get_state()
+    assert st == 0 and its == rep["linear_iterations"] and np.allclose(err, err2, rtol=1e-12)
+    assert np.array_equal(pg, p) and np.array_equal(swg, sat[0::2])
