@@ -86,6 +86,15 @@ PROTOTYPES = {
     "jb_perm_destroy": (I32, [P]),
     "jb_perm_apply": (I32, [P, P, P, I32, I32]),
     "jb_twophase_set_permutation": (I32, [P, P]),
+    "jb_nccl_unique_id": (I32, [C.c_char_p]),
+    "jb_comm_create": (I32, [P, I32, I32, C.c_char_p, PP]),
+    "jb_comm_destroy": (I32, [P]),
+    "jb_dist_create": (I32, [P, I64, I64, I32, PI32, PI64, PI64, PI64, PP]),
+    "jb_dist_destroy": (I32, [P]),
+    "jb_dist_halo_exchange": (I32, [P, P, I32]),
+    "jb_dist_allreduce": (I32, [P, PF64, I32, I32]),
+    "jb_krylov_set_dist": (I32, [P, P]),
+    "jb_twophase_set_owned": (I32, [P, I64]),
     "jb_twophase_perform_step_host": (I32, [P, P, P, PF64, PF64, PF64, F64, F64, F64, F64, I32, F64, F64, PF64, PI32, PI32]),
 }
 

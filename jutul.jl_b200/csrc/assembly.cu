@@ -272,7 +272,7 @@ int jb_launch_twophase_state(jb_twophase* m, const double* d_p, const double* d_
 int jb_launch_twophase_assemble(jb_twophase* m, const double* d_M0, double dt, double* d_r, bool jac) {
     jb_tpfa* t = m->t;
     jb_ctx* ctx = t->mesh->ctx;
-    const i64 nc = t->mesh->nc;
+    const i64 nc = m->n_assemble >= 0 ? m->n_assemble : t->mesh->nc;   // owned rows only in a distributed run
     constexpr int LPC = 8;
     ProfScope _ps(ctx, JB_PROF_ASSEMBLY);
     const i64 cells_per_cta = 256 / LPC;
@@ -349,6 +349,11 @@ int32_t jb_twophase_create(jb_tpfa* t, const double* Tf, const double* gdz, cons
     return JB_OK;
 }
 int32_t jb_twophase_destroy(jb_twophase* m) { delete m; return JB_OK; }
+int32_t jb_twophase_set_owned(jb_twophase* m, int64_t n_owned) {
+    if (!m || n_owned > m->t->mesh->nc) return JB_ERR_ARG;
+    m->n_assemble = n_owned;
+    return JB_OK;
+}
 
 int32_t jb_twophase_set_sources(jb_twophase* m, int64_t nsrc, const int64_t* cells, const double* vals) {
     if (!m || nsrc < 0 || (nsrc > 0 && (!cells || !vals))) return JB_ERR_ARG;

@@ -151,6 +151,7 @@ struct jb_twophase {
     DBuf<int32_t> d_src_cells;
     DBuf<double> d_src_vals;
     i64 nsrc = 0;
+    i64 n_assemble = -1;              // rows to assemble (owned cells of a distributed run); -1 = all
     // resident state for the host-facing perform_step
     DBuf<double> d_p, d_s, d_M0, d_r, d_dx;
 };
@@ -181,7 +182,12 @@ struct jb_ilu {
     double* graph_x = nullptr;
 };
 
-struct KrylovScalars;  // device-side scalar block (krylov.cu)
+// ---- multi-GPU: one process per GPU, NCCL over NVLink (dist.cu) ----
+struct jb_comm;
+struct jb_dist;
+int jb_dist_halo_launch(jb_dist* D, double* d_vec, int bs);                 // enqueue on the context's stream
+int jb_dist_allreduce_launch(jb_dist* D, double* d_buf, int n, int op_max);  // in place, enqueue only
+i64 jb_dist_n_owned(jb_dist* D);
 
 struct jb_krylov {
     jb_csr* csr;
@@ -194,6 +200,7 @@ struct jb_krylov {
     double* h_flags = nullptr;  // pinned
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int hist_cap = 0;
+    jb_dist* dist = nullptr;   // distributed solve: dots over owned rows + all-reduce, halo exchange before each SpMV
     // gmres
     DBuf<double> V;  // (mem+1) x m basis
     int gm_mem = 0;
@@ -204,7 +211,7 @@ enum { JB_DOT_NONE = 0, JB_DOT_CV = 1, JB_DOT_TS_TT = 2 };
 
 int jb_launch_spmv(jb_csr* A, double alpha, const double* d_x, double beta, double* d_y);
 // y = A*x fused with dot products; results accumulated by the finalizer into sc (see krylov.cu)
-int jb_launch_spmv_dots(jb_csr* A, const double* d_x, double* d_y, int mode, const double* d_u, double* d_sc);
+int jb_launch_spmv_dots(jb_csr* A, const double* d_x, double* d_y, int mode, const double* d_u, double* d_sc, i64 n_dot = -1);
 
 int jb_ilu_symbolic(jb_ilu* F, const int64_t* partition);
 int jb_ilu_upload(jb_ilu* F);

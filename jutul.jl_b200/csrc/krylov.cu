@@ -12,6 +12,13 @@
 // host round trip sits between kernels. The host enqueues one iteration ahead
 // and polls a pinned copy of the flags; once `done` is set all later kernels of
 // the solve return immediately.
+//
+// Distributed form (jb_krylov_set_dist; ext/JutulPartitionedArraysExt/krylov.jl:1-146,
+// linalg.jl:37-93): vectors hold [owned | ghost] cells; every vector update and inner
+// product runs over the owned rows; the raw local sums are all-reduced in place with NCCL
+// on the same stream and a one-thread kernel applies the scalar recurrence, so every rank
+// holds bitwise-identical scalars and takes identical decisions; the operand of each SpMV
+// gets its ghost section from a halo exchange (consistent!(X), linalg.jl:46).
 #include "jb_internal.cuh"
 #include "jb_krylov_scalars.cuh"
 #include "jb_reduce.cuh"
@@ -29,19 +36,8 @@ __global__ void __launch_bounds__(256) bicg_init_kernel(i64 m, const double* __r
         d[1] = fma(__ldg(b + i), ri, d[1]);
     }
     grid_reduce<2, OpSum>(d, partials, counter, [=](double(&t)[2]) {
-        const double rnorm = sqrt(t[0]);
-        sc[KS_RNORM] = rnorm; sc[KS_R0] = rnorm;
-        sc[KS_EPS] = sc[KS_ATOL] + sc[KS_RTOL] * rnorm;
-        sc[KS_RHO] = t[1];
-        sc[KS_ALPHA] = 1.0; sc[KS_OMEGA] = 1.0; sc[KS_BETA] = 0.0;
-        sc[KS_ITER] = 0.0;
-        hist[0] = rnorm;
-        double done = 0.0, status = 1.0;
-        if (rnorm == 0.0) { done = 1.0; status = 0.0; }            // x = 0 is the solution
-        else if (t[1] == 0.0) { done = 1.0; status = 2.0; }        // "Breakdown b'c = 0"
-        else if (rnorm <= sc[KS_EPS]) { done = 1.0; status = 0.0; }
-        else if (sc[KS_ITMAX] <= 0.0) { done = 1.0; status = 1.0; }
-        sc[KS_DONE] = done; sc[KS_STATUS] = status;
+        sc[KS_SUM0] = t[0]; sc[KS_SUM1] = t[1];
+        if (sc[KS_DIST] == 0.0) ks_fin_init(sc, hist);
     });
 }
 
@@ -72,25 +68,8 @@ __global__ void __launch_bounds__(256) bicg_update2_kernel(i64 m, double* sc, co
         d[1] = fma(ri, ri, d[1]);
     }
     grid_reduce<2, OpSum>(d, partials, counter, [=](double(&tt)[2]) {
-        const double alpha = sc[KS_ALPHA], om = sc[KS_OMEGA], rho = sc[KS_RHO];
-        const double next_rho = tt[0];
-        sc[KS_BETA] = (next_rho / rho) * (alpha / om);
-        sc[KS_RHO] = next_rho;
-        const double rnorm = sqrt(tt[1]);
-        sc[KS_RNORM] = rnorm;
-        const double iter = sc[KS_ITER] + 1.0;
-        sc[KS_ITER] = iter;
-        if ((int)iter < hist_cap) hist[(int)iter] = rnorm;
-        const bool mach = (rnorm + 1.0 <= 1.0);
-        bool solved = (rnorm <= sc[KS_EPS]) || mach;
-        bool user_exit = false;
-        if (sc[KS_MANUAL] != 0.0)   // krylov_termination_criterion (src/linsolve/krylov.jl:198-205)
-            user_exit = (rnorm <= sc[KS_ABS_TOL] + sc[KS_REL_TOL] * sc[KS_R0]) && (iter + 1.0 > sc[KS_MIN_IT]);
-        const bool tired = iter >= sc[KS_ITMAX];
-        const bool breakdown = (alpha == 0.0) || isnan(alpha);
-        if (solved || user_exit) { sc[KS_DONE] = 1.0; sc[KS_STATUS] = 0.0; }
-        else if (breakdown) { sc[KS_DONE] = 1.0; sc[KS_STATUS] = 2.0; }
-        else if (tired) { sc[KS_DONE] = 1.0; sc[KS_STATUS] = 1.0; }
+        sc[KS_SUM0] = tt[0]; sc[KS_SUM1] = tt[1];
+        if (sc[KS_DIST] == 0.0) ks_fin_update2(sc, hist, hist_cap);
     });
 }
 
@@ -105,7 +84,7 @@ __global__ void __launch_bounds__(256) bicg_update3_kernel(i64 m, const double* 
     }
 }
 
-// stand-alone dots for the left-preconditioned / unfused paths
+// stand-alone dots for the left-preconditioned path
 template <int MODE>
 __global__ void __launch_bounds__(256) bicg_dot_kernel(i64 m, double* sc, const double* __restrict__ a, const double* __restrict__ b,
                                                        double* partials, unsigned int* counter) {
@@ -117,9 +96,19 @@ __global__ void __launch_bounds__(256) bicg_dot_kernel(i64 m, double* sc, const 
         if (MODE == JB_DOT_TS_TT) d[1] = fma(ai, ai, d[1]);
     }
     grid_reduce<2, OpSum>(d, partials, counter, [=](double(&t)[2]) {
-        if (MODE == JB_DOT_CV) sc[KS_ALPHA] = sc[KS_RHO] / t[0];
-        else sc[KS_OMEGA] = t[0] / t[1];
+        sc[KS_SUM0] = t[0]; sc[KS_SUM1] = t[1];
+        if (sc[KS_DIST] == 0.0) { if (MODE == JB_DOT_CV) ks_fin_alpha(sc); else ks_fin_omega(sc); }
     });
+}
+
+// distributed: scalar recurrence after the all-reduce of sc[KS_SUM0..1]. which: 0 init, 1 alpha, 2 omega, 3 update2
+__global__ void krylov_finalize_kernel(int which, double* sc, double* hist, int hist_cap) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (which == 0) { ks_fin_init(sc, hist); return; }
+    if (sc[KS_DONE] != 0.0) return;
+    if (which == 1) ks_fin_alpha(sc);
+    else if (which == 2) ks_fin_omega(sc);
+    else ks_fin_update2(sc, hist, hist_cap);
 }
 
 __global__ void __launch_bounds__(256) negate_kernel(i64 m, const double* __restrict__ x, double* __restrict__ dx) {
@@ -149,6 +138,11 @@ int32_t jb_krylov_create(jb_csr* A, jb_ilu* ilu, int32_t kind, jb_krylov** out) 
     ok = ok && cudaMallocHost((void**)&K->h_flags, 4 * KS_SIZE * sizeof(double)) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&K->ev[0], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&K->ev[1], cudaEventDisableTiming) == cudaSuccess;
+    if (ok) {   // ghost sections of SpMV operands must never hold NaN garbage before the first exchange
+        cudaMemsetAsync(K->y.p, 0, m * sizeof(double), ctx->stream); cudaMemsetAsync(K->z.p, 0, m * sizeof(double), ctx->stream);
+        cudaMemsetAsync(K->p.p, 0, m * sizeof(double), ctx->stream); cudaMemsetAsync(K->s.p, 0, m * sizeof(double), ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
     if (!ok) { delete K; JB_FAIL(ctx, JB_ERR_ALLOC, "jb_krylov_create: allocation failed"); }
     *out = K;
     return JB_OK;
@@ -162,6 +156,12 @@ int32_t jb_krylov_destroy(jb_krylov* K) {
     delete K;
     return JB_OK;
 }
+int32_t jb_krylov_set_dist(jb_krylov* K, jb_dist* D) {
+    if (!K) return JB_ERR_ARG;
+    if (D && jb_dist_n_owned(D) > K->csr->n) return JB_ERR_ARG;
+    K->dist = D;
+    return JB_OK;
+}
 
 }  // extern "C"
 
@@ -172,7 +172,10 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
     jb_csr* A = K->csr;
     jb_ctx* ctx = A->ctx;
     cudaStream_t st = ctx->stream;
-    const i64 m = K->m;
+    jb_dist* D = K->dist;
+    const int bs = A->bs;
+    const i64 n_own = D ? jb_dist_n_owned(D) : A->n;     // rows that enter updates and inner products
+    const i64 m = n_own * bs;
     const int g = vec_grid(ctx, m);
     jb_ilu* F = K->ilu;
     const bool right = (side == 0 && F), left = (side == 1 && F);
@@ -187,83 +190,97 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
     h_sc[KS_ATOL] = manual ? 1e-20 : atol;
     h_sc[KS_RTOL] = manual ? 1e-20 : rtol;
     h_sc[KS_ITMAX] = (double)itmax;
+    h_sc[KS_DIST] = D ? 1.0 : 0.0;
     memcpy(K->h_flags + 2 * KS_SIZE, h_sc, sizeof(h_sc));
     JB_CUDA(ctx, cudaMemcpyAsync(sc, K->h_flags + 2 * KS_SIZE, sizeof(h_sc), cudaMemcpyHostToDevice, st));
 
+    int rc;
+    // all-reduce of the two raw sums + scalar recurrence (distributed only)
+    auto reduce_fin = [&](int which) -> int {
+        if (!D) return JB_OK;
+        int r2 = jb_dist_allreduce_launch(D, sc + KS_SUM0, 2, 0);
+        if (r2 != JB_OK) return r2;
+        krylov_finalize_kernel<<<1, 32, 0, st>>>(which, sc, K->d_hist.p, K->hist_cap);
+        JB_CHECK_LAUNCH(ctx);
+        return JB_OK;
+    };
+#define JB_VEC_BEGIN if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
+#define JB_VEC_END if (ctx->prof_on) jb_prof_end(ctx);
+
     const double* rin = d_b;
     if (left) {
-        int rc = jb_launch_ilu_apply_sc(F, d_b, K->r.p, nullptr);
+        rc = jb_launch_ilu_apply_sc(F, d_b, K->r.p, nullptr);
         if (rc != JB_OK) return rc;
         rin = K->r.p;
     }
-    if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
+    JB_VEC_BEGIN
     bicg_init_kernel<<<g, 256, 0, st>>>(m, d_b, rin, K->r.p, K->p.p, K->x.p, K->v.p, K->s.p, sc, K->d_hist.p, ctx->d_partials, ctx->d_counters);
     JB_CHECK_LAUNCH(ctx);
-    if (ctx->prof_on) jb_prof_end(ctx);
+    JB_VEC_END
+    if ((rc = reduce_fin(0)) != JB_OK) return rc;
     JB_CUDA(ctx, cudaMemcpyAsync(K->h_flags, sc, KS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
     JB_CUDA(ctx, cudaEventRecord(K->ev[0], st));
 
-    int enq = 0;
-    bool done = false;
-    // it = index of the iteration being enqueued; flags of iteration it-1 (slot (it) & 1) are awaited before enqueuing it+1
-    for (int it = 1; it <= itmax && !done; it++) {
+    for (int it = 1; it <= itmax; it++) {
         // keep one iteration in flight ahead of the host: before enqueuing iteration `it`, make sure the
         // flags written after iteration it-2 (same pinned slot this iteration will reuse) are not `done`.
         if (it >= 2) {
             const int slot_prev = it & 1;
             JB_CUDA(ctx, cudaEventSynchronize(K->ev[slot_prev]));
-            if (K->h_flags[slot_prev * KS_SIZE + KS_DONE] != 0.0) { done = true; break; }
+            if (K->h_flags[slot_prev * KS_SIZE + KS_DONE] != 0.0) break;
         }
-        int rc;
-        const double* yv = K->p.p;
+        double* yv = K->p.p;
         if (right) { rc = jb_launch_ilu_apply_sc(F, K->p.p, K->y.p, sc); if (rc != JB_OK) return rc; yv = K->y.p; }
+        if (D && (rc = jb_dist_halo_launch(D, yv, bs)) != JB_OK) return rc;           // consistent!(y)
         if (!left) {
-            rc = jb_launch_spmv_dots(A, yv, K->v.p, JB_DOT_CV, d_b, sc);      // v = A y, alpha = rho/<c,v>
+            rc = jb_launch_spmv_dots(A, yv, K->v.p, JB_DOT_CV, d_b, sc, n_own);       // v = A y, alpha = rho/<c,v>
             if (rc != JB_OK) return rc;
         } else {
             rc = jb_launch_spmv_dots(A, yv, K->q.p, JB_DOT_NONE, nullptr, nullptr); if (rc != JB_OK) return rc;
             rc = jb_launch_ilu_apply_sc(F, K->q.p, K->v.p, sc); if (rc != JB_OK) return rc;
-            if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
+            JB_VEC_BEGIN
             bicg_dot_kernel<JB_DOT_CV><<<g, 256, 0, st>>>(m, sc, K->v.p, d_b, ctx->d_partials, ctx->d_counters);
             JB_CHECK_LAUNCH(ctx);
-            if (ctx->prof_on) jb_prof_end(ctx);
+            JB_VEC_END
         }
-        if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
+        if ((rc = reduce_fin(1)) != JB_OK) return rc;
+        JB_VEC_BEGIN
         bicg_update1_kernel<<<g, 256, 0, st>>>(m, sc, K->r.p, K->v.p, yv, K->s.p, K->x.p);
         JB_CHECK_LAUNCH(ctx);
-        if (ctx->prof_on) jb_prof_end(ctx);
-        const double* zv = K->s.p;
+        JB_VEC_END
+        double* zv = K->s.p;
         if (right) { rc = jb_launch_ilu_apply_sc(F, K->s.p, K->z.p, sc); if (rc != JB_OK) return rc; zv = K->z.p; }
+        if (D && (rc = jb_dist_halo_launch(D, zv, bs)) != JB_OK) return rc;           // consistent!(z)
         if (!left) {
-            rc = jb_launch_spmv_dots(A, zv, K->t.p, JB_DOT_TS_TT, K->s.p, sc);  // t = A z, omega = <t,s>/<t,t>
+            rc = jb_launch_spmv_dots(A, zv, K->t.p, JB_DOT_TS_TT, K->s.p, sc, n_own);  // t = A z, omega = <t,s>/<t,t>
             if (rc != JB_OK) return rc;
         } else {
             rc = jb_launch_spmv_dots(A, zv, K->q.p, JB_DOT_NONE, nullptr, nullptr); if (rc != JB_OK) return rc;
             rc = jb_launch_ilu_apply_sc(F, K->q.p, K->t.p, sc); if (rc != JB_OK) return rc;
-            if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
+            JB_VEC_BEGIN
             bicg_dot_kernel<JB_DOT_TS_TT><<<g, 256, 0, st>>>(m, sc, K->t.p, K->s.p, ctx->d_partials, ctx->d_counters);
             JB_CHECK_LAUNCH(ctx);
-            if (ctx->prof_on) jb_prof_end(ctx);
+            JB_VEC_END
         }
-        if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
+        if ((rc = reduce_fin(2)) != JB_OK) return rc;
+        JB_VEC_BEGIN
         bicg_update2_kernel<<<g, 256, 0, st>>>(m, sc, K->s.p, K->t.p, zv, d_b, K->x.p, K->r.p, K->d_hist.p, K->hist_cap, ctx->d_partials,
                                                ctx->d_counters);
         JB_CHECK_LAUNCH(ctx);
-        if (ctx->prof_on) jb_prof_end(ctx);
-        if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
+        JB_VEC_END
+        if ((rc = reduce_fin(3)) != JB_OK) return rc;
+        JB_VEC_BEGIN
         bicg_update3_kernel<<<g, 256, 0, st>>>(m, sc, K->r.p, K->v.p, K->p.p);
         JB_CHECK_LAUNCH(ctx);
-        if (ctx->prof_on) jb_prof_end(ctx);
+        JB_VEC_END
         const int slot = it & 1;
         JB_CUDA(ctx, cudaMemcpyAsync(K->h_flags + slot * KS_SIZE, sc, KS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
         JB_CUDA(ctx, cudaEventRecord(K->ev[slot], st));
-        enq = it;
     }
-    (void)enq;
-    if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_VECTOR);
+    JB_VEC_BEGIN
     negate_kernel<<<g, 256, 0, st>>>(m, K->x.p, d_dx);   // dx = -x (update_dx_from_vector!)
     JB_CHECK_LAUNCH(ctx);
-    if (ctx->prof_on) jb_prof_end(ctx);
+    JB_VEC_END
     JB_CUDA(ctx, cudaMemcpyAsync(K->h_flags + 3 * KS_SIZE, sc, KS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
     JB_CUDA(ctx, cudaStreamSynchronize(st));
     const double* f = K->h_flags + 3 * KS_SIZE;

@@ -94,12 +94,14 @@ __global__ void __launch_bounds__(256) spmv_kernel(i64 n, const int32_t* __restr
     if (MODE == JB_DOT_CV) {
         double r[1] = {d0};
         grid_reduce<1, OpSum>(r, partials, counter, [=](double(&t)[1]) {
-            sc[KS_ALPHA] = sc[KS_RHO] / t[0];   // alpha_k = rho_k / <c, v_k>
+            sc[KS_SUM0] = t[0];
+            if (sc[KS_DIST] == 0.0) ks_fin_alpha(sc);   // alpha_k = rho_k / <c, v_k>
         });
     } else if (MODE == JB_DOT_TS_TT) {
         double r[2] = {d0, d1};
         grid_reduce<2, OpSum>(r, partials, counter, [=](double(&t)[2]) {
-            sc[KS_OMEGA] = t[0] / t[1];         // omega_k = <t,s>/<t,t>
+            sc[KS_SUM0] = t[0]; sc[KS_SUM1] = t[1];
+            if (sc[KS_DIST] == 0.0) ks_fin_omega(sc);   // omega_k = <t,s>/<t,t>
         });
     }
 }
@@ -109,7 +111,8 @@ template <int BS, int MODE>
 __global__ void __launch_bounds__(256) spmv_stream_kernel(int nchunks, const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ rowptr,
                                                           const int32_t* __restrict__ colidx, const double* __restrict__ val,
                                                           const double* __restrict__ x, double* __restrict__ y, double alpha, double beta,
-                                                          const double* __restrict__ u, double* sc, double* partials, unsigned int* counter) {
+                                                          const double* __restrict__ u, double* sc, double* partials, unsigned int* counter,
+                                                          i64 n_dot) {
     if (MODE != JB_DOT_NONE) {
         if (sc[KS_DONE] != 0.0) return;
     }
@@ -128,23 +131,31 @@ __global__ void __launch_bounds__(256) spmv_stream_kernel(int nchunks, const int
                 double v = alpha * acc[e];
                 if (beta != 0.0) v += beta * y[row * BS + e];
                 y[row * BS + e] = v;
-                if (MODE == JB_DOT_CV) d0 = fma(__ldg(u + row * BS + e), v, d0);
-                if (MODE == JB_DOT_TS_TT) { d0 = fma(v, __ldg(u + row * BS + e), d0); d1 = fma(v, v, d1); }
+                if (MODE != JB_DOT_NONE && (i64)row < n_dot) {     // inner products run over owned rows only
+                    if (MODE == JB_DOT_CV) d0 = fma(__ldg(u + row * BS + e), v, d0);
+                    if (MODE == JB_DOT_TS_TT) { d0 = fma(v, __ldg(u + row * BS + e), d0); d1 = fma(v, v, d1); }
+                }
             }
         }
         __syncthreads();
     }
     if (MODE == JB_DOT_CV) {
         double r[1] = {d0};
-        grid_reduce<1, OpSum>(r, partials, counter, [=](double(&t)[1]) { sc[KS_ALPHA] = sc[KS_RHO] / t[0]; });
+        grid_reduce<1, OpSum>(r, partials, counter, [=](double(&t)[1]) {
+            sc[KS_SUM0] = t[0];
+            if (sc[KS_DIST] == 0.0) ks_fin_alpha(sc);
+        });
     } else if (MODE == JB_DOT_TS_TT) {
         double r[2] = {d0, d1};
-        grid_reduce<2, OpSum>(r, partials, counter, [=](double(&t)[2]) { sc[KS_OMEGA] = t[0] / t[1]; });
+        grid_reduce<2, OpSum>(r, partials, counter, [=](double(&t)[2]) {
+            sc[KS_SUM0] = t[0]; sc[KS_SUM1] = t[1];
+            if (sc[KS_DIST] == 0.0) ks_fin_omega(sc);
+        });
     }
 }
 
 template <int BS, int MODE>
-static int launch_spmv_stream(jb_csr* A, double alpha, const double* x, double beta, double* y, const double* u, double* sc) {
+static int launch_spmv_stream(jb_csr* A, double alpha, const double* x, double beta, double* y, const double* u, double* sc, i64 n_dot) {
     jb_ctx* ctx = A->ctx;
     ProfScope _ps(ctx, JB_PROF_SPMV);
     const int nchunks = (int)A->h_chunks.size() - 1;
@@ -158,7 +169,7 @@ static int launch_spmv_stream(jb_csr* A, double alpha, const double* x, double b
     if (MODE != JB_DOT_NONE && cap > JB_MAX_PARTIALS) cap = JB_MAX_PARTIALS;
     const int grid = std::max(1, std::min(nchunks, cap));
     spmv_stream_kernel<BS, MODE><<<grid, 256, smem, ctx->stream>>>(nchunks, A->d_chunks.p, A->d_rowptr.p, A->d_colidx.p, A->d_val.p, x, y, alpha,
-                                                                  beta, u, sc, ctx->d_partials, ctx->d_counters);
+                                                                  beta, u, sc, ctx->d_partials, ctx->d_counters, n_dot < 0 ? A->n : n_dot);
     JB_CHECK_LAUNCH(ctx);
     return JB_OK;
 }
@@ -180,13 +191,14 @@ static int launch_spmv_t(jb_csr* A, double alpha, const double* x, double beta, 
 }
 
 template <int MODE>
-static int launch_spmv_mode(jb_csr* A, double alpha, const double* x, double beta, double* y, const double* u, double* sc) {
-    if (!A->h_chunks.empty()) {
+static int launch_spmv_mode(jb_csr* A, double alpha, const double* x, double beta, double* y, const double* u, double* sc, i64 n_dot = -1) {
+    if (!A->h_chunks.empty() || n_dot >= 0) {
+        if (A->h_chunks.empty()) return JB_ERR_UNSUPPORTED;   // distributed dots need the stream form
         switch (A->bs) {
-            case 1: return launch_spmv_stream<1, MODE>(A, alpha, x, beta, y, u, sc);
-            case 2: return launch_spmv_stream<2, MODE>(A, alpha, x, beta, y, u, sc);
-            case 3: return launch_spmv_stream<3, MODE>(A, alpha, x, beta, y, u, sc);
-            case 4: return launch_spmv_stream<4, MODE>(A, alpha, x, beta, y, u, sc);
+            case 1: return launch_spmv_stream<1, MODE>(A, alpha, x, beta, y, u, sc, n_dot);
+            case 2: return launch_spmv_stream<2, MODE>(A, alpha, x, beta, y, u, sc, n_dot);
+            case 3: return launch_spmv_stream<3, MODE>(A, alpha, x, beta, y, u, sc, n_dot);
+            case 4: return launch_spmv_stream<4, MODE>(A, alpha, x, beta, y, u, sc, n_dot);
         }
     }
     // fallback (a row longer than the shared-memory tile): lanes-per-row kernel,
@@ -212,9 +224,9 @@ static int launch_spmv_mode(jb_csr* A, double alpha, const double* x, double bet
 int jb_launch_spmv(jb_csr* A, double alpha, const double* d_x, double beta, double* d_y) {
     return launch_spmv_mode<JB_DOT_NONE>(A, alpha, d_x, beta, d_y, nullptr, nullptr);
 }
-int jb_launch_spmv_dots(jb_csr* A, const double* d_x, double* d_y, int mode, const double* d_u, double* d_sc) {
-    if (mode == JB_DOT_CV) return launch_spmv_mode<JB_DOT_CV>(A, 1.0, d_x, 0.0, d_y, d_u, d_sc);
-    if (mode == JB_DOT_TS_TT) return launch_spmv_mode<JB_DOT_TS_TT>(A, 1.0, d_x, 0.0, d_y, d_u, d_sc);
+int jb_launch_spmv_dots(jb_csr* A, const double* d_x, double* d_y, int mode, const double* d_u, double* d_sc, i64 n_dot) {
+    if (mode == JB_DOT_CV) return launch_spmv_mode<JB_DOT_CV>(A, 1.0, d_x, 0.0, d_y, d_u, d_sc, n_dot);
+    if (mode == JB_DOT_TS_TT) return launch_spmv_mode<JB_DOT_TS_TT>(A, 1.0, d_x, 0.0, d_y, d_u, d_sc, n_dot);
     return launch_spmv_mode<JB_DOT_NONE>(A, 1.0, d_x, 0.0, d_y, nullptr, nullptr);
 }
 

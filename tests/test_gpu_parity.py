@@ -477,3 +477,17 @@ def test_reordering_does_not_change_the_physics(J, O, ctx):
     pg, swg = sim.get_state()
     assert st == 0 and its == rep["linear_iterations"] and np.allclose(err, err2, rtol=1e-12)
     assert np.array_equal(pg, p) and np.array_equal(swg, sat[0::2])
+
+
+def test_distributed_matches_single_gpu(J):
+    """Needs >= 2 GPUs on the box (skipped otherwise): torchrun the 2-rank check script."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29631", os.path.join(root, "tests", "dist_gpu_check.py")], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
