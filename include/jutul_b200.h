@@ -51,6 +51,7 @@ typedef struct jb_krylov jb_krylov;
 typedef struct jb_perm jb_perm;
 typedef struct jb_comm jb_comm;
 typedef struct jb_dist jb_dist;
+typedef struct jb_nfvm jb_nfvm;
 
 /* ---- lifecycle: JutulContext (src/core_types/contexts/*.jl, src/context.jl:65-78:
  *      initialize_context!, synchronize) ------------------------------------ */
@@ -156,6 +157,17 @@ int32_t jb_heat_assemble(jb_csr* csr, int64_t nx, int64_t ny, double hx, double 
 int32_t jb_poisson_assemble(jb_tpfa* t, const double* d_K /*nf*/, const double* d_U, const double* d_U0,
                             int32_t time_dependent, double dt, int64_t nsrc, const int64_t* src_cells,
                             const double* src_vals, double* d_r);
+
+/* ---- NFVM run-time flux: evaluate_flux / ntpfa_half_flux / compute_r / tpfa_flux (src/NFVM/evaluation.jl:1-88) on
+ *      NFVMLinearDiscretization / NFVMNonLinearDiscretization (src/NFVM/types.jl:5-35). Per face: cell pair, T_left,
+ *      T_right and the MPFA remainder as a CSR row of (cell, T) (ptr 1-based, nf+1). scheme 0 = linear (L_* only),
+ *      1 = :ntpfa, 2 = :nmpfa (L_* = ft_left, R_* = ft_right). d_p is nph x nc (column-major), ph 1-based; d_q[nf]. */
+int32_t jb_nfvm_create(jb_ctx* ctx, int64_t nf, int64_t nc, int32_t scheme, const int64_t* left, const int64_t* right,
+                       const double* L_Tl, const double* L_Tr, const int64_t* L_ptr, const int64_t* L_cell, const double* L_T,
+                       const double* R_Tl, const double* R_Tr, const int64_t* R_ptr, const int64_t* R_cell, const double* R_T,
+                       jb_nfvm** out);
+int32_t jb_nfvm_destroy(jb_nfvm* d);
+int32_t jb_nfvm_evaluate_flux(jb_nfvm* d, const double* d_p, int64_t nph, int64_t ph, double* d_q);
 
 /* ---- post_update_linearized_system! for ghost rows: unit_diagonalize!
  *      (ext/JutulPartitionedArraysExt/linalg.jl:1-35): rows >= n_owned become -I, r = 0. */

@@ -406,6 +406,36 @@ def partition(N, num_coarse, weights=None, nc=None, partitioner="metis"):
     return part
 
 
+class NFVMDiscretization(_Handle):
+    """NFVMLinearDiscretization / NFVMNonLinearDiscretization per face (src/NFVM/types.jl:5-35) resident on the device.
+    `L` (and `R` for the nonlinear schemes) are dicts with T_left, T_right (per face) and the MPFA remainder as CSR:
+    ptr (1-based, nf+1), cell (1-based), T."""
+
+    _destroy = "jb_nfvm_destroy"
+
+    def __init__(self, ctx, left, right, nc, L, R=None, scheme="linear"):
+        self.ctx = ctx
+        sc = {"linear": 0, "ntpfa": 1, "nmpfa": 2}[scheme]
+        left = np.ascontiguousarray(left, dtype=i64); right = np.ascontiguousarray(right, dtype=i64)
+        self.nf = left.shape[0]
+
+        def arrs(d):
+            if d is None:
+                return [None] * 5
+            return [np.ascontiguousarray(d["T_left"], dtype=f64), np.ascontiguousarray(d["T_right"], dtype=f64),
+                    np.ascontiguousarray(d["ptr"], dtype=i64), np.ascontiguousarray(d["cell"], dtype=i64), np.ascontiguousarray(d["T"], dtype=f64)]
+        a, b = arrs(L), arrs(R)
+        self._keep = (left, right, a, b)
+        h = C.c_void_p()
+        check(ctx.lib.jb_nfvm_create(ctx.h, self.nf, int(nc), sc, _pi(left), _pi(right), _pd(a[0]), _pd(a[1]), _pi(a[2]), _pi(a[3]), _pd(a[4]),
+                                     _pd(b[0]), _pd(b[1]), _pi(b[2]), _pi(b[3]), _pd(b[4]), C.byref(h)), ctx.h, "jb_nfvm_create")
+        self.h = h
+
+    def evaluate_flux(self, p, q, nph=1, ph=1):
+        check(self.ctx.lib.jb_nfvm_evaluate_flux(self.h, _dp(p), nph, ph, _dp(q)), self.ctx.h, "jb_nfvm_evaluate_flux")
+        return q
+
+
 def multicolor_ordering(N, nc):
     """B200-friendly cell renumbering (setup, host): Cuthill-McKee locality + greedy colouring, numbered colour
     by colour. Returns (perm, ncolors) with perm[c] = new 1-based label of (1-based) cell c+1."""

@@ -2,8 +2,8 @@
 #include "jb_internal.cuh"
 
 const std::string& jb_global_error();
-int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double rtol, double atol, int itmax, int min_it, int side, int* iters,
-                         double* hist, int hist_cap, int* status_out);
+int jb_krylov_dispatch(jb_krylov* K, const double* d_b, double* d_dx, double rtol, double atol, int itmax, int min_it, int side, int* iters,
+                       double* hist, int hist_cap, int* status_out);
 int jb_launch_update_scalar(jb_ctx* ctx, double* d_v, const double* d_dx, i64 stride, i64 n, double w, double abs_max, double rel_max,
                             double minv, double maxv, double scale);
 int jb_launch_update_pair(jb_ctx* ctx, double* d_s, const double* d_dx, i64 stride, i64 n, double w, double abs_max, double minval, double maxval);
@@ -211,7 +211,7 @@ int32_t jb_twophase_perform_step_host(jb_twophase* m, jb_ilu* ilu, jb_krylov* ks
         if (rc != JB_OK) return rc;
     }
     int iters = 0;
-    rc = jb_krylov_solve_impl(ks, m->d_r.p, m->d_dx.p, rtol, atol, itmax, 1, ilu ? 0 : -1, &iters, nullptr, 0, &status);
+    rc = jb_krylov_dispatch(ks, m->d_r.p, m->d_dx.p, rtol, atol, itmax, 1, ilu ? 0 : -1, &iters, nullptr, 0, &status);
     if (rc != JB_OK) return rc;
     *lin_iters = iters;
     // update_primary_variables! (src/models.jl:928-953): dx is bs x nc; pressure row 0, saturation row 1

@@ -175,6 +175,31 @@ __global__ void __launch_bounds__(256) ilu_sweep_stream_kernel(int c0, int c1, c
     }
 }
 
+// Levels whose rows have no off-diagonal entry inside the block (e.g. the first colour of a multicolour ordering) need no
+// gather at all: x_i = b_i (forward) or x_i = D_i^{-1} x_i (backward). One thread per row, full occupancy.
+template <int BS, bool BACKWARD>
+__global__ void __launch_bounds__(256) ilu_light_level_kernel(int32_t t0, int32_t t1, const int32_t* __restrict__ order, const double* __restrict__ dinv,
+                                                              const double* b, double* x, const double* sc) {
+    if (sc && sc[KS_DONE] != 0.0) return;
+    const int32_t t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t1) return;
+    const size_t i = (size_t)__ldg(order + t);
+    double v[BS];
+#pragma unroll
+    for (int e = 0; e < BS; e++) v[e] = BACKWARD ? x[i * BS + e] : b[i * BS + e];
+    if (BACKWARD) {
+        double d[BS * BS], out[BS];
+#pragma unroll
+        for (int q = 0; q < BS * BS; q++) d[q] = __ldg(dinv + i * BS * BS + q);
+        blk_mulvec<BS>(d, v, out);
+#pragma unroll
+        for (int e = 0; e < BS; e++) x[i * BS + e] = out[e];
+    } else {
+#pragma unroll
+        for (int e = 0; e < BS; e++) x[i * BS + e] = v[e];
+    }
+}
+
 template <int BS>
 static int ilu_apply_stream_t(jb_ilu* F, const double* b, double* x, const double* sc) {
     jb_ctx* ctx = F->csr->ctx;
@@ -191,6 +216,12 @@ static int ilu_apply_stream_t(jb_ilu* F, const double* b, double* x, const doubl
     for (int l = 0; l < F->nlevF; l++) {
         const int c0 = F->h_levF_chunk[l], c1 = F->h_levF_chunk[l + 1];
         if (c1 <= c0) continue;
+        const int32_t t0 = F->h_levF_ptr[l], t1 = F->h_levF_ptr[l + 1];
+        if (F->h_LptrT[t1] == F->h_LptrT[t0]) {
+            ilu_light_level_kernel<BS, false><<<(t1 - t0 + 255) / 256, 256, 0, s>>>(t0, t1, F->d_forder.p, F->d_dinv.p, b, x, sc);
+            JB_CHECK_LAUNCH(ctx);
+            continue;
+        }
         ilu_sweep_stream_kernel<BS, false><<<std::min(c1 - c0, cap), 256, smem, s>>>(c0, c1, F->d_chunksF.p, F->d_LptrT.p, F->d_Lcol.p, F->d_fv.p, 0,
                                                                                      F->d_forder.p, F->d_dinv.p, b, x, sc);
         JB_CHECK_LAUNCH(ctx);
@@ -198,6 +229,12 @@ static int ilu_apply_stream_t(jb_ilu* F, const double* b, double* x, const doubl
     for (int l = 0; l < F->nlevB; l++) {
         const int c0 = F->h_levB_chunk[l], c1 = F->h_levB_chunk[l + 1];
         if (c1 <= c0) continue;
+        const int32_t t0 = F->h_levB_ptr[l], t1 = F->h_levB_ptr[l + 1];
+        if (F->h_UptrT[t1] == F->h_UptrT[t0]) {
+            ilu_light_level_kernel<BS, true><<<(t1 - t0 + 255) / 256, 256, 0, s>>>(t0, t1, F->d_border.p, F->d_dinv.p, b, x, sc);
+            JB_CHECK_LAUNCH(ctx);
+            continue;
+        }
         ilu_sweep_stream_kernel<BS, true><<<std::min(c1 - c0, cap), 256, smem, s>>>(c0, c1, F->d_chunksB.p, F->d_UptrT.p, F->d_Ucol.p, F->d_fv.p,
                                                                                     (size_t)(F->nL + F->n), F->d_border.p, F->d_dinv.p, b, x, sc);
         JB_CHECK_LAUNCH(ctx);

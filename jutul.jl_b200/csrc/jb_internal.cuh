@@ -201,9 +201,10 @@ struct jb_krylov {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int hist_cap = 0;
     jb_dist* dist = nullptr;   // distributed solve: dots over owned rows + all-reduce, halo exchange before each SpMV
-    // gmres
-    DBuf<double> V;  // (mem+1) x m basis
-    int gm_mem = 0;
+    // gmres: Arnoldi basis (grows on demand), packed Hessenberg/R columns, Givens c/s, z, y
+    std::vector<double*> gm_V;
+    DBuf<double*> gm_Vptr;
+    DBuf<double> gm_R, gm_cs;
 };
 
 // ---- launchers implemented in the kernel translation units (all enqueue on ctx->stream) ----

@@ -126,7 +126,7 @@ extern "C" {
 int32_t jb_krylov_create(jb_csr* A, jb_ilu* ilu, int32_t kind, jb_krylov** out) {
     if (!A || !out) return JB_ERR_ARG;
     jb_ctx* ctx = A->ctx;
-    if (kind != 0) JB_FAIL(ctx, JB_ERR_UNSUPPORTED, "jb_krylov_create: only kind 0 (bicgstab) is implemented in this build");
+    if (kind != 0 && kind != 1) JB_FAIL(ctx, JB_ERR_UNSUPPORTED, "jb_krylov_create: kind must be 0 (bicgstab) or 1 (gmres)");
     jb_krylov* K = new jb_krylov();
     K->csr = A; K->ilu = ilu; K->kind = kind; K->m = A->n * A->bs;
     const size_t m = (size_t)K->m;
@@ -152,6 +152,7 @@ int32_t jb_krylov_destroy(jb_krylov* K) {
         if (K->h_flags) cudaFreeHost(K->h_flags);
         if (K->ev[0]) cudaEventDestroy(K->ev[0]);
         if (K->ev[1]) cudaEventDestroy(K->ev[1]);
+        for (double* p : K->gm_V) cudaFree(p);
     }
     delete K;
     return JB_OK;
@@ -296,11 +297,20 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
     return JB_OK;
 }
 
+int jb_gmres_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double rtol, double atol, int itmax, int side, int* iters, double* hist,
+                        int hist_cap, int* status_out);
+// kind 0: bicgstab, kind 1: gmres (min_iterations is honoured by bicgstab only)
+int jb_krylov_dispatch(jb_krylov* K, const double* d_b, double* d_dx, double rtol, double atol, int itmax, int min_it, int side, int* iters,
+                       double* hist, int hist_cap, int* status_out) {
+    if (K->kind == 1) return jb_gmres_solve_impl(K, d_b, d_dx, rtol, atol, itmax, side, iters, hist, hist_cap, status_out);
+    return jb_krylov_solve_impl(K, d_b, d_dx, rtol, atol, itmax, min_it, side, iters, hist, hist_cap, status_out);
+}
+
 extern "C" int32_t jb_krylov_solve(jb_krylov* K, const double* d_r, double* d_dx, double rtol, double atol, int32_t itmax, int32_t min_it,
                                    int32_t side, int32_t* iters, double* hist, int32_t hist_cap) {
     if (!K || !d_r || !d_dx || itmax < 0) return JB_ERR_ARG;
     int status = 0;
-    int rc = jb_krylov_solve_impl(K, d_r, d_dx, rtol, atol, itmax, min_it, side, iters, hist, hist_cap, &status);
+    int rc = jb_krylov_dispatch(K, d_r, d_dx, rtol, atol, itmax, min_it, side, iters, hist, hist_cap, &status);
     if (rc != JB_OK) return rc;
     return status;
 }

@@ -392,3 +392,92 @@ int32_t jb_perm_apply(jb_perm* P, const double* d_src, double* d_dst, int32_t bs
 }
 
 }  // extern "C"
+
+// ---- NFVM run-time flux: evaluate_flux / ntpfa_half_flux / compute_r / tpfa_flux (src/NFVM/evaluation.jl:1-88) ----
+// One lane per face; the MPFA remainder is a short CSR row of (cell, T) pairs per face.
+struct jb_nfvm {
+    jb_ctx* ctx;
+    i64 nf;
+    int scheme;   // 0 linear, 1 :ntpfa, 2 :nmpfa
+    DBuf<int32_t> left, right, L_ptr, L_cell, R_ptr, R_cell;
+    DBuf<double> L_Tl, L_Tr, L_T, R_Tl, R_Tr, R_T;
+};
+
+__device__ __forceinline__ double nfvm_compute_r(const int32_t* __restrict__ ptr, const int32_t* __restrict__ cell, const double* __restrict__ T,
+                                                 const double* __restrict__ p, i64 nph, i64 ph0, i64 f) {
+    double r = 0.0;
+    for (int32_t k = __ldg(ptr + f); k < __ldg(ptr + f + 1); k++) r += __ldg(p + (size_t)__ldg(cell + k) * nph + ph0) * __ldg(T + k);
+    return r;
+}
+__global__ void __launch_bounds__(256) nfvm_flux_kernel(i64 nf, int scheme, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                                        const double* __restrict__ L_Tl, const double* __restrict__ L_Tr,
+                                                        const int32_t* __restrict__ L_ptr, const int32_t* __restrict__ L_cell, const double* __restrict__ L_T,
+                                                        const double* __restrict__ R_Tl, const double* __restrict__ R_Tr,
+                                                        const int32_t* __restrict__ R_ptr, const int32_t* __restrict__ R_cell, const double* __restrict__ R_T,
+                                                        const double* __restrict__ p, i64 nph, i64 ph0, double* __restrict__ q) {
+    for (i64 f = (i64)blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += (i64)gridDim.x * blockDim.x) {
+        const double p_l = __ldg(p + (size_t)__ldg(left + f) * nph + ph0), p_r = __ldg(p + (size_t)__ldg(right + f) * nph + ph0);
+        const double r_l = nfvm_compute_r(L_ptr, L_cell, L_T, p, nph, ph0, f);
+        double q_l = __dadd_rn(__dmul_rn(__ldg(L_Tl + f), p_l), __dmul_rn(__ldg(L_Tr + f), p_r));
+        q_l = q_l + r_l;
+        if (scheme == 0) { q[f] = q_l; continue; }
+        double r_r = nfvm_compute_r(R_ptr, R_cell, R_T, p, nph, ph0, f);
+        double q_r = __dadd_rn(__dmul_rn(__ldg(R_Tl + f), p_l), __dmul_rn(__ldg(R_Tr + f), p_r));
+        q_r = -(q_r + r_r); r_r = -r_r;
+        double r_lw = r_l, r_rw = r_r;
+        if (scheme == 2) { r_lw = fabs(r_l); r_rw = fabs(r_r); }
+        const double r_total = r_lw + r_rw;
+        double mu_l = 0.5, mu_r = 0.5;
+        if (!(fabs(r_total) < 1e-10)) { mu_l = r_rw / r_total; mu_r = r_lw / r_total; }
+        q[f] = __dsub_rn(__dmul_rn(mu_l, q_l), __dmul_rn(mu_r, q_r));
+    }
+}
+
+extern "C" {
+
+static int nfvm_half(jb_ctx* ctx, i64 nf, i64 nc, const double* Tl, const double* Tr, const int64_t* ptr, const int64_t* cell, const double* T,
+                     DBuf<double>& dTl, DBuf<double>& dTr, DBuf<int32_t>& dptr, DBuf<int32_t>& dcell, DBuf<double>& dT) {
+    std::vector<int32_t> hp(nf + 1);
+    for (i64 f = 0; f <= nf; f++) { if (ptr[f] < 1) return JB_ERR_ARG; hp[f] = (int32_t)(ptr[f] - 1); }
+    const i64 nnz = hp[nf];
+    std::vector<int32_t> hc(nnz);
+    for (i64 k = 0; k < nnz; k++) { if (cell[k] < 1 || cell[k] > nc) return JB_ERR_ARG; hc[k] = (int32_t)(cell[k] - 1); }
+    std::vector<double> a(Tl, Tl + nf), b(Tr, Tr + nf), c(T, T + nnz);
+    cudaStream_t s = ctx->stream;
+    bool ok = dTl.upload(a, s) == cudaSuccess && dTr.upload(b, s) == cudaSuccess && dptr.upload(hp, s) == cudaSuccess &&
+              dcell.upload(hc, s) == cudaSuccess && dT.upload(c, s) == cudaSuccess;
+    return ok ? JB_OK : JB_ERR_ALLOC;
+}
+
+int32_t jb_nfvm_create(jb_ctx* ctx, int64_t nf, int64_t nc, int32_t scheme, const int64_t* left, const int64_t* right, const double* L_Tl,
+                       const double* L_Tr, const int64_t* L_ptr, const int64_t* L_cell, const double* L_T, const double* R_Tl, const double* R_Tr,
+                       const int64_t* R_ptr, const int64_t* R_cell, const double* R_T, jb_nfvm** out) {
+    if (!ctx || !out || nf < 1 || scheme < 0 || scheme > 2 || !left || !right || !L_Tl || !L_Tr || !L_ptr) return JB_ERR_ARG;
+    if (scheme > 0 && (!R_Tl || !R_Tr || !R_ptr)) return JB_ERR_ARG;
+    jb_nfvm* d = new jb_nfvm();
+    d->ctx = ctx; d->nf = nf; d->scheme = scheme;
+    std::vector<int32_t> hl(nf), hr(nf);
+    for (i64 f = 0; f < nf; f++) {
+        if (left[f] < 1 || left[f] > nc || right[f] < 1 || right[f] > nc) { delete d; JB_FAIL(ctx, JB_ERR_ARG, "jb_nfvm_create: cell out of range"); }
+        hl[f] = (int32_t)(left[f] - 1); hr[f] = (int32_t)(right[f] - 1);
+    }
+    int rc = (d->left.upload(hl, ctx->stream) == cudaSuccess && d->right.upload(hr, ctx->stream) == cudaSuccess) ? JB_OK : JB_ERR_ALLOC;
+    if (rc == JB_OK) rc = nfvm_half(ctx, nf, nc, L_Tl, L_Tr, L_ptr, L_cell, L_T, d->L_Tl, d->L_Tr, d->L_ptr, d->L_cell, d->L_T);
+    if (rc == JB_OK && scheme > 0) rc = nfvm_half(ctx, nf, nc, R_Tl, R_Tr, R_ptr, R_cell, R_T, d->R_Tl, d->R_Tr, d->R_ptr, d->R_cell, d->R_T);
+    if (rc != JB_OK) { delete d; JB_FAIL(ctx, rc, "jb_nfvm_create: bad stencil arrays or allocation failure"); }
+    *out = d;
+    return JB_OK;
+}
+int32_t jb_nfvm_destroy(jb_nfvm* d) { delete d; return JB_OK; }
+int32_t jb_nfvm_evaluate_flux(jb_nfvm* d, const double* d_p, int64_t nph, int64_t ph, double* d_q) {
+    if (!d || !d_p || !d_q || nph < 1 || ph < 1 || ph > nph) return JB_ERR_ARG;
+    jb_ctx* ctx = d->ctx;
+    ProfScope _ps(ctx, JB_PROF_ASSEMBLY);
+    nfvm_flux_kernel<<<sgrid(ctx, d->nf), 256, 0, ctx->stream>>>(d->nf, d->scheme, d->left.p, d->right.p, d->L_Tl.p, d->L_Tr.p, d->L_ptr.p, d->L_cell.p,
+                                                                d->L_T.p, d->R_Tl.p, d->R_Tr.p, d->R_ptr.p, d->R_cell.p, d->R_T.p, d_p, nph, ph - 1, d_q);
+    JB_CHECK_LAUNCH(ctx);
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+
+}  // extern "C"

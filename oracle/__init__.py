@@ -280,6 +280,34 @@ def bicgstab(n, bs, rowptr, colidx, nz, b, ilu=None, side="right", rtol=1e-3, at
     return x, st, iters.value, hist[: iters.value + 1].copy()
 
 
+def gmres(n, bs, rowptr, colidx, nz, b, ilu=None, side="right", rtol=1e-3, atol=1e-12, itmax=100, memory=20, restart=False):
+    x = np.zeros(n * bs)
+    hist = np.zeros(itmax + 2)
+    iters = C.c_int64(0)
+    s = {"right": 0, "left": 1, "none": -1}[side]
+    h = ilu.h if ilu is not None else None
+    lib().orc_gmres.restype = C.c_int
+    st = lib().orc_gmres(_ci(n), C.c_int(bs), _I(rowptr), _I(colidx), _D(_ad(nz)), h, C.c_int(s), _D(_ad(b)), _D(x), _cd(rtol), _cd(atol),
+                         _ci(itmax), _ci(memory), C.c_int(int(restart)), C.byref(iters), _D(hist), _ci(hist.shape[0]))
+    return x, st, iters.value, hist[: iters.value + 1].copy()
+
+
+def nfvm_evaluate_flux(left, right, L, R, p, nph=1, ph=1, scheme="linear"):
+    sc = {"linear": 0, "ntpfa": 1, "nmpfa": 2}[scheme]
+    left = _ai(left); right = _ai(right)
+    nf = left.shape[0]
+    q = np.zeros(nf)
+
+    def arrs(d):
+        if d is None:
+            return [None] * 5
+        return [_ad(d["T_left"]), _ad(d["T_right"]), _ai(d["ptr"]), _ai(d["cell"]), _ad(d["T"])]
+    a, b = arrs(L), arrs(R)
+    lib().orc_nfvm_evaluate_flux(_ci(nf), C.c_int(sc), _I(left), _I(right), _D(a[0]), _D(a[1]), _I(a[2]), _I(a[3]), _D(a[4]),
+                                 _D(b[0]), _D(b[1]), _I(b[2]), _I(b[3]), _D(b[4]), _D(_ad(p)), _ci(nph), _ci(ph), _D(q))
+    return q
+
+
 # ------------------------------------------------------------------ Newton glue
 _NAN = float("nan")
 

@@ -913,3 +913,160 @@ void orc_process_partition(const i64* N, i64 nf, i64 nc, const i64* partition, c
 void orc_partition_linear(i64 m, i64 n, i64* p) { for (i64 i = 1; i <= n; i++) p[i - 1] = (i64)std::ceil((double)i / ((double)n / (double)m)); }
 
 }  // extern "C"
+
+// ----------------------------------------------------------------------------
+// GMRES in the operation order of Krylov.jl 0.9.x `gmres!` (third-party, not
+// vendored; GenericKrylov() default solver, src/linsolve/krylov.jl:43,212-238):
+// Arnoldi with modified Gram-Schmidt, Givens rotations (sym_givens), x0 = 0,
+// memory 20; restart = false (Jutul's serial call: the basis grows past `memory`)
+// or true (ext/JutulPartitionedArraysExt/krylov.jl:67-74,126-146).
+// side: 0 right (N), 1 left (M), -1 none. hist = [|r0|, estimates...].
+// Returns 0 solved / 1 itmax / 2 breakdown.
+// ----------------------------------------------------------------------------
+extern "C" {
+static void sym_givens(double a, double b, double* c, double* s, double* rho) {
+    if (b == 0) { *c = (a == 0) ? 1.0 : sgn(a); *s = 0; *rho = std::fabs(a); }
+    else if (a == 0) { *c = 0; *s = sgn(b); *rho = std::fabs(b); }
+    else if (std::fabs(b) > std::fabs(a)) { double t = a / b; *s = sgn(b) / std::sqrt(1 + t * t); *c = *s * t; *rho = b / *s; }
+    else { double t = b / a; *c = sgn(a) / std::sqrt(1 + t * t); *s = *c * t; *rho = a / *c; }
+}
+int orc_gmres(i64 n, int bs, const i64* rowptr, const i64* colidx, const double* nz, void* ilu, int side, const double* b, double* x,
+              double rtol, double atol, i64 itmax, i64 memory, int restart, i64* iters, double* hist, i64 hist_cap) {
+    const i64 m = n * bs;
+    auto A = [&](const double* in, double* out) { orc_spmv(n, bs, rowptr, colidx, nz, 1.0, in, 0.0, out); };
+    auto P = [&](const double* in, double* out) { orc_ilu0_solve(ilu, in, out); };
+    const bool left = (side == 1 && ilu), right = (side == 0 && ilu);
+    std::vector<double> r0(m), w(m), q(m), p(m), xr(m, 0.0);
+    for (i64 i = 0; i < m; i++) x[i] = 0.0;
+    if (left) P(b, r0.data()); else vcopy(m, b, r0.data());
+    double beta = std::sqrt(vdot(m, r0.data(), r0.data()));
+    double rNorm = beta;
+    i64 nh = 0;
+    if (hist && nh < hist_cap) hist[nh++] = rNorm;
+    *iters = 0;
+    if (beta == 0) return 0;
+    const double eps = atol + rtol * rNorm;
+    const double btol = 2.220446049250313e-16;   // eps(T)^(3/4)? Krylov.jl uses btol = eps(T)^(3/4)
+    const double btol34 = std::pow(btol, 0.75);
+    i64 iter = 0, inner_itmax = itmax;
+    bool solved = rNorm <= eps, tired = iter >= itmax, breakdown = false;
+    std::vector<std::vector<double>> V;
+    std::vector<double> c, s, R, z;
+    while (!(solved || tired || breakdown)) {
+        i64 mem = memory;
+        V.assign(mem, std::vector<double>(m, 0.0));
+        c.assign(mem, 0.0); s.assign(mem, 0.0); z.assign(mem, 0.0); R.assign(mem * (mem + 1) / 2, 0.0);
+        i64 nr = 0;
+        if (restart) std::fill(xr.begin(), xr.end(), 0.0);
+        z[0] = beta;
+        for (i64 i = 0; i < m; i++) V[0][i] = r0[i] / rNorm;
+        i64 inner = 0;
+        bool inner_tired = false;
+        while (!(solved || inner_tired || breakdown)) {
+            inner++;
+            if (!restart && inner > mem) {
+                V.emplace_back(m, 0.0); z.push_back(0.0); c.push_back(0.0); s.push_back(0.0);
+                R.resize(R.size() + inner, 0.0);
+            }
+            const double* pv = V[inner - 1].data();
+            if (right) { P(V[inner - 1].data(), p.data()); pv = p.data(); }
+            A(pv, w.data());
+            if (left) P(w.data(), q.data()); else vcopy(m, w.data(), q.data());
+            for (i64 i = 1; i <= inner; i++) {
+                R[nr + i - 1] = vdot(m, V[i - 1].data(), q.data());
+                vaxpy(m, -R[nr + i - 1], V[i - 1].data(), q.data());
+            }
+            const double Hbis = std::sqrt(vdot(m, q.data(), q.data()));
+            for (i64 i = 1; i <= inner - 1; i++) {
+                const double Rtmp = c[i - 1] * R[nr + i - 1] + s[i - 1] * R[nr + i];
+                R[nr + i] = s[i - 1] * R[nr + i - 1] - c[i - 1] * R[nr + i];
+                R[nr + i - 1] = Rtmp;
+            }
+            double rho;
+            sym_givens(R[nr + inner - 1], Hbis, &c[inner - 1], &s[inner - 1], &rho);
+            R[nr + inner - 1] = rho;
+            const double zeta = s[inner - 1] * z[inner - 1];
+            z[inner - 1] = c[inner - 1] * z[inner - 1];
+            rNorm = std::fabs(zeta);
+            if (hist && nh < hist_cap) hist[nh++] = rNorm;
+            nr += inner;
+            const bool mach = (rNorm + 1.0 <= 1.0);
+            breakdown = Hbis <= btol34;
+            solved = (rNorm <= eps) || mach;
+            inner_tired = restart ? inner >= std::min(mem, inner_itmax) : inner >= inner_itmax;
+            if (!(solved || inner_tired || breakdown)) {
+                if (!restart && inner >= mem) { V.emplace_back(m, 0.0); z.push_back(0.0); }
+                for (i64 i = 0; i < m; i++) V[inner][i] = q[i] / Hbis;
+                z[inner] = zeta;
+            }
+        }
+        std::vector<double> y(z.begin(), z.begin() + inner);
+        for (i64 i = inner; i >= 1; i--) {
+            i64 pos = nr + i - inner - 1;   // 0-based position of r_{i,inner}
+            for (i64 j = inner; j >= i + 1; j--) { y[i - 1] -= R[pos] * y[j - 1]; pos = pos - j + 1; }
+            if (std::fabs(R[pos]) <= btol34) y[i - 1] = 0; else y[i - 1] = y[i - 1] / R[pos];
+        }
+        double* xt = restart ? xr.data() : x;
+        if (!restart) { /* x accumulates V*y directly; with right preconditioning N is applied to the whole sum */ }
+        std::vector<double> acc(m, 0.0);
+        for (i64 i = 1; i <= inner; i++) vaxpy(m, y[i - 1], V[i - 1].data(), acc.data());
+        if (right) { P(acc.data(), p.data()); for (i64 i = 0; i < m; i++) acc[i] = p[i]; }
+        if (restart) { for (i64 i = 0; i < m; i++) x[i] += acc[i]; }
+        else { for (i64 i = 0; i < m; i++) xt[i] = acc[i]; }
+        inner_itmax -= inner; iter += inner; tired = iter >= itmax;
+        if (restart && !(solved || tired || breakdown)) {
+            // r0 = M^{-1}(b - A x)
+            A(x, w.data());
+            for (i64 i = 0; i < m; i++) w[i] = b[i] - w[i];
+            if (left) P(w.data(), r0.data()); else vcopy(m, w.data(), r0.data());
+            beta = std::sqrt(vdot(m, r0.data(), r0.data()));
+            rNorm = beta;
+        }
+    }
+    *iters = iter;
+    if (solved) return 0;
+    if (breakdown) return 2;
+    return 1;
+}
+}  // extern "C"
+
+// ----------------------------------------------------------------------------
+// NFVM run-time flux, src/NFVM/evaluation.jl:1-88 with the types of
+// src/NFVM/types.jl:5-35. Per face a linear discretisation holds (left, right,
+// T_left, T_right, mpfa = [(cell, T)...]); the nonlinear one holds two of them
+// (ft_left, ft_right) and blends their half fluxes with the NTPFA/NMPFA weights.
+// Arrays are CSR over faces (ptr 1-based). p is nph x nc (column-major), ph 1-based.
+// scheme: 0 linear (evaluate_flux(p, hf::NFVMLinearDiscretization, ph)),
+//         1 :ntpfa, 2 :nmpfa (evaluate_flux(p, nfvm, ph)).
+// For scheme > 0 the R_* arrays describe ft_right; for scheme 0 they are ignored.
+// ----------------------------------------------------------------------------
+extern "C" void orc_nfvm_evaluate_flux(i64 nf, int scheme, const i64* left, const i64* right,
+                                       const double* L_Tl, const double* L_Tr, const i64* L_ptr, const i64* L_cell, const double* L_T,
+                                       const double* R_Tl, const double* R_Tr, const i64* R_ptr, const i64* R_cell, const double* R_T,
+                                       const double* p, i64 nph, i64 ph, double* q) {
+    auto P = [&](i64 c) { return p[(c - 1) * nph + (ph - 1)]; };
+    for (i64 f = 0; f < nf; f++) {
+        const double p_l = P(left[f]), p_r = P(right[f]);
+        auto compute_r = [&](const i64* ptr, const i64* cell, const double* T) {
+            double r = 0.0;
+            for (i64 k = ptr[f]; k <= ptr[f + 1] - 1; k++) r += P(cell[k - 1]) * T[k - 1];
+            return r;
+        };
+        if (scheme == 0) {
+            q[f] = (L_Tl[f] * p_l + L_Tr[f] * p_r) + compute_r(L_ptr, L_cell, L_T);
+            continue;
+        }
+        double r_l = compute_r(L_ptr, L_cell, L_T);
+        double q_l = (L_Tl[f] * p_l + L_Tr[f] * p_r); q_l += r_l;
+        double r_r = compute_r(R_ptr, R_cell, R_T);
+        double q_r = (R_Tl[f] * p_l + R_Tr[f] * p_r); q_r += r_r;
+        q_r = -1 * q_r; r_r = -1 * r_r;
+        double r_lw = r_l, r_rw = r_r;
+        if (scheme == 2) { r_lw = std::fabs(r_l); r_rw = std::fabs(r_r); }
+        const double r_total = r_lw + r_rw;
+        double mu_l, mu_r;
+        if (std::fabs(r_total) < 1e-10) { mu_l = mu_r = 0.5; }
+        else { mu_l = r_rw / r_total; mu_r = r_lw / r_total; }
+        q[f] = mu_l * q_l - mu_r * q_r;
+    }
+}

@@ -1,4 +1,4 @@
-"""Runs each hot kernel a few times on the 1M-cell (or given) workload — target command for ncu captures."""
+"""Runs each hot kernel a few times on the given workload (multicolour device numbering) — target command for ncu captures."""
 import sys
 sys.path.insert(0, '.')
 import numpy as np
@@ -8,7 +8,7 @@ dims = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "100,100,100").sp
 w = J.workloads.unstructured_hex(*dims)
 n = w["nc"]
 ctx = J.B200Context(0)
-sim = J.TwoPhaseSimulator(ctx, w["N"], n, w["Tf"], w["gdz"], w["pv"], w["params"])
+sim = J.TwoPhaseSimulator(ctx, w["N"], n, w["Tf"], w["gdz"], w["pv"], w["params"], ordering="multicolor")
 sim.set_forces(w["src_cells"], w["src_vals"])
 sim.set_state(w["p0"], w["sw0"])
 x = ctx.transfer(np.random.default_rng(0).standard_normal(2 * n)); y = ctx.zeros(2 * n)

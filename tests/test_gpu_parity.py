@@ -491,3 +491,56 @@ def test_distributed_matches_single_gpu(J):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29631", os.path.join(root, "tests", "dist_gpu_check.py")], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("side", ["right", "left", "none"])
+def test_gmres_matches_oracle(J, O, ctx, side):
+    """GenericKrylov() default solver: GMRES (Krylov.jl order, memory 20, restart = false, basis grows)."""
+    w, s, sim, nz, r = _jacobian_on_gpu(J, O, ctx, dims=(10, 9, 7))
+    n = w["nc"]
+    sim.jac.scale(sim.r, "diagonal")          # keeps the unpreconditioned case solvable
+    nz = sim.jac.nonzeros(); r = sim.r.get()
+    prec = None if side == "none" else sim.prec
+    kry = J.GenericKrylov(sim.jac, "gmres", prec, relative_tolerance=1e-8, precond_side="left" if side == "left" else "right",
+                          max_iterations=300)
+    ok, its, hist, st = J.linear_solve(kry, sim.r, sim.dx)
+    ilu = O.ILU0(n, 2, s["rowptr"], s["colidx"]); ilu.factor(nz)
+    x, st_o, its_o, hist_o = O.gmres(n, 2, s["rowptr"], s["colidx"], nz, r, ilu if side != "none" else None, side=side, rtol=1e-8, itmax=300)
+    assert ok and st == 0 and st_o == 0
+    assert its > 20 or side != "none"          # the basis grows past memory = 20 without restart
+    assert abs(its - its_o) <= 1
+    m = min(len(hist), len(hist_o))
+    assert np.allclose(hist[:m], hist_o[:m], rtol=1e-5, atol=1e-12 * hist[0])   # residual estimates, iteration by iteration
+    assert np.all(np.diff(hist) <= 1e-12 * hist[0])
+    dx = sim.dx.get()
+    assert np.linalg.norm(dx + x) <= 1e-6 * np.linalg.norm(x)
+    A = to_scipy(n, 2, s["rowptr"], s["colidx"], nz)
+    if side != "left":
+        assert abs(np.linalg.norm(r + A @ dx) - hist[-1]) <= 1e-6 * hist[0]
+    # zero right-hand side and iteration cap
+    ok, its, hist, st = J.linear_solve(kry, ctx.zeros(2 * n), sim.dx)
+    assert ok and its == 0 and np.all(sim.dx.get() == 0)
+    kry2 = J.GenericKrylov(sim.jac, "gmres", prec, relative_tolerance=1e-30, max_iterations=3)
+    ok, its, hist, st = J.linear_solve(kry2, sim.r, sim.dx)
+    assert (not ok) and st == J.JB_NOT_CONVERGED and its == 3
+
+
+@pytest.mark.parametrize("scheme", ["linear", "ntpfa", "nmpfa"])
+def test_nfvm_evaluate_flux_matches_oracle(J, O, ctx, scheme):
+    from test_oracle_linear import _nfvm_case
+    rng = np.random.default_rng(7)
+    nc, nph = 300, 2
+    left, right, L, R, p = _nfvm_case(rng, nc=nc, nf=1000, nph=nph)
+    d = J.NFVMDiscretization(ctx, left, right, nc, L, None if scheme == "linear" else R, scheme)
+    dp, dq = ctx.transfer(p), ctx.zeros(left.shape[0])
+    for ph in (1, 2):
+        d.evaluate_flux(dp, dq, nph, ph)
+        ref = O.nfvm_evaluate_flux(left, right, L, None if scheme == "linear" else R, p, nph, ph, scheme)
+        scale = np.abs(ref).max()
+        assert np.abs(dq.get() - ref).max() <= 1e-12 * scale
+    # empty remainders and a single face
+    e = dict(T_left=np.array([2.0]), T_right=np.array([-2.0]), ptr=np.array([1, 1]), cell=np.zeros(0, dtype=np.int64), T=np.zeros(0))
+    d1 = J.NFVMDiscretization(ctx, [1], [2], 2, e, e if scheme != "linear" else None, scheme)
+    q1 = ctx.zeros(1)
+    d1.evaluate_flux(ctx.transfer(np.array([3.0, 1.0])), q1)
+    assert q1.get()[0] == (4.0 if scheme == "linear" else 0.5 * 4.0 - 0.5 * (-4.0))

@@ -178,3 +178,59 @@ def test_scaling(O, J):
     d = A2.toarray()
     for c in range(n):
         assert np.allclose(d[2 * c:2 * c + 2, 2 * c:2 * c + 2], np.eye(2), atol=1e-8)
+
+
+@pytest.mark.parametrize("side,restart", [("right", False), ("left", False), ("none", False), ("right", True)])
+def test_gmres_solves(O, J, side, restart):
+    """Krylov.jl gmres! restatement: monotone residual estimates, true residual matches the estimate (right/none)."""
+    w, s, M0, p, nz, r = _twophase_system(O, J)
+    n = w["nc"]
+    O.scale_diagonal(n, 2, s["rowptr"], s["colidx"], nz, r)
+    A = to_scipy(n, 2, s["rowptr"], s["colidx"], nz)
+    ilu = O.ILU0(n, 2, s["rowptr"], s["colidx"]); ilu.factor(nz)
+    x, st, its, hist = O.gmres(n, 2, s["rowptr"], s["colidx"], nz, r, ilu if side != "none" else None, side=side, rtol=1e-9,
+                               itmax=400, memory=20, restart=restart)
+    assert st == 0 and its >= 1
+    if not restart:
+        assert hist.shape[0] == its + 1 and np.all(np.diff(hist) <= 1e-14 * hist[0])     # GMRES residuals never increase
+    xd = spla.spsolve(A.tocsc(), r)
+    assert np.linalg.norm(x - xd) <= 1e-5 * np.linalg.norm(xd)
+    if side != "left":
+        assert abs(np.linalg.norm(r - A @ x) - hist[-1]) <= 1e-6 * hist[0]
+
+
+def _nfvm_case(rng, nc=50, nf=120, nph=2, max_mpfa=5):
+    left = rng.integers(1, nc + 1, nf); right = (left + rng.integers(0, nc - 1, nf)) % nc + 1
+
+    def half():
+        cnt = rng.integers(0, max_mpfa + 1, nf)
+        ptr = np.concatenate([[1], 1 + np.cumsum(cnt)])
+        return dict(T_left=rng.standard_normal(nf), T_right=rng.standard_normal(nf), ptr=ptr, cell=rng.integers(1, nc + 1, ptr[-1] - 1),
+                    T=rng.standard_normal(ptr[-1] - 1))
+    return left, right, half(), half(), rng.standard_normal(nph * nc)
+
+
+def test_nfvm_evaluate_flux_oracle(O):
+    """src/NFVM/evaluation.jl: linear scheme with an empty MPFA remainder is the TPFA flux T_l p_l + T_r p_r; the
+    nonlinear blend reduces to 0.5 (q_l - q_r) when both remainders vanish."""
+    rng = np.random.default_rng(0)
+    left, right, L, R, p = _nfvm_case(rng, nph=1)
+    q = O.nfvm_evaluate_flux(left, right, L, None, p, scheme="linear")
+    ref = np.array([L["T_left"][f] * p[left[f] - 1] + L["T_right"][f] * p[right[f] - 1]
+                    + sum(p[L["cell"][k - 1] - 1] * L["T"][k - 1] for k in range(L["ptr"][f], L["ptr"][f + 1])) for f in range(left.shape[0])])
+    assert np.allclose(q, ref, rtol=1e-14, atol=1e-14)
+    empty = lambda d: dict(d, ptr=np.ones_like(d["ptr"]), cell=np.zeros(0, dtype=np.int64), T=np.zeros(0))
+    Le, Re = empty(L), empty(R)
+    qn = O.nfvm_evaluate_flux(left, right, Le, Re, p, scheme="ntpfa")
+    ql = Le["T_left"] * p[left - 1] + Le["T_right"] * p[right - 1]
+    qr = -(Re["T_left"] * p[left - 1] + Re["T_right"] * p[right - 1])
+    assert np.allclose(qn, 0.5 * ql - 0.5 * qr, rtol=1e-14, atol=1e-14)
+    # the weights sum to one: mu_l + mu_r = 1 => q lies between the two half fluxes for :nmpfa
+    qm = O.nfvm_evaluate_flux(left, right, L, R, p, scheme="nmpfa")
+    rl = np.array([sum(p[L["cell"][k - 1] - 1] * L["T"][k - 1] for k in range(L["ptr"][f], L["ptr"][f + 1])) for f in range(left.shape[0])])
+    rr = -np.array([sum(p[R["cell"][k - 1] - 1] * R["T"][k - 1] for k in range(R["ptr"][f], R["ptr"][f + 1])) for f in range(left.shape[0])])
+    q_l = L["T_left"] * p[left - 1] + L["T_right"] * p[right - 1] + rl
+    q_r = -(R["T_left"] * p[left - 1] + R["T_right"] * p[right - 1]) + rr
+    tot = np.abs(rl) + np.abs(rr)
+    mu_l = np.where(tot < 1e-10, 0.5, np.abs(rr) / np.where(tot == 0, 1, tot)); mu_r = np.where(tot < 1e-10, 0.5, np.abs(rl) / np.where(tot == 0, 1, tot))
+    assert np.allclose(qm, mu_l * q_l - mu_r * q_r, rtol=1e-13, atol=1e-13)
