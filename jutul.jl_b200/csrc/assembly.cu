@@ -176,6 +176,93 @@ __global__ void __launch_bounds__(256, 4) twophase_assemble_kernel(i64 nc, TPPar
     }
 }
 
+
+// ---- row-chunk stream form of the fused assembly (default) --------------------------------------------------
+// A CTA owns a chunk of <= 128 consecutive cells / <= 1024 half-faces. All threads stream the chunk's half-face
+// arrays (other, T, sign*gdz, Jacobian position) with unit stride, find the owning cell by bisection of the chunk's
+// offsets in shared memory, gather the two 32-byte cell records, evaluate both perspectives of the two-point flux,
+// write the off-diagonal block straight to its slot in the row and park the (residual, diagonal) contribution of the
+// half-face in shared memory. One thread per cell then adds accumulation + half-faces in conn_pos order (the order of
+// fill_conservation_eq!, src/conservation/conservation.jl:373-430) and writes r and the diagonal block.
+#define JB_ASM_CELLS 64
+#define JB_ASM_HF 512
+#define JB_ASM_THREADS 128
+template <bool JAC>
+__global__ void __launch_bounds__(JB_ASM_THREADS) twophase_assemble_stream_kernel(int nchunks, const int32_t* __restrict__ chunk_ptr, TPParams P,
+                                                                       const int32_t* __restrict__ hf_pos, const int32_t* __restrict__ hf_other,
+                                                                       const int32_t* __restrict__ hf_rowpos, const double* __restrict__ hf_T,
+                                                                       const double* __restrict__ hf_sgdz, const int32_t* __restrict__ diag_pos,
+                                                                       const double4* __restrict__ rec, const double* __restrict__ pv,
+                                                                       const double* __restrict__ M0, const double* __restrict__ src, double inv_dt,
+                                                                       double* __restrict__ nz, double* __restrict__ r) {
+    __shared__ int32_t s_pos[JB_ASM_CELLS + 1];
+    __shared__ unsigned char s_owner[JB_ASM_HF];   // chunk-local cell of each half-face
+    extern __shared__ double s_part[];     // [6][JB_ASM_HF + pad]: r_w, r_o, d(w)/dp, d(o)/dp, d(w)/dS, d(o)/dS per half-face
+    constexpr int NP = JAC ? 6 : 2;
+    constexpr int LD = JB_ASM_HF + 1;
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const int c0 = __ldg(chunk_ptr + ch), nr = __ldg(chunk_ptr + ch + 1) - c0;
+        for (int j = threadIdx.x; j <= nr; j += blockDim.x) s_pos[j] = __ldg(hf_pos + c0 + j);
+        __syncthreads();
+        const int base = s_pos[0], cnt = s_pos[nr] - base;
+        for (int j = threadIdx.x; j < nr; j += blockDim.x)
+            for (int e = s_pos[j] - base; e < s_pos[j + 1] - base; e++) s_owner[e] = (unsigned char)j;
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+            const int i = base + e;
+            const int32_t o = __ldcs(hf_other + i);
+            const double T = __ldcs(hf_T + i), sg = __ldcs(hf_sgdz + i);
+            const CellP self = cell_props(P, ld_rec(rec + c0 + s_owner[e]));
+            const CellP other = cell_props(P, ld_rec(rec + o));
+            double part[6], blk[4];
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                double F, dFdp, dFds;
+                flux_phase(P, self, other, a, T, sg, F, dFdp, dFds);
+                part[a] = F; part[2 + a] = dFdp; part[4 + a] = dFds;
+                if (JAC) {
+                    double Fo, dFo_dp, dFo_ds;
+                    flux_phase(P, other, self, a, T, -sg, Fo, dFo_dp, dFo_ds);   // the neighbour's half-face towards us
+                    blk[a] = -dFo_dp; blk[2 + a] = -dFo_ds;
+                }
+            }
+            if (JAC) {
+                double2* dst = reinterpret_cast<double2*>(nz + (size_t)__ldcs(hf_rowpos + i) * 4);
+                dst[0] = make_double2(blk[0], blk[1]);
+                dst[1] = make_double2(blk[2], blk[3]);
+            }
+#pragma unroll
+            for (int q = 0; q < NP; q++) s_part[q * LD + e] = part[q];
+        }
+        __syncthreads();
+        // two threads per cell: thread (j, a) owns equation a -> r[a], d/dp, d/dS
+        for (int w = threadIdx.x; w < 2 * nr; w += blockDim.x) {
+            const int j = w >> 1, a = w & 1;
+            const size_t c = (size_t)c0 + j;
+            const double4 rs = ld_rec(rec + c);
+            const double S = a ? 1.0 - rs.y : rs.y;
+            const double dS = a ? -1.0 : 1.0;
+            const double rho = a ? rs.w : rs.z;
+            const double pvc = __ldg(pv + c);
+            const double mass = pvc * (rho * S);
+            double ar = (mass - __ldg(M0 + 2 * c + a)) * inv_dt;
+            if (src) ar += __ldg(src + 2 * c + a);
+            double adp = (pvc * (P.c[a] * rho * S)) * inv_dt;
+            double ads = (pvc * (rho * dS)) * inv_dt;
+            for (int e = s_pos[j] - base; e < s_pos[j + 1] - base; e++) {
+                ar += s_part[a * LD + e];
+                if (JAC) { adp += s_part[(2 + a) * LD + e]; ads += s_part[(4 + a) * LD + e]; }
+            }
+            r[2 * c + a] = ar;
+            if (JAC) {
+                double* dst = nz + (size_t)__ldg(diag_pos + c) * 4;
+                dst[a] = adp; dst[2 + a] = ads;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- variant B: face-parallel with atomics -----------------------------------------------
 __global__ void __launch_bounds__(256) twophase_acc_kernel(i64 nc, TPParams P, const double4* __restrict__ rec, const double* __restrict__ pv,
                                                            const double* __restrict__ M0, const double* __restrict__ src, double dt,
@@ -278,6 +365,35 @@ int jb_launch_twophase_assemble(jb_twophase* m, const double* d_M0, double dt, d
     const i64 cells_per_cta = 256 / LPC;
     const int grid = (int)std::max<i64>(1, (nc + cells_per_cta - 1) / cells_per_cta);
     const double* src = m->nsrc > 0 ? m->d_src.p : nullptr;
+    if (!m->h_chunks.empty()) {
+        // chunks were cut over all local cells; a distributed run assembles the owned prefix only
+        int nchunks = (int)m->h_chunks.size() - 1;
+        if (m->n_assemble >= 0) nchunks = m->n_chunks_owned;
+        const size_t smem = (size_t)(jac ? 6 : 2) * (JB_ASM_HF + 1) * sizeof(double);
+        static int per_sm[2] = {0, 0};
+        if (per_sm[jac] == 0) {
+            if (jac) {
+                cudaFuncSetAttribute(twophase_assemble_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], twophase_assemble_stream_kernel<true>, JB_ASM_THREADS, smem);
+            } else {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], twophase_assemble_stream_kernel<false>, JB_ASM_THREADS, smem);
+            }
+            if (per_sm[jac] < 1) per_sm[jac] = 1;
+        }
+        const int g = std::max(1, std::min(nchunks, ctx->sm_count * per_sm[jac]));
+        if (jac)
+            twophase_assemble_stream_kernel<true><<<g, JB_ASM_THREADS, smem, ctx->stream>>>(nchunks, m->d_chunks.p, make_params(m), t->mesh->d_hf_pos.p,
+                                                                                 t->mesh->d_hf_other.p, t->d_hf_rowpos.p, m->d_hf_T.p, m->d_hf_sgdz.p,
+                                                                                 t->csr->d_diag.p, reinterpret_cast<const double4*>(m->d_rec.p),
+                                                                                 m->d_pv.p, d_M0, src, 1.0 / dt, t->csr->d_val.p, d_r);
+        else
+            twophase_assemble_stream_kernel<false><<<g, JB_ASM_THREADS, smem, ctx->stream>>>(nchunks, m->d_chunks.p, make_params(m), t->mesh->d_hf_pos.p,
+                                                                                  t->mesh->d_hf_other.p, t->d_hf_rowpos.p, m->d_hf_T.p, m->d_hf_sgdz.p,
+                                                                                  t->csr->d_diag.p, reinterpret_cast<const double4*>(m->d_rec.p),
+                                                                                  m->d_pv.p, d_M0, src, 1.0 / dt, t->csr->d_val.p, d_r);
+        JB_CHECK_LAUNCH(ctx);
+        return JB_OK;
+    }
     if (jac)
         twophase_assemble_kernel<LPC, true><<<grid, 256, 0, ctx->stream>>>(nc, make_params(m), t->mesh->d_hf_pos.p, t->mesh->d_hf_other.p,
                                                                            t->d_hf_rowpos.p, m->d_hf_T.p, m->d_hf_sgdz.p, t->csr->d_diag.p,
@@ -340,7 +456,22 @@ int32_t jb_twophase_create(jb_tpfa* t, const double* Tf, const double* gdz, cons
             const int32_t f = mesh->h_hf_face[i];
             if (mesh->h_hf_sign[i] > 0) plr[f] = t->h_hf_rowpos[i]; else prl[f] = t->h_hf_rowpos[i];
         }
+    // row chunks for the stream assembly kernel (<= JB_ASM_CELLS cells, <= JB_ASM_HF half-faces)
+    {
+        int32_t start = 0;
+        bool fits = true;
+        const int32_t ncell = (int32_t)mesh->nc;
+        while (start < ncell) {
+            int32_t end = start;
+            while (end < ncell && end - start < JB_ASM_CELLS && mesh->h_hf_pos[end + 1] - mesh->h_hf_pos[start] <= JB_ASM_HF) end++;
+            if (end == start) { fits = false; break; }
+            m->h_chunks.push_back(start);
+            start = end;
+        }
+        if (fits) m->h_chunks.push_back(ncell); else m->h_chunks.clear();
+    }
     cudaStream_t s = ctx->stream;
+    if (!m->h_chunks.empty() && m->d_chunks.upload(m->h_chunks, s) != cudaSuccess) { delete m; JB_FAIL(ctx, JB_ERR_ALLOC, "jb_twophase_create: device allocation failed"); }
     bool ok = m->d_hf_T.upload(hT, s) == cudaSuccess && m->d_hf_sgdz.upload(hG, s) == cudaSuccess && m->d_face_T.upload(fT, s) == cudaSuccess &&
               m->d_face_gdz.upload(fG, s) == cudaSuccess && m->d_pv.upload(hpv, s) == cudaSuccess && m->d_pos_lr.upload(plr, s) == cudaSuccess &&
               m->d_pos_rl.upload(prl, s) == cudaSuccess && m->d_rec.alloc((size_t)mesh->nc * 4) == cudaSuccess;
@@ -352,6 +483,27 @@ int32_t jb_twophase_destroy(jb_twophase* m) { delete m; return JB_OK; }
 int32_t jb_twophase_set_owned(jb_twophase* m, int64_t n_owned) {
     if (!m || n_owned > m->t->mesh->nc) return JB_ERR_ARG;
     m->n_assemble = n_owned;
+    if (n_owned >= 0 && !m->h_chunks.empty()) {
+        // re-cut so that a chunk boundary falls exactly on n_owned
+        jb_mesh* mesh = m->t->mesh;
+        m->h_chunks.clear();
+        const int32_t bounds[2] = {(int32_t)n_owned, (int32_t)mesh->nc};
+        int32_t start = 0;
+        bool fits = true;
+        m->n_chunks_owned = 0;
+        for (int part = 0; part < 2 && fits; part++) {
+            while (start < bounds[part]) {
+                int32_t end = start;
+                while (end < bounds[part] && end - start < JB_ASM_CELLS && mesh->h_hf_pos[end + 1] - mesh->h_hf_pos[start] <= JB_ASM_HF) end++;
+                if (end == start) { fits = false; break; }
+                m->h_chunks.push_back(start);
+                start = end;
+            }
+            if (part == 0) m->n_chunks_owned = (int)m->h_chunks.size();
+        }
+        if (fits) m->h_chunks.push_back((int32_t)mesh->nc); else m->h_chunks.clear();
+        if (!m->h_chunks.empty() && m->d_chunks.upload(m->h_chunks, mesh->ctx->stream) != cudaSuccess) return JB_ERR_ALLOC;
+    }
     return JB_OK;
 }
 

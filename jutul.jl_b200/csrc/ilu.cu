@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) ilu_sweep_stream_kernel(int c0, int c1, c
 #pragma unroll
             for (int e = 0; e < BS; e++) v[e] = BACKWARD ? x[(size_t)i * BS + e] : b[(size_t)i * BS + e];
         }
-        stream_chunk_products<BS, 4>(t0, nr, ptrT, col, fv, val_block_offset, x, s_rp, s_prod);
+        stream_chunk_products<BS, JB_STREAM_U>(t0, nr, ptrT, col, fv, val_block_offset, x, s_rp, s_prod);
         if ((int)threadIdx.x < nr) {
             double acc[BS];
             stream_row_sum<BS>(threadIdx.x, s_rp, s_prod, acc);

@@ -152,6 +152,9 @@ struct jb_twophase {
     DBuf<double> d_src_vals;
     i64 nsrc = 0;
     i64 n_assemble = -1;              // rows to assemble (owned cells of a distributed run); -1 = all
+    std::vector<int32_t> h_chunks;    // cell chunks of the stream assembly kernel
+    DBuf<int32_t> d_chunks;
+    int n_chunks_owned = 0;
     // resident state for the host-facing perform_step
     DBuf<double> d_p, d_s, d_M0, d_r, d_dx;
 };

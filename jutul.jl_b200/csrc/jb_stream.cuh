@@ -16,6 +16,9 @@
 
 #define JB_CHUNK_ROWS 256
 #define JB_CHUNK_CAP 2048   // entries (blocks) per chunk tile
+#ifndef JB_STREAM_U
+#define JB_STREAM_U 2      // entries in flight per thread in the streaming phase
+#endif
 
 template <int BS> struct StreamLoad;
 template <> struct StreamLoad<1> {

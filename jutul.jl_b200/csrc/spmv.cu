@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) spmv_stream_kernel(int nchunks, const int
     double d0 = 0.0, d1 = 0.0;
     for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const int t0 = __ldg(chunk_ptr + c), nr = __ldg(chunk_ptr + c + 1) - t0;
-        stream_chunk_products<BS, 4>(t0, nr, rowptr, colidx, val, 0, x, s_rp, s_prod);
+        stream_chunk_products<BS, JB_STREAM_U>(t0, nr, rowptr, colidx, val, 0, x, s_rp, s_prod);
         if ((int)threadIdx.x < nr) {
             const size_t row = (size_t)t0 + threadIdx.x;
             double acc[BS];
