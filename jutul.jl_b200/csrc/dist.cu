@@ -27,7 +27,44 @@ struct jb_dist {
     DBuf<int32_t> d_send_idx;               // owned local cell ids to pack, grouped by neighbour
     DBuf<double> d_send_buf;                // packed values (max block size 4)
     i64 nsend;
+    // ---- peer-memory path (NVLink loads/stores on IPC-mapped buffers; no NCCL on the data path) ----
+    bool p2p = false;
+    double* sym = nullptr;                  // this rank's symmetric buffer (cudaMalloc, exported through IPC)
+    std::vector<double*> peer_sym;          // every rank's symmetric buffer mapped into this process (own entry = sym)
+    DBuf<double*> d_peer_sym;
+    DBuf<int32_t> d_neigh;                  // neighbour ranks
+    DBuf<i64> d_send_ptr, d_recv_ptr, d_remote_off, d_remote_cap;   // per neighbour: remote_off = where my data starts in the neighbour's staging, remote_cap = its ghost count
+    DBuf<unsigned int> d_ticket;
+    DBuf<int32_t> d_err;
+    unsigned long long ar_epoch = 0, halo_epoch = 0;
+    i64 stage_cap = 0;                      // ghost cells (staging holds 2 parities x stage_cap x 4 doubles)
 };
+
+// symmetric buffer layout (in doubles / 8-byte words)
+#define JB_P2P_MAXW 16
+#define JB_P2P_NRED 4
+__host__ __device__ inline size_t p2p_ar_slot(int parity, int rank) { return ((size_t)parity * JB_P2P_MAXW + rank) * JB_P2P_NRED; }
+__host__ __device__ inline size_t p2p_ar_flag(int parity, int rank) { return 2 * JB_P2P_MAXW * JB_P2P_NRED + (size_t)parity * JB_P2P_MAXW + rank; }
+__host__ __device__ inline size_t p2p_halo_flag(int parity, int rank) { return 2 * JB_P2P_MAXW * JB_P2P_NRED + 2 * JB_P2P_MAXW + (size_t)parity * JB_P2P_MAXW + rank; }
+__host__ __device__ inline size_t p2p_stage_base() { return 2 * JB_P2P_MAXW * JB_P2P_NRED + 4 * JB_P2P_MAXW; }
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// bounded spin: a lost peer must never hang the GPU (returns false on timeout)
+__device__ __forceinline__ bool p2p_wait(const unsigned long long* flag, unsigned long long epoch) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < epoch) {
+        if (clock64() - t0 > 60000000000LL) return false;   // ~30 s: ranks may reach a collective seconds apart (host skew)
+        __nanosleep(40);
+    }
+    return true;
+}
 
 #define JB_NCCL(ctx, call)                                                                         \
     do {                                                                                           \
@@ -49,6 +86,132 @@ __global__ void __launch_bounds__(256) halo_pack_kernel(i64 n, const int32_t* __
     }
 }
 
+
+// ---- fused all-reduce + scalar recurrence over peer memory ------------------------------------------------
+// One warp: lane q pushes this rank's partial sums into rank q's slot table (NVLink store), publishes the epoch with a
+// release store, then waits for rank q's epoch in the local table. Lane 0 adds the slots in rank order, so every
+// rank obtains bitwise the same totals, and applies the Krylov scalar recurrence (jb_krylov_scalars.cuh) in place:
+// the all-reduce and its consumer are ONE kernel with no NCCL call and no extra launch.
+#include "jb_krylov_scalars.cuh"
+__global__ void p2p_allreduce_kernel(double* const* __restrict__ peers, int rank, int world, unsigned long long epoch, double* vals, int n,
+                                     int op_max, int fin_which, double* sc, double* hist, int hist_cap, int32_t* err) {
+    const int lane = threadIdx.x;
+    const int parity = (int)(epoch & 1ULL);
+    if (lane < world) {
+        double* dst = peers[lane];
+        for (int k = 0; k < n; k++) dst[p2p_ar_slot(parity, rank) + k] = vals[k];
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long*>(dst) + p2p_ar_flag(parity, rank), epoch);
+    }
+    bool ok = true;
+    if (lane < world) ok = p2p_wait(reinterpret_cast<unsigned long long*>(peers[rank]) + p2p_ar_flag(parity, lane), epoch);
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        if (!ok) *err = 1;
+        __threadfence_system();
+        const double* mine = peers[rank];
+        for (int k = 0; k < n; k++) {
+            double a = __ldcv(mine + p2p_ar_slot(parity, 0) + k);
+            for (int q = 1; q < world; q++) {
+                const double b = __ldcv(mine + p2p_ar_slot(parity, q) + k);
+                a = op_max ? ((a != a) ? a : ((b != b) ? b : fmax(a, b))) : a + b;
+            }
+            vals[k] = a;
+        }
+        if (fin_which == 0) ks_fin_init(sc, hist);
+        else if (fin_which > 0 && sc[KS_DONE] == 0.0) {
+            if (fin_which == 1) ks_fin_alpha(sc);
+            else if (fin_which == 2) ks_fin_omega(sc);
+            else if (fin_which == 3) ks_fin_update2(sc, hist, hist_cap);
+        }
+    }
+}
+
+// ---- halo exchange over peer memory -----------------------------------------------------------------------
+// push: every thread stores one boundary cell straight into the neighbour's staging area (NVLink), the last CTA
+// publishes the epoch to all neighbours. pull: waits for the neighbours' epochs and copies staging -> ghost section.
+template <int BS>
+__global__ void __launch_bounds__(256) p2p_halo_push_kernel(double* const* __restrict__ peers, int rank, int nneigh, const int32_t* __restrict__ neigh,
+                                                            const i64* __restrict__ send_ptr, const i64* __restrict__ remote_off,
+                                                            const int32_t* __restrict__ send_idx, const double* __restrict__ vec, i64 nsend,
+                                                            unsigned long long epoch, const i64* __restrict__ remote_cap, unsigned int* ticket) {
+    const int parity = (int)(epoch & 1ULL);
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nsend; i += (i64)gridDim.x * blockDim.x) {
+        int k = 0;
+        while (k + 1 < nneigh && i >= send_ptr[k + 1]) k++;
+        double* dst = peers[neigh[k]] + p2p_stage_base() + ((size_t)parity * remote_cap[k] + remote_off[k] + (i - send_ptr[k])) * 4;
+        const size_t c = (size_t)__ldg(send_idx + i);
+#pragma unroll
+        for (int e = 0; e < BS; e++) dst[e] = vec[c * BS + e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+    __syncthreads();
+    if (last && (int)threadIdx.x < nneigh) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long*>(peers[neigh[threadIdx.x]]) + p2p_halo_flag(parity, rank), epoch);
+    }
+}
+template <int BS>
+__global__ void __launch_bounds__(256) p2p_halo_pull_kernel(double* mine, int nneigh, const int32_t* __restrict__ neigh, i64 n_owned, i64 n_ghost,
+                                                            i64 stage_cap, double* __restrict__ vec, unsigned long long epoch, int32_t* err) {
+    const int parity = (int)(epoch & 1ULL);
+    __shared__ bool ok_s;
+    if (threadIdx.x < 32) {
+        bool ok = true;
+        for (int k = threadIdx.x; k < nneigh; k += 32)
+            ok = ok && p2p_wait(reinterpret_cast<unsigned long long*>(mine) + p2p_halo_flag(parity, neigh[k]), epoch);
+        ok = __all_sync(0xffffffffu, ok);
+        if (threadIdx.x == 0) { ok_s = ok; if (!ok) *err = 2; }
+    }
+    __syncthreads();
+    if (!ok_s) return;
+    const double* stage = mine + p2p_stage_base() + (size_t)parity * stage_cap * 4;
+    for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n_ghost; g += (i64)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int e = 0; e < BS; e++) vec[(n_owned + g) * BS + e] = __ldcv(stage + (size_t)g * 4 + e);
+    }
+}
+
+static int p2p_halo_launch(jb_dist* D, double* d_vec, int bs) {
+    jb_ctx* ctx = D->comm->ctx;
+    cudaStream_t st = ctx->stream;
+    const unsigned long long epoch = ++D->halo_epoch;
+    const i64 n_ghost = D->n_local - D->n_owned;
+    const int gp = (int)std::max<i64>(1, std::min<i64>((D->nsend + 255) / 256, (i64)ctx->sm_count * 2));
+    const int gq = (int)std::max<i64>(1, std::min<i64>((n_ghost + 255) / 256, (i64)ctx->sm_count * 2));
+#define JB_P2P_HALO(BS)                                                                                                                      \
+    p2p_halo_push_kernel<BS><<<gp, 256, 0, st>>>(D->d_peer_sym.p, D->comm->rank, D->nneigh, D->d_neigh.p, D->d_send_ptr.p, D->d_remote_off.p,    \
+                                                 D->d_send_idx.p, d_vec, D->nsend, epoch, D->d_remote_cap.p, D->d_ticket.p);                  \
+    JB_CHECK_LAUNCH(ctx);                                                                                                                    \
+    p2p_halo_pull_kernel<BS><<<gq, 256, 0, st>>>(D->sym, D->nneigh, D->d_neigh.p, D->n_owned, n_ghost, D->stage_cap, d_vec, epoch, D->d_err.p); \
+    JB_CHECK_LAUNCH(ctx);
+    switch (bs) {
+        case 1: JB_P2P_HALO(1) break;
+        case 2: JB_P2P_HALO(2) break;
+        case 3: JB_P2P_HALO(3) break;
+        case 4: JB_P2P_HALO(4) break;
+        default: return JB_ERR_UNSUPPORTED;
+    }
+#undef JB_P2P_HALO
+    return JB_OK;
+}
+
+// all-reduce of d_buf[0..n) fused with the Krylov scalar recurrence `fin_which` (-1: none)
+int jb_dist_allreduce_fin_launch(jb_dist* D, double* d_buf, int n, int op_max, int fin_which, double* sc, double* hist, int hist_cap) {
+    jb_ctx* ctx = D->comm->ctx;
+    if (!D->p2p) return JB_ERR_UNSUPPORTED;
+    ProfScope _ps(ctx, JB_PROF_OTHER);
+    const unsigned long long epoch = ++D->ar_epoch;
+    p2p_allreduce_kernel<<<1, 32, 0, ctx->stream>>>(D->d_peer_sym.p, D->comm->rank, D->comm->world, epoch, d_buf, n, op_max, fin_which, sc, hist,
+                                                    hist_cap, D->d_err.p);
+    JB_CHECK_LAUNCH(ctx);
+    return JB_OK;
+}
+bool jb_dist_is_p2p(jb_dist* D) { return D && D->p2p; }
+
 i64 jb_dist_n_owned(jb_dist* D) { return D->n_owned; }
 
 int jb_dist_halo_launch(jb_dist* D, double* d_vec, int bs) {
@@ -56,6 +219,7 @@ int jb_dist_halo_launch(jb_dist* D, double* d_vec, int bs) {
     cudaStream_t st = ctx->stream;
     if (D->nneigh == 0) return JB_OK;
     ProfScope _ps(ctx, JB_PROF_OTHER);
+    if (D->p2p) return p2p_halo_launch(D, d_vec, bs);
     if (D->nsend > 0) {
         const int g = (int)std::max<i64>(1, std::min<i64>((D->nsend + 255) / 256, (i64)ctx->sm_count * 4));
         switch (bs) {
@@ -79,6 +243,7 @@ int jb_dist_halo_launch(jb_dist* D, double* d_vec, int bs) {
 
 int jb_dist_allreduce_launch(jb_dist* D, double* d_buf, int n, int op_max) {
     jb_ctx* ctx = D->comm->ctx;
+    if (D->p2p) return jb_dist_allreduce_fin_launch(D, d_buf, n, op_max, -1, nullptr, nullptr, 0);
     ProfScope _ps(ctx, JB_PROF_OTHER);
     JB_NCCL(ctx, ncclAllReduce(d_buf, d_buf, (size_t)n, ncclDouble, op_max ? ncclMax : ncclSum, D->comm->comm, ctx->stream));
     return JB_OK;
@@ -137,7 +302,68 @@ int32_t jb_dist_create(jb_comm* comm, int64_t n_owned, int64_t n_local, int32_t 
     *out = D;
     return JB_OK;
 }
-int32_t jb_dist_destroy(jb_dist* D) { delete D; return JB_OK; }
+int32_t jb_dist_destroy(jb_dist* D) {
+    if (D) {
+        for (size_t q = 0; q < D->peer_sym.size(); q++)
+            if (D->peer_sym[q] && D->peer_sym[q] != D->sym) cudaIpcCloseMemHandle(D->peer_sym[q]);
+        if (D->sym) cudaFree(D->sym);
+    }
+    delete D;
+    return JB_OK;
+}
+
+// Peer-memory setup, step 1: allocate this rank's symmetric buffer and export it (64-byte cudaIpcMemHandle).
+int32_t jb_dist_p2p_export(jb_dist* D, char* handle64) {
+    if (!D || !handle64) return JB_ERR_ARG;
+    jb_ctx* ctx = D->comm->ctx;
+    if (D->comm->world > JB_P2P_MAXW) JB_FAIL(ctx, JB_ERR_UNSUPPORTED, "jb_dist_p2p_export: world size above JB_P2P_MAXW");
+    D->stage_cap = std::max<i64>(D->n_local - D->n_owned, 1);
+    const size_t words = p2p_stage_base() + (size_t)2 * D->stage_cap * 4;
+    JB_CUDA(ctx, cudaMalloc((void**)&D->sym, words * sizeof(double)));
+    JB_CUDA(ctx, cudaMemset(D->sym, 0, words * sizeof(double)));
+    cudaIpcMemHandle_t h;
+    JB_CUDA(ctx, cudaIpcGetMemHandle(&h, D->sym));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    memcpy(handle64, &h, 64);
+    return JB_OK;
+}
+// Step 2 (after an all-gather of the handles and of every rank's receive offsets by the launcher):
+// handles: world x 64 bytes; remote_off[k] / remote_cap[k]: offset of my data and ghost count in neighbour k's staging.
+int32_t jb_dist_p2p_open(jb_dist* D, const char* handles, const int64_t* remote_off, const int64_t* remote_cap) {
+    if (!D || !handles || !D->sym || (D->nneigh > 0 && (!remote_off || !remote_cap))) return JB_ERR_ARG;
+    jb_ctx* ctx = D->comm->ctx;
+    const int W = D->comm->world;
+    D->peer_sym.assign(W, nullptr);
+    for (int q = 0; q < W; q++) {
+        if (q == D->comm->rank) { D->peer_sym[q] = D->sym; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)q * 64, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) JB_FAIL(ctx, JB_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        D->peer_sym[q] = (double*)p;
+    }
+    std::vector<int32_t> hn(D->neigh.begin(), D->neigh.end());
+    std::vector<i64> ro(remote_off, remote_off + D->nneigh), rc(remote_cap, remote_cap + D->nneigh);
+    std::vector<unsigned int> z(1, 0);
+    std::vector<int32_t> ze(1, 0);
+    cudaStream_t s = ctx->stream;
+    bool ok = D->d_peer_sym.upload(D->peer_sym, s) == cudaSuccess && D->d_neigh.upload(hn, s) == cudaSuccess &&
+              D->d_send_ptr.upload(D->send_ptr, s) == cudaSuccess && D->d_recv_ptr.upload(D->recv_ptr, s) == cudaSuccess &&
+              D->d_remote_off.upload(ro, s) == cudaSuccess && D->d_remote_cap.upload(rc, s) == cudaSuccess && D->d_ticket.upload(z, s) == cudaSuccess &&
+              D->d_err.upload(ze, s) == cudaSuccess;
+    if (!ok) JB_FAIL(ctx, JB_ERR_ALLOC, "jb_dist_p2p_open: allocation failed");
+    D->p2p = true;
+    return JB_OK;
+}
+// 0 ok; 1 an all-reduce timed out; 2 a halo exchange timed out (a peer is gone) — the caller must abort the run
+int32_t jb_dist_p2p_status(jb_dist* D) {
+    if (!D || !D->p2p) return 0;
+    int32_t e = 0;
+    cudaMemcpyAsync(&e, D->d_err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, D->comm->ctx->stream);
+    cudaStreamSynchronize(D->comm->ctx->stream);
+    return e;
+}
 
 int32_t jb_dist_halo_exchange(jb_dist* D, double* d_vec, int32_t bs) {
     if (!D || !d_vec) return JB_ERR_ARG;

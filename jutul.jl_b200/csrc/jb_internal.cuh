@@ -191,6 +191,8 @@ struct jb_dist;
 int jb_dist_halo_launch(jb_dist* D, double* d_vec, int bs);                 // enqueue on the context's stream
 int jb_dist_allreduce_launch(jb_dist* D, double* d_buf, int n, int op_max);  // in place, enqueue only
 i64 jb_dist_n_owned(jb_dist* D);
+bool jb_dist_is_p2p(jb_dist* D);
+int jb_dist_allreduce_fin_launch(jb_dist* D, double* d_buf, int n, int op_max, int fin_which, double* sc, double* hist, int hist_cap);
 
 struct jb_krylov {
     jb_csr* csr;

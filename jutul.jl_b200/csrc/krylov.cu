@@ -199,6 +199,8 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
     // all-reduce of the two raw sums + scalar recurrence (distributed only)
     auto reduce_fin = [&](int which) -> int {
         if (!D) return JB_OK;
+        if (jb_dist_is_p2p(D))   // all-reduce over peer memory fused with the recurrence: one kernel
+            return jb_dist_allreduce_fin_launch(D, sc + KS_SUM0, 2, 0, which, sc, K->d_hist.p, K->hist_cap);
         int r2 = jb_dist_allreduce_launch(D, sc + KS_SUM0, 2, 0);
         if (r2 != JB_OK) return r2;
         krylov_finalize_kernel<<<1, 32, 0, st>>>(which, sc, K->d_hist.p, K->hist_cap);

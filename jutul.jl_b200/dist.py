@@ -152,7 +152,7 @@ class Communicator:
 
 
 class HaloPlan:
-    def __init__(self, comm, plan):
+    def __init__(self, comm, plan, td=None):
         ctx = comm.ctx
         self.ctx, self.comm, self.plan = ctx, comm, plan
         neigh = np.ascontiguousarray(plan["neigh"], dtype=np.int32)
@@ -164,6 +164,42 @@ class HaloPlan:
                                      sp.ctypes.data_as(_lib.PI64), si.ctypes.data_as(_lib.PI64), rp.ctypes.data_as(_lib.PI64), C.byref(h)),
               ctx.h, "jb_dist_create")
         self.h = h
+        self.p2p = False
+        if td is not None and os.environ.get("JB_P2P", "1") != "0":
+            self._setup_peer_memory(td)
+
+    def _setup_peer_memory(self, td):
+        """All-gather the IPC handles of the symmetric buffers and every rank's staging offsets (setup only)."""
+        import torch
+        ctx, comm, plan = self.ctx, self.comm, self.plan
+        W = comm.world
+        buf = C.create_string_buffer(64)
+        check(ctx.lib.jb_dist_p2p_export(self.h, buf), ctx.h, "jb_dist_p2p_export")
+        dev = torch.device("cuda", ctx.device) if td.get_backend() == "nccl" else torch.device("cpu")
+        mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone().to(dev)
+        allh = [torch.zeros_like(mine) for _ in range(W)]
+        td.all_gather(allh, mine)
+        handles = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+        off = np.full(W + 1, -1, dtype=np.int64)               # off[src] = where src's data starts in my staging; off[W] = my ghost count
+        for k, q in enumerate(plan["neigh"]):
+            off[int(q)] = plan["recv_ptr"][k]
+        off[W] = max(plan["n_ghost"], 1)
+        t_off = torch.from_numpy(off).to(dev)
+        allo = [torch.zeros_like(t_off) for _ in range(W)]
+        td.all_gather(allo, t_off)
+        tab = np.stack([t.cpu().numpy() for t in allo])        # tab[q][src]
+        ro = np.array([tab[int(q)][comm.rank] for q in plan["neigh"]], dtype=np.int64)
+        rc = np.array([tab[int(q)][W] for q in plan["neigh"]], dtype=np.int64)
+        assert np.all(ro >= 0), "halo plans of neighbouring ranks are inconsistent"
+        check(ctx.lib.jb_dist_p2p_open(self.h, handles, ro.ctypes.data_as(_lib.PI64), rc.ctypes.data_as(_lib.PI64)), ctx.h, "jb_dist_p2p_open")
+        ctx.synchronize()
+        td.barrier()
+        self.p2p = True
+
+    def check(self):
+        st = self.ctx.lib.jb_dist_p2p_status(self.h)
+        if st != 0:
+            raise _lib.JutulB200Error(f"peer-memory collective timed out (code {st}): a rank is gone or the ranks diverged")
 
     def exchange(self, vec, bs):
         check(self.ctx.lib.jb_dist_halo_exchange(self.h, vec.ptr, bs), self.ctx.h, "jb_dist_halo_exchange")
@@ -179,7 +215,7 @@ class DistTwoPhaseSimulator:
     """Per-rank simulator of the distributed two-phase problem (PArraySimulator analogue)."""
 
     def __init__(self, ctx, comm, w, part, rtol=1e-3, atol=None, max_linear_iterations=100, tolerance=1e-3, max_nonlinear_iterations=15,
-                 dp_abs_max=None, ds_abs_max=0.2, local_order="default"):
+                 dp_abs_max=None, ds_abs_max=0.2, local_order="default", td=None):
         J = _pkg()
         self.ctx, self.comm = ctx, comm
         self.plan = plan = decompose(w["N"], w["nc"], part, comm.rank, local_order)
@@ -190,7 +226,7 @@ class DistTwoPhaseSimulator:
         self.storage = J.ConservationLawTPFAStorage(self.disc, self.jac)
         self.law = J.TwoPhaseConservationLaw(self.storage, w["Tf"][faces], w["gdz"][faces], w["pv"][cells], w["params"])
         check(ctx.lib.jb_twophase_set_owned(self.law.h, self.n_owned), ctx.h, "jb_twophase_set_owned")
-        self.halo = HaloPlan(comm, plan)
+        self.halo = HaloPlan(comm, plan, td)
         lp = np.ones(self.n_local, dtype=np.int64); lp[self.n_owned:] = 2      # ghosts decoupled: local ILU(0) of the owned block
         self.prec = J.ILUZeroPreconditioner(self.jac, lp if plan["n_ghost"] > 0 else None)
         self.krylov = J.GenericKrylov(self.jac, "bicgstab", self.prec, relative_tolerance=rtol, absolute_tolerance=atol,
@@ -240,6 +276,8 @@ class DistTwoPhaseSimulator:
         J.update_primary_variable(self.ctx, self.p, self.dx, self.n_owned, dx_stride=2, abs_max=self.dp_abs_max)
         J.unit_update_pairs(self.ctx, self.s, self.dx.offset(1), self.n_owned, dx_stride=2, abs_max=self.ds_abs_max)
         self.halo.exchange(self.p, 1); self.halo.exchange(self.s, 2)                        # parray_synchronize_primary_variables
+        if self.halo.p2p:
+            self.halo.check()
         return False, e, rep
 
     def solve_ministep(self, dt):
@@ -278,7 +316,7 @@ def run_bench(args, J):
     part = part_t.cpu().numpy()
     t_part = time.perf_counter() - t0
     sim = DistTwoPhaseSimulator(ctx, comm, w, part, rtol=args.rtol, max_linear_iterations=args.max_linear_iterations, tolerance=args.tolerance,
-                                local_order="multicolor" if args.ordering == "multicolor" else "default")
+                                local_order="multicolor" if args.ordering == "multicolor" else "default", td=td)
     dt = w["dt"]
     p_init, s_init = ctx.transfer(sim.p.get()), ctx.transfer(sim.s.get())
 
@@ -379,7 +417,8 @@ def run_bench(args, J):
                        "newton_tolerance": args.tolerance, "parallelism": f"domain decomposition, {world} ranks, NCCL halo + all-reduce",
                        "l2_policy": "inputs larger than L2 per rank" if (nb_loc * 32) > 126e6 else "local Jacobian fits L2: no flush (strong scaling)",
                        "owned_ghost_per_rank": [[int(a[0]), int(a[1])] for a in all_sizes], "partition_seconds": t_part,
-                       "cell_ordering": args.ordering, "ilu": sim.prec.info()},
+                       "cell_ordering": args.ordering, "ilu": sim.prec.info(),
+                       "collectives": "peer memory over NVLink (fused all-reduce + recurrence kernel, direct halo stores)" if sim.halo.p2p else "NCCL"},
             "newton_iterations_per_step": n_newton / max(args.steps, 1), "converged": all(r[0] for r in results),
             "linear_iterations_per_newton": float(np.mean(lin_its)) if lin_its else None, "linear_iterations": results[0][2],
             "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "kernels": kernels,
