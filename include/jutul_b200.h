@@ -226,6 +226,9 @@ int32_t jb_maxabs_rows(jb_ctx* ctx, const double* d_r, int32_t bs, int64_t n, do
 int32_t jb_partition_metis(int64_t nc, int64_t nf, const int64_t* N, const double* weights, int64_t k,
                            int64_t* part);
 int32_t jb_partition_linear(int64_t m, int64_t n, int64_t* part);
+/* process_partition (src/partitioning.jl:128-160): split disconnected blocks into connected components */
+int32_t jb_process_partition(int64_t nc, int64_t nf, const int64_t* N, const int64_t* partition, const double* weights,
+                             int64_t* new_partition);
 
 /* ---- cell renumbering (setup-time, host). The reference lets the local system be renumbered before
  *      ILU(0) (SymRCM option, ext/JutulPartitionedArraysExt/utils.jl:58-89); jb_order_multicolor returns

@@ -436,6 +436,16 @@ class NFVMDiscretization(_Handle):
         return q
 
 
+def process_partition(N, nc, part, weights=None):
+    """process_partition(neighbors, partition; weights) (src/partitioning.jl:128-160)."""
+    lib = _lib.load()
+    N = np.ascontiguousarray(N, dtype=i64); part = np.ascontiguousarray(part, dtype=i64)
+    out = np.zeros(int(nc), dtype=i64)
+    w = None if weights is None else np.ascontiguousarray(weights, dtype=f64)
+    check(lib.jb_process_partition(int(nc), N.shape[0], _pi(N), _pi(part), _pd(w), _pi(out)), None, "jb_process_partition")
+    return out
+
+
 def multicolor_ordering(N, nc):
     """B200-friendly cell renumbering (setup, host): Cuthill-McKee locality + greedy colouring, numbered colour
     by colour. Returns (perm, ncolors) with perm[c] = new 1-based label of (1-based) cell c+1."""

@@ -84,6 +84,7 @@ PROTOTYPES = {
     "jb_maxabs_rows": (I32, [P, P, I32, I64, PF64]),
     "jb_partition_metis": (I32, [I64, I64, PI64, PF64, I64, PI64]),
     "jb_partition_linear": (I32, [I64, I64, PI64]),
+    "jb_process_partition": (I32, [I64, I64, PI64, PI64, PF64, PI64]),
     "jb_order_multicolor": (I32, [I64, I64, PI64, PI64, PI64]),
     "jb_perm_create": (I32, [P, PI64, I64, PP]),
     "jb_perm_destroy": (I32, [P]),

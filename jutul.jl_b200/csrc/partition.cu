@@ -145,3 +145,51 @@ extern "C" int32_t jb_order_multicolor(int64_t nc, int64_t nf, const int64_t* N,
     if (ncolors) *ncolors = ncol;
     return JB_OK;
 }
+
+// process_partition(neighbors, partition; weights) (src/partitioning.jl:128-160): every block of the partition that is
+// not connected is split into its connected components; the first component keeps the label, the others receive
+// max_p + 1, max_p + 2, ... in the order the blocks and components are met (components ordered by their smallest cell).
+// Faces with zero weight do not connect cells. Setup-time host logic.
+extern "C" int32_t jb_process_partition(int64_t nc, int64_t nf, const int64_t* N, const int64_t* partition, const double* weights,
+                                        int64_t* new_partition) {
+    if (!N || !partition || !new_partition || nc < 1 || nf < 0) return JB_ERR_ARG;
+    i64 max_p = 0;
+    for (i64 c = 0; c < nc; c++) { if (partition[c] < 1) return JB_ERR_ARG; new_partition[c] = partition[c]; max_p = std::max(max_p, partition[c]); }
+    // block-internal adjacency (CSR)
+    std::vector<i64> xadj(nc + 1, 0);
+    auto internal = [&](i64 f, i64& l, i64& r) {
+        l = N[2 * f] - 1; r = N[2 * f + 1] - 1;
+        if (l < 0 || l >= nc || r < 0 || r >= nc) return false;
+        if (weights && weights[f] == 0.0) return false;
+        return partition[l] == partition[r] && l != r;
+    };
+    for (i64 f = 0; f < nf; f++) { i64 l, r; if (internal(f, l, r)) { xadj[l + 1]++; xadj[r + 1]++; } }
+    for (i64 c = 0; c < nc; c++) xadj[c + 1] += xadj[c];
+    std::vector<i64> adj(xadj[nc]), cur(xadj.begin(), xadj.end() - 1);
+    for (i64 f = 0; f < nf; f++) { i64 l, r; if (internal(f, l, r)) { adj[cur[l]++] = r; adj[cur[r]++] = l; } }
+    // cells grouped by block, ascending cell index inside a block
+    std::vector<i64> bptr(max_p + 2, 0), bcells(nc);
+    for (i64 c = 0; c < nc; c++) bptr[partition[c] + 1]++;
+    for (i64 b = 1; b <= max_p + 1; b++) bptr[b] += bptr[b - 1];
+    { std::vector<i64> bc(bptr.begin(), bptr.end() - 1); for (i64 c = 0; c < nc; c++) bcells[bc[partition[c]]++] = c; }
+    std::vector<char> seen(nc, 0);
+    std::vector<i64> stack;
+    i64 next_label = max_p;
+    for (i64 b = 1; b <= max_p; b++) {
+        bool first = true;
+        for (i64 k = bptr[b]; k < bptr[b + 1]; k++) {
+            const i64 c = bcells[k];
+            if (seen[c]) continue;
+            i64 label = b;
+            if (!first) label = ++next_label;
+            first = false;
+            stack.assign(1, c); seen[c] = 1;
+            while (!stack.empty()) {
+                const i64 u = stack.back(); stack.pop_back();
+                new_partition[u] = label;
+                for (i64 e = xadj[u]; e < xadj[u + 1]; e++) if (!seen[adj[e]]) { seen[adj[e]] = 1; stack.push_back(adj[e]); }
+            }
+        }
+    }
+    return JB_OK;
+}

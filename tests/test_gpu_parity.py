@@ -544,3 +544,93 @@ def test_nfvm_evaluate_flux_matches_oracle(J, O, ctx, scheme):
     q1 = ctx.zeros(1)
     d1.evaluate_flux(ctx.transfer(np.array([3.0, 1.0])), q1)
     assert q1.get()[0] == (4.0 if scheme == "linear" else 0.5 * 4.0 - 0.5 * (-4.0))
+
+
+# ---------------------------------------------------------------- genuinely irregular graphs (ragged rows, odd cycles)
+def _random_graph_workload(J, nc=900, extra=2200, seed=5):
+    """Hex grid plus random extra faces between arbitrary cells (no duplicates, no self-loops): cell degrees 3..15,
+    triangles in the graph (ILU update lists with fill candidates), not bipartite (> 2 colours)."""
+    w = J.workloads.unstructured_hex(10, 10, 9, seed=seed)
+    assert w["nc"] == nc
+    rng = np.random.default_rng(seed)
+    have = set(map(tuple, np.sort(w["N"], axis=1).tolist()))
+    new = []
+    while len(new) < extra:
+        a, b = rng.integers(1, nc + 1, 2)
+        k = (min(a, b), max(a, b))
+        if a == b or k in have:
+            continue
+        have.add(k); new.append((a, b))
+    N = np.concatenate([w["N"], np.array(new, dtype=np.int64)])
+    order = rng.permutation(N.shape[0])
+    w2 = dict(w)
+    w2["N"] = np.ascontiguousarray(N[order]); w2["nf"] = N.shape[0]
+    Tf = np.concatenate([w["Tf"], rng.uniform(0.1, 1.0, extra) * np.median(w["Tf"])])[order]
+    gdz = np.concatenate([w["gdz"], -J.workloads.GRAVITY * (w["z"][np.array(new)[:, 1] - 1] - w["z"][np.array(new)[:, 0] - 1])])[order]
+    w2["Tf"], w2["gdz"] = Tf, gdz
+    return w2
+
+
+@pytest.mark.parametrize("ordering", [None, "multicolor"])
+def test_irregular_graph_full_chain(J, O, ctx, ordering):
+    w = _random_graph_workload(J)
+    n = w["nc"]
+    sim = J.TwoPhaseSimulator(ctx, w["N"], n, w["Tf"], w["gdz"], w["pv"], w["params"], rtol=1e-9, max_linear_iterations=400, ordering=ordering)
+    sim.set_forces(w["src_cells"], w["src_vals"])
+    sim.set_state(w["p0"], w["sw0"])
+    if ordering is None:
+        s = oracle_system(O, w)
+        hf = sim.disc.half_face_map()
+        for k in ("faces", "face_pos", "cells", "face_sign"):
+            assert np.array_equal(hf[k], s["hf"][k])
+        rp, ci = sim.jac.pattern()
+        assert np.array_equal(rp, s["rowptr"]) and np.array_equal(ci, s["colidx"])
+        assert np.diff(rp).max() >= 10 and np.diff(rp).min() <= 5            # ragged rows
+        d, h = sim.storage.jacobian_positions()
+        assert np.array_equal(d, s["diag_pos"]) and np.array_equal(h, s["hf_pos"])
+        conv, err, rep = sim.perform_step(w["dt"])
+        M0 = O.mass_2ph(w["pv"], w["params"], w["p0"], w["sw0"])
+        nz, r = O.assemble_2ph(s["hf"], s["diag_pos"], s["hf_pos"], w["Tf"], w["gdz"], w["pv"], w["params"], w["p0"], w["sw0"], M0, w["dt"],
+                               s["colidx"].shape[0], w["src_cells"], w["src_vals"])
+        assert np.abs(sim.r.get() - r).max() <= 1e-11 * np.abs(r).max()
+        assert np.abs(sim.jac.nonzeros() - nz).max() <= 1e-11 * np.abs(nz).max()
+        ilu = O.ILU0(n, 2, s["rowptr"], s["colidx"]); ilu.factor(sim.jac.nonzeros())
+        fg, fo = sim.prec.factors(), ilu.get()
+        for k in ("Lptr", "Lcol", "Uptr", "Ucol"):
+            assert np.array_equal(fg[k], fo[k])
+        for k in ("L", "U", "D"):     # triangles in the graph => the update lists carry real fill-pattern work
+            assert np.abs(fg[k] - fo[k]).max() <= 1e-10 * np.abs(fo[k]).max()
+        x, st, its, hist = O.bicgstab(n, 2, s["rowptr"], s["colidx"], sim.jac.nonzeros(), sim.r.get(), ilu, rtol=1e-9, itmax=400)
+        assert abs(rep["linear_iterations"] - its) <= max(2, its // 10)
+        assert np.allclose(rep["linear_residuals"][:5], hist[:5], rtol=1e-6)
+    else:
+        assert sim.ncolors > 2
+        info = sim.prec.info()
+        assert info["forward_levels"] <= sim.ncolors
+        ok, reps = sim.solve_ministep(w["dt"])
+        ref = J.TwoPhaseSimulator(ctx, w["N"], n, w["Tf"], w["gdz"], w["pv"], w["params"], rtol=1e-9, max_linear_iterations=400)
+        ref.set_forces(w["src_cells"], w["src_vals"])
+        ref.set_state(w["p0"], w["sw0"])
+        ok2, reps2 = ref.solve_ministep(w["dt"])
+        assert ok and ok2 and len(reps) == len(reps2)
+        (p1, s1), (p2, s2) = sim.get_state(), ref.get_state()
+        assert np.abs(p1 - p2).max() <= 1e-7 * np.abs(p2).max() and np.abs(s1 - s2).max() <= 1e-7
+
+
+def test_error_codes_and_bad_arguments(J, ctx):
+    with pytest.raises(J.JutulB200Error):
+        J.TwoPointPotentialFlowHardCoded(ctx, np.array([[1, 1]]), 2)            # self-loop
+    with pytest.raises(J.JutulB200Error):
+        J.TwoPointPotentialFlowHardCoded(ctx, np.array([[1, 5]]), 2)            # out of range
+    with pytest.raises(J.JutulB200Error):
+        J.build_sparse_matrix(ctx, [1, 2], [1, 3], 2, 1)                        # column out of range
+    with pytest.raises(J.JutulB200Error):
+        J.CellPermutation(ctx, [1, 1, 3])                                       # not a permutation
+    # missing diagonal in the pattern: "Diagonal must be present in sparsity pattern." (src/StaticCSR/ilu0.jl:72)
+    A = J.build_sparse_matrix(ctx, [1, 2], [2, 1], 2, 1)
+    with pytest.raises(J.JutulB200Error):
+        J.ILUZeroPreconditioner(A)
+    # single cell, no faces
+    disc = J.TwoPointPotentialFlowHardCoded(ctx, np.zeros((0, 2), dtype=np.int64), 1)
+    jac = J.tpfa_jacobian(disc, 2)
+    assert jac.nnz == 1 and jac.pattern()[1].tolist() == [1]
