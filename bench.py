@@ -172,8 +172,10 @@ def run_b200(args):
 
     # ---- e2e: the reference-facing perform_step call with HOST (pinned-size) buffers: H2D of p, s, M0 and D2H of p, s
     #      inside every Newton iteration
-    p0_h, s0_h, M0_h = sim.download(p_init), sim.download(s_init, 2), sim.download(sim.M0, 2)   # caller's numbering
-    p_h, s_h = p0_h.copy(), s0_h.copy()
+    p0_h, s0_h, M0_src = sim.download(p_init), sim.download(s_init, 2), sim.download(sim.M0, 2)   # caller's numbering
+    # the buffers handed to the API live in pinned host memory
+    p_h, s_h, M0_h = ctx.pinned_empty(nc), ctx.pinned_empty(2 * nc), ctx.pinned_empty(2 * nc)
+    p_h[:] = p0_h; s_h[:] = s0_h; M0_h[:] = M0_src
     h2d = d2h = 0
 
     def step_host(solve=True):
@@ -198,7 +200,7 @@ def run_b200(args):
     nn2 = sum(r[1] for r in res2)
     e2e = {"value": nn2 / wall2, "unit": UNIT, "h2d_bytes_per_step": int(h2d / n_e2e_steps), "d2h_bytes_per_step": int(d2h / n_e2e_steps),
            "ms_per_step": 1e3 * wall2 / n_e2e_steps, "newton_iterations_per_step": nn2 / n_e2e_steps,
-           "api": "jb_twophase_perform_step_host (host p, s, M0 in; p, s, errors out) once per Newton iteration"}
+           "api": "jb_twophase_perform_step_host (pinned host p, s, M0 in; p, s, errors out) once per Newton iteration"}
 
     # ---- cpu_baseline: bounded sample of the same workload on the host cores (oracle = CPU restatement)
     cpu = None

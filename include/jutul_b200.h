@@ -237,6 +237,10 @@ int32_t jb_process_partition(int64_t nc, int64_t nf, const int64_t* N, const int
  *      jb_perm_*: device-side application to per-cell vectors of block size bs; to_caller = 0 maps
  *      caller -> device numbering (dst[perm[i]] = src[i]), 1 maps back (dst[i] = src[perm[i]]). */
 int32_t jb_order_multicolor(int64_t nc, int64_t nf, const int64_t* N, int64_t* perm, int64_t* ncolors);
+/* variant for a rank of a distributed run: cells flagged in last[nc] (sub-domain boundary cells) are numbered at the end
+ * of their colour, so interior rows are contiguous and their SpMV overlaps the halo exchange */
+int32_t jb_order_multicolor_boundary_last(int64_t nc, int64_t nf, const int64_t* N, const int64_t* last, int64_t* perm,
+                                          int64_t* ncolors);
 int32_t jb_perm_create(jb_ctx* ctx, const int64_t* perm, int64_t n, jb_perm** out);
 int32_t jb_perm_destroy(jb_perm* p);
 int32_t jb_perm_apply(jb_perm* p, const double* d_src, double* d_dst, int32_t bs, int32_t to_caller);

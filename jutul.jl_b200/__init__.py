@@ -77,8 +77,23 @@ class B200Context:
     def empty(self, n):
         return DeviceArray(self, int(n))
 
+    def pinned_empty(self, n):
+        """Float64 numpy array in page-locked host memory (jb_pinned_alloc): host buffers of the end-to-end entry points
+        should live here so that H2D / D2H copies run at PCIe speed."""
+        n = int(n)
+        ptr = C.c_void_p()
+        check(self.lib.jb_pinned_alloc(max(n, 1) * 8, C.byref(ptr)), self.h, "jb_pinned_alloc")
+        buf = (C.c_double * max(n, 1)).from_address(ptr.value)
+        arr = np.frombuffer(buf, dtype=f64, count=n)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append((ptr, buf))          # freed with the context
+        return arr
+
     def close(self):
         if getattr(self, "h", None):
+            for ptr, _ in getattr(self, "_pinned", []):
+                self.lib.jb_pinned_free(ptr)
+            self._pinned = []
             self.lib.jb_ctx_destroy(self.h)
             self.h = None
 
@@ -114,6 +129,13 @@ class DeviceArray:
 
     def get(self):
         out = np.empty(self.n, dtype=f64)
+        if self.n:
+            check(self.ctx.lib.jb_d2h(self.ctx.h, out.ctypes.data_as(C.c_void_p), self.ptr, self.n * 8), self.ctx.h, "jb_d2h")
+        return out
+
+    def get_into(self, out):
+        """Download into a caller-provided (ideally pinned) contiguous float64 array."""
+        assert out.dtype == f64 and out.flags["C_CONTIGUOUS"] and out.size == self.n
         if self.n:
             check(self.ctx.lib.jb_d2h(self.ctx.h, out.ctypes.data_as(C.c_void_p), self.ptr, self.n * 8), self.ctx.h, "jb_d2h")
         return out
@@ -446,14 +468,20 @@ def process_partition(N, nc, part, weights=None):
     return out
 
 
-def multicolor_ordering(N, nc):
+def multicolor_ordering(N, nc, last=None):
     """B200-friendly cell renumbering (setup, host): Cuthill-McKee locality + greedy colouring, numbered colour
-    by colour. Returns (perm, ncolors) with perm[c] = new 1-based label of (1-based) cell c+1."""
+    by colour. Returns (perm, ncolors) with perm[c] = new 1-based label of (1-based) cell c+1. `last` (nc flags): cells
+    numbered at the end of their colour (sub-domain boundary cells of a distributed rank)."""
     lib = _lib.load()
     N = np.ascontiguousarray(N, dtype=i64)
     perm = np.zeros(int(nc), dtype=i64)
     ncol = C.c_int64(0)
-    check(lib.jb_order_multicolor(int(nc), N.shape[0], _pi(N), _pi(perm), C.byref(ncol)), None, "jb_order_multicolor")
+    if last is None:
+        check(lib.jb_order_multicolor(int(nc), N.shape[0], _pi(N), _pi(perm), C.byref(ncol)), None, "jb_order_multicolor")
+    else:
+        fl = np.ascontiguousarray(last, dtype=i64)
+        check(lib.jb_order_multicolor_boundary_last(int(nc), N.shape[0], _pi(N), _pi(fl), _pi(perm), C.byref(ncol)), None,
+              "jb_order_multicolor_boundary_last")
     return perm, ncol.value
 
 

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "jb_partition_linear": (I32, [I64, I64, PI64]),
     "jb_process_partition": (I32, [I64, I64, PI64, PI64, PF64, PI64]),
     "jb_order_multicolor": (I32, [I64, I64, PI64, PI64, PI64]),
+    "jb_order_multicolor_boundary_last": (I32, [I64, I64, PI64, PI64, PI64, PI64]),
     "jb_perm_create": (I32, [P, PI64, I64, PP]),
     "jb_perm_destroy": (I32, [P]),
     "jb_perm_apply": (I32, [P, P, P, I32, I32]),

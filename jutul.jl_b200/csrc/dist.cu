@@ -175,19 +175,24 @@ __global__ void __launch_bounds__(256) p2p_halo_pull_kernel(double* mine, int nn
     }
 }
 
-static int p2p_halo_launch(jb_dist* D, double* d_vec, int bs) {
+// which: 1 = push only (starts a new epoch), 2 = pull only (completes the current epoch), 3 = both
+static int p2p_halo_launch(jb_dist* D, double* d_vec, int bs, int which = 3) {
     jb_ctx* ctx = D->comm->ctx;
     cudaStream_t st = ctx->stream;
-    const unsigned long long epoch = ++D->halo_epoch;
+    const unsigned long long epoch = (which & 1) ? ++D->halo_epoch : D->halo_epoch;
     const i64 n_ghost = D->n_local - D->n_owned;
     const int gp = (int)std::max<i64>(1, std::min<i64>((D->nsend + 255) / 256, (i64)ctx->sm_count * 2));
     const int gq = (int)std::max<i64>(1, std::min<i64>((n_ghost + 255) / 256, (i64)ctx->sm_count * 2));
-#define JB_P2P_HALO(BS)                                                                                                                      \
-    p2p_halo_push_kernel<BS><<<gp, 256, 0, st>>>(D->d_peer_sym.p, D->comm->rank, D->nneigh, D->d_neigh.p, D->d_send_ptr.p, D->d_remote_off.p,    \
-                                                 D->d_send_idx.p, d_vec, D->nsend, epoch, D->d_remote_cap.p, D->d_ticket.p);                  \
-    JB_CHECK_LAUNCH(ctx);                                                                                                                    \
-    p2p_halo_pull_kernel<BS><<<gq, 256, 0, st>>>(D->sym, D->nneigh, D->d_neigh.p, D->n_owned, n_ghost, D->stage_cap, d_vec, epoch, D->d_err.p); \
-    JB_CHECK_LAUNCH(ctx);
+#define JB_P2P_HALO(BS)                                                                                                                          \
+    if (which & 1) {                                                                                                                             \
+        p2p_halo_push_kernel<BS><<<gp, 256, 0, st>>>(D->d_peer_sym.p, D->comm->rank, D->nneigh, D->d_neigh.p, D->d_send_ptr.p, D->d_remote_off.p,    \
+                                                     D->d_send_idx.p, d_vec, D->nsend, epoch, D->d_remote_cap.p, D->d_ticket.p);                  \
+        JB_CHECK_LAUNCH(ctx);                                                                                                                    \
+    }                                                                                                                                            \
+    if (which & 2) {                                                                                                                             \
+        p2p_halo_pull_kernel<BS><<<gq, 256, 0, st>>>(D->sym, D->nneigh, D->d_neigh.p, D->n_owned, n_ghost, D->stage_cap, d_vec, epoch, D->d_err.p); \
+        JB_CHECK_LAUNCH(ctx);                                                                                                                    \
+    }
     switch (bs) {
         case 1: JB_P2P_HALO(1) break;
         case 2: JB_P2P_HALO(2) break;
@@ -212,6 +217,18 @@ int jb_dist_allreduce_fin_launch(jb_dist* D, double* d_buf, int n, int op_max, i
 }
 bool jb_dist_is_p2p(jb_dist* D) { return D && D->p2p; }
 
+int jb_dist_halo_push_launch(jb_dist* D, double* d_vec, int bs) {
+    if (!D->p2p) return JB_ERR_UNSUPPORTED;
+    if (D->nneigh == 0) return JB_OK;
+    ProfScope _ps(D->comm->ctx, JB_PROF_OTHER);
+    return p2p_halo_launch(D, d_vec, bs, 1);
+}
+int jb_dist_halo_pull_launch(jb_dist* D, double* d_vec, int bs) {
+    if (!D->p2p) return JB_ERR_UNSUPPORTED;
+    if (D->nneigh == 0) return JB_OK;
+    ProfScope _ps(D->comm->ctx, JB_PROF_OTHER);
+    return p2p_halo_launch(D, d_vec, bs, 2);
+}
 i64 jb_dist_n_owned(jb_dist* D) { return D->n_owned; }
 
 int jb_dist_halo_launch(jb_dist* D, double* d_vec, int bs) {

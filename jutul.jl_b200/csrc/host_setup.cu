@@ -147,6 +147,31 @@ int32_t jb_csr_create_tpfa(jb_mesh* m, int32_t bs, jb_csr** out) {
     return JB_OK;
 }
 int32_t jb_csr_destroy(jb_csr* A) { delete A; return JB_OK; }
+}  // extern "C"
+
+// Classify the stream chunks of a rank-local matrix ([owned | ghost] numbering): interior = every row and every column of
+// the chunk is owned; boundary = some owned row reads a ghost column (or the chunk straddles n_owned). Chunks of ghost rows
+// only are dropped (those rows are -I and never needed by the distributed SpMV).
+int jb_csr_split_owned(jb_csr* A, i64 n_owned) {
+    if (A->h_chunks.empty()) return JB_ERR_UNSUPPORTED;
+    std::vector<int32_t> li, lb;
+    const int nch = (int)A->h_chunks.size() - 1;
+    for (int c = 0; c < nch; c++) {
+        const int32_t r0 = A->h_chunks[c], r1 = A->h_chunks[c + 1];
+        if (r0 >= n_owned) continue;
+        bool interior = r1 <= n_owned;
+        for (int32_t k = A->h_rowptr[r0]; interior && k < A->h_rowptr[r1]; k++) if (A->h_colidx[k] >= n_owned) interior = false;
+        (interior ? li : lb).push_back(c);
+    }
+    A->n_chunks_int = (int)li.size(); A->n_chunks_bnd = (int)lb.size();
+    if (li.empty()) li.push_back(0);
+    if (lb.empty()) lb.push_back(0);
+    if (A->d_chunks_int.upload(li, A->ctx->stream) != cudaSuccess || A->d_chunks_bnd.upload(lb, A->ctx->stream) != cudaSuccess) return JB_ERR_ALLOC;
+    A->has_split = true;
+    return JB_OK;
+}
+
+extern "C" {
 int64_t jb_csr_nnz(jb_csr* A) { return A ? A->nnzb : -1; }
 int64_t jb_csr_nrows(jb_csr* A) { return A ? A->n : -1; }
 int32_t jb_csr_get(jb_csr* A, int64_t* rowptr, int64_t* colidx) {

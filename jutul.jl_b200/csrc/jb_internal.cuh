@@ -120,7 +120,16 @@ struct jb_csr {
     std::vector<int32_t> h_chunks;                    // row-chunk boundaries for the stream kernels (empty: fallback)
     DBuf<int32_t> d_rowptr, d_colidx, d_diag, d_chunks;
     DBuf<double> d_val;
+    // distributed SpMV in two launches (set by jb_csr_split_owned): chunks whose rows and columns are all owned, and chunks
+    // with an owned row that reads a ghost column. split_phase: 0 = ordinary single launch, 1 = interior, 2 = boundary.
+    DBuf<int32_t> d_chunks_int, d_chunks_bnd;
+    int n_chunks_int = 0, n_chunks_bnd = 0;
+    int split_phase = 0;
+    bool has_split = false;
 };
+int jb_csr_split_owned(jb_csr* A, i64 n_owned);
+int jb_dist_halo_push_launch(jb_dist* D, double* d_vec, int bs);   // peer-memory path only
+int jb_dist_halo_pull_launch(jb_dist* D, double* d_vec, int bs);
 
 struct jb_tpfa {
     jb_mesh* mesh;
@@ -205,6 +214,7 @@ struct jb_krylov {
     double* h_flags = nullptr;  // pinned
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int hist_cap = 0;
+    bool overlap = false;      // interior SpMV overlapped with the halo exchange (JB_OVERLAP=1)
     jb_dist* dist = nullptr;   // distributed solve: dots over owned rows + all-reduce, halo exchange before each SpMV
     // gmres: Arnoldi basis (grows on demand), packed Hessenberg/R columns, Givens c/s, z, y
     std::vector<double*> gm_V;

@@ -71,3 +71,36 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NR], double* partials, u
         if (threadIdx.x == 0) fin(acc);
     }
 }
+
+// Two-launch form: kernel A (finalize = false) only deposits its per-CTA partials in slots [0, gridA); kernel B, later on
+// the same stream, deposits at slot_offset = gridA and its last CTA adds all total_slots partials in slot order.
+template <int NR, class Op, class Fin>
+__device__ __forceinline__ void grid_reduce_ex(double (&v)[NR], double* partials, unsigned int* counter, int slot_offset, int total_slots,
+                                               bool finalize, Fin fin) {
+    __shared__ double smem[NR * 32];
+    __shared__ bool is_last;
+    block_reduce<NR, Op>(v, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) partials[(size_t)(slot_offset + blockIdx.x) * NR + r] = v[r];
+    }
+    if (!finalize) return;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int ticket = atomicInc(counter, gridDim.x - 1);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double acc[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) acc[r] = Op::ident();
+        for (unsigned int b = threadIdx.x; b < (unsigned int)total_slots; b += blockDim.x) {
+#pragma unroll
+            for (int r = 0; r < NR; r++) acc[r] = Op::comb(acc[r], __ldcg(&partials[(size_t)b * NR + r]));
+        }
+        block_reduce<NR, Op>(acc, smem);
+        if (threadIdx.x == 0) fin(acc);
+    }
+}

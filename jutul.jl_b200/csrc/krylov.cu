@@ -19,6 +19,7 @@
 // on the same stream and a one-thread kernel applies the scalar recurrence, so every rank
 // holds bitwise-identical scalars and takes identical decisions; the operand of each SpMV
 // gets its ghost section from a halo exchange (consistent!(X), linalg.jl:46).
+#include <cstdlib>
 #include "jb_internal.cuh"
 #include "jb_krylov_scalars.cuh"
 #include "jb_reduce.cuh"
@@ -161,6 +162,11 @@ int32_t jb_krylov_set_dist(jb_krylov* K, jb_dist* D) {
     if (!K) return JB_ERR_ARG;
     if (D && jb_dist_n_owned(D) > K->csr->n) return JB_ERR_ARG;
     K->dist = D;
+    // interior/boundary SpMV overlap with the halo exchange: opt-in (JB_OVERLAP=1); it pays only when the per-rank problem is
+    // large enough that the second (boundary) launch costs less than the exposed halo wait
+    const char* ov = getenv("JB_OVERLAP");
+    K->overlap = ov && ov[0] == '1';
+    if (D && K->overlap && !K->csr->has_split) jb_csr_split_owned(K->csr, jb_dist_n_owned(D));
     return JB_OK;
 }
 
@@ -234,8 +240,18 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
         }
         double* yv = K->p.p;
         if (right) { rc = jb_launch_ilu_apply_sc(F, K->p.p, K->y.p, sc); if (rc != JB_OK) return rc; yv = K->y.p; }
-        if (D && (rc = jb_dist_halo_launch(D, yv, bs)) != JB_OK) return rc;           // consistent!(y)
-        if (!left) {
+        const bool overlap = D && !left && jb_dist_is_p2p(D) && A->has_split && K->overlap;
+        if (overlap) {
+            // consistent!(y) overlapped with the interior rows: push -> interior SpMV -> pull -> boundary SpMV (+ reduction)
+            if ((rc = jb_dist_halo_push_launch(D, yv, bs)) != JB_OK) return rc;
+            A->split_phase = 1; rc = jb_launch_spmv_dots(A, yv, K->v.p, JB_DOT_CV, d_b, sc, n_own); A->split_phase = 0;
+            if (rc != JB_OK) return rc;
+            if ((rc = jb_dist_halo_pull_launch(D, yv, bs)) != JB_OK) return rc;
+            A->split_phase = 2; rc = jb_launch_spmv_dots(A, yv, K->v.p, JB_DOT_CV, d_b, sc, n_own); A->split_phase = 0;
+            if (rc != JB_OK) return rc;
+        } else if (D && (rc = jb_dist_halo_launch(D, yv, bs)) != JB_OK) return rc;    // consistent!(y)
+        if (overlap) {
+        } else if (!left) {
             rc = jb_launch_spmv_dots(A, yv, K->v.p, JB_DOT_CV, d_b, sc, n_own);       // v = A y, alpha = rho/<c,v>
             if (rc != JB_OK) return rc;
         } else {
@@ -253,8 +269,16 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
         JB_VEC_END
         double* zv = K->s.p;
         if (right) { rc = jb_launch_ilu_apply_sc(F, K->s.p, K->z.p, sc); if (rc != JB_OK) return rc; zv = K->z.p; }
-        if (D && (rc = jb_dist_halo_launch(D, zv, bs)) != JB_OK) return rc;           // consistent!(z)
-        if (!left) {
+        if (overlap) {
+            if ((rc = jb_dist_halo_push_launch(D, zv, bs)) != JB_OK) return rc;
+            A->split_phase = 1; rc = jb_launch_spmv_dots(A, zv, K->t.p, JB_DOT_TS_TT, K->s.p, sc, n_own); A->split_phase = 0;
+            if (rc != JB_OK) return rc;
+            if ((rc = jb_dist_halo_pull_launch(D, zv, bs)) != JB_OK) return rc;
+            A->split_phase = 2; rc = jb_launch_spmv_dots(A, zv, K->t.p, JB_DOT_TS_TT, K->s.p, sc, n_own); A->split_phase = 0;
+            if (rc != JB_OK) return rc;
+        } else if (D && (rc = jb_dist_halo_launch(D, zv, bs)) != JB_OK) return rc;    // consistent!(z)
+        if (overlap) {
+        } else if (!left) {
             rc = jb_launch_spmv_dots(A, zv, K->t.p, JB_DOT_TS_TT, K->s.p, sc, n_own);  // t = A z, omega = <t,s>/<t,t>
             if (rc != JB_OK) return rc;
         } else {

@@ -83,7 +83,7 @@ int32_t jb_partition_metis(int64_t nc, int64_t nf, const int64_t* N, const doubl
 // Rows of one colour are mutually independent, so the triangular sweeps have as many levels as colours (2 on
 // bipartite hex-like grids) and every level is one contiguous, locality-ordered range of rows.
 // perm[c_old] (1-based) = new label (1-based).
-extern "C" int32_t jb_order_multicolor(int64_t nc, int64_t nf, const int64_t* N, int64_t* perm, int64_t* ncolors) {
+static int32_t order_multicolor_impl(int64_t nc, int64_t nf, const int64_t* N, const int64_t* last, int64_t* perm, int64_t* ncolors) {
     if (!N || !perm || nc < 1 || nf < 0) return JB_ERR_ARG;
     std::vector<i64> xadj(nc + 1, 0);
     for (i64 f = 0; f < nf; f++) {
@@ -138,12 +138,24 @@ extern "C" int32_t jb_order_multicolor(int64_t nc, int64_t nf, const int64_t* N,
         color[v] = c;
         if (c == ncol) ncol++;
     }
-    std::vector<i64> start(ncol + 1, 0);
-    for (i64 v = 0; v < nc; v++) start[color[v] + 1]++;
-    for (int32_t c = 0; c < ncol; c++) start[c + 1] += start[c];
-    for (int32_t v : order) perm[v] = ++start[color[v]];     // BFS rank inside the colour, 1-based
+    // numbering: colour by colour; inside a colour the cells flagged `last` (sub-domain boundary cells of a distributed
+    // run) come after the others, each group in breadth-first rank
+    std::vector<i64> start(2 * (size_t)ncol + 1, 0);
+    auto bucket = [&](int32_t v) { return 2 * (size_t)color[v] + ((last && last[v]) ? 1 : 0); };
+    for (i64 v = 0; v < nc; v++) start[bucket((int32_t)v) + 1]++;
+    for (size_t b = 0; b < 2 * (size_t)ncol; b++) start[b + 1] += start[b];
+    for (int32_t v : order) perm[v] = ++start[bucket(v)];     // 1-based
     if (ncolors) *ncolors = ncol;
     return JB_OK;
+}
+extern "C" int32_t jb_order_multicolor(int64_t nc, int64_t nf, const int64_t* N, int64_t* perm, int64_t* ncolors) {
+    return order_multicolor_impl(nc, nf, N, nullptr, perm, ncolors);
+}
+// same, with the cells flagged in `last` (nc flags) numbered at the end of their colour: the interior rows of a rank
+// then form contiguous ranges, so the interior SpMV can run while the halo is in flight
+extern "C" int32_t jb_order_multicolor_boundary_last(int64_t nc, int64_t nf, const int64_t* N, const int64_t* last, int64_t* perm,
+                                                      int64_t* ncolors) {
+    return order_multicolor_impl(nc, nf, N, last, perm, ncolors);
 }
 
 // process_partition(neighbors, partition; weights) (src/partitioning.jl:128-160): every block of the partition that is

@@ -112,14 +112,17 @@ __global__ void __launch_bounds__(256) spmv_stream_kernel(int nchunks, const int
                                                           const int32_t* __restrict__ colidx, const double* __restrict__ val,
                                                           const double* __restrict__ x, double* __restrict__ y, double alpha, double beta,
                                                           const double* __restrict__ u, double* sc, double* partials, unsigned int* counter,
-                                                          i64 n_dot) {
+                                                          i64 n_dot, const int32_t* __restrict__ chunk_list, int slot_offset, int total_slots,
+                                                          int finalize) {
     if (MODE != JB_DOT_NONE) {
         if (sc[KS_DONE] != 0.0) return;
     }
     __shared__ int32_t s_rp[JB_CHUNK_ROWS + 1];
     extern __shared__ double s_prod[];
     double d0 = 0.0, d1 = 0.0;
-    for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    // nchunks = number of work items; chunk_list (optional) selects a subset of the chunks (interior / boundary rows of a rank)
+    for (int k = blockIdx.x; k < nchunks; k += gridDim.x) {
+        const int c = chunk_list ? __ldg(chunk_list + k) : k;
         const int t0 = __ldg(chunk_ptr + c), nr = __ldg(chunk_ptr + c + 1) - t0;
         stream_chunk_products<BS, JB_STREAM_U>(t0, nr, rowptr, colidx, val, 0, x, s_rp, s_prod);
         if ((int)threadIdx.x < nr) {
@@ -141,13 +144,13 @@ __global__ void __launch_bounds__(256) spmv_stream_kernel(int nchunks, const int
     }
     if (MODE == JB_DOT_CV) {
         double r[1] = {d0};
-        grid_reduce<1, OpSum>(r, partials, counter, [=](double(&t)[1]) {
+        grid_reduce_ex<1, OpSum>(r, partials, counter, slot_offset, total_slots, finalize != 0, [=](double(&t)[1]) {
             sc[KS_SUM0] = t[0];
             if (sc[KS_DIST] == 0.0) ks_fin_alpha(sc);
         });
     } else if (MODE == JB_DOT_TS_TT) {
         double r[2] = {d0, d1};
-        grid_reduce<2, OpSum>(r, partials, counter, [=](double(&t)[2]) {
+        grid_reduce_ex<2, OpSum>(r, partials, counter, slot_offset, total_slots, finalize != 0, [=](double(&t)[2]) {
             sc[KS_SUM0] = t[0]; sc[KS_SUM1] = t[1];
             if (sc[KS_DIST] == 0.0) ks_fin_omega(sc);
         });
@@ -167,9 +170,25 @@ static int launch_spmv_stream(jb_csr* A, double alpha, const double* x, double b
     }
     int cap = ctx->sm_count * per_sm;
     if (MODE != JB_DOT_NONE && cap > JB_MAX_PARTIALS) cap = JB_MAX_PARTIALS;
+    if (A->split_phase != 0) {
+        // distributed two-launch form: phase 1 = interior chunks (no ghost column; runs while the halo is in flight, deposits its
+        // partial sums), phase 2 = boundary chunks (after the halo pull; finalises over both launches' partials)
+        const bool interior = A->split_phase == 1;
+        const int nwork = interior ? A->n_chunks_int : A->n_chunks_bnd;
+        const int cap2 = std::min(cap, JB_MAX_PARTIALS / 2);
+        const int g_int = std::max(1, std::min(A->n_chunks_int, cap2));
+        const int grid2 = interior ? g_int : std::max(1, std::min(std::max(nwork, 1), cap2));
+        spmv_stream_kernel<BS, MODE><<<grid2, 256, smem, ctx->stream>>>(nwork, A->d_chunks.p, A->d_rowptr.p, A->d_colidx.p, A->d_val.p, x, y, alpha, beta,
+                                                                       u, sc, ctx->d_partials, ctx->d_counters, n_dot < 0 ? A->n : n_dot,
+                                                                       interior ? A->d_chunks_int.p : A->d_chunks_bnd.p, interior ? 0 : g_int,
+                                                                       interior ? g_int : g_int + grid2, interior ? 0 : 1);
+        JB_CHECK_LAUNCH(ctx);
+        return JB_OK;
+    }
     const int grid = std::max(1, std::min(nchunks, cap));
     spmv_stream_kernel<BS, MODE><<<grid, 256, smem, ctx->stream>>>(nchunks, A->d_chunks.p, A->d_rowptr.p, A->d_colidx.p, A->d_val.p, x, y, alpha,
-                                                                  beta, u, sc, ctx->d_partials, ctx->d_counters, n_dot < 0 ? A->n : n_dot);
+                                                                  beta, u, sc, ctx->d_partials, ctx->d_counters, n_dot < 0 ? A->n : n_dot, nullptr, 0,
+                                                                  grid, 1);
     JB_CHECK_LAUNCH(ctx);
     return JB_OK;
 }
