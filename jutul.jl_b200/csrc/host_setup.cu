@@ -353,6 +353,20 @@ int jb_ilu_symbolic(jb_ilu* F, const int64_t* partition) {
     };
     cut(F->h_LptrT, F->h_levF_ptr, F->nlevF, F->h_chunksF, F->h_levF_chunk);
     cut(F->h_UptrT, F->h_levB_ptr, F->nlevB, F->h_chunksB, F->h_levB_chunk);
+    // two-colour structure: second forward level == rows without U entries, first forward level == second backward level
+    // (no row has both L and U entries; rows with neither — e.g. the decoupled ghost rows of a distributed run — are "isolated")
+    F->two_colour = false;
+    F->h_iso.clear();
+    if (F->stream_ok && F->nlevF == 2 && F->nlevB == 2) {
+        bool ok = true;
+        for (i64 r = 0; ok && r < n; r++) {
+            const bool hasL = F->h_Lend[r] != F->h_Lstart[r], hasU = F->h_Uend[r] != F->h_Ustart[r];
+            if (hasL && hasU) ok = false;
+            if (!hasL && !hasU) F->h_iso.push_back((int32_t)r);
+        }
+        F->two_colour = ok;
+        if (!ok) F->h_iso.clear();
+    }
     return JB_OK;
 }
 
@@ -372,6 +386,7 @@ int jb_ilu_upload(jb_ilu* F) {
               F->d_Lmap.upload(F->h_Lmap, s) == cudaSuccess && F->d_Umap.upload(F->h_Umap, s) == cudaSuccess &&
               F->d_Dmap.upload(F->h_Dmap, s) == cudaSuccess && F->d_upd_ptr.upload(F->h_upd_ptr, s) == cudaSuccess &&
               F->d_upd_tgt.upload(F->h_upd_tgt, s) == cudaSuccess && F->d_upd_src.upload(F->h_upd_src, s) == cudaSuccess;
+    ok = ok && (F->h_iso.empty() || F->d_iso.upload(F->h_iso, s) == cudaSuccess);
     ok = ok && F->d_LptrT.upload(F->h_LptrT, s) == cudaSuccess && F->d_UptrT.upload(F->h_UptrT, s) == cudaSuccess &&
          F->d_chunksF.upload(F->h_chunksF, s) == cudaSuccess && F->d_chunksB.upload(F->h_chunksB, s) == cudaSuccess;
     const size_t b2 = (size_t)F->bs * F->bs;

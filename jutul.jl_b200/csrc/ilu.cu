@@ -134,12 +134,14 @@ __global__ void __launch_bounds__(256) ilu_backward_level_kernel(int32_t t0, int
 
 // ---- row-chunk stream form of the sweeps (default; see jb_stream.cuh). One launch per level; a CTA streams the
 //      L (or U) entries of its chunk with unit stride and gathers x of earlier levels. ----
-template <int BS, bool BACKWARD>
+template <int BS>
 __global__ void __launch_bounds__(256) ilu_sweep_stream_kernel(int c0, int c1, const int32_t* __restrict__ chunk_ptr,
                                                                const int32_t* __restrict__ ptrT, const int32_t* __restrict__ col,
                                                                const double* __restrict__ fv, size_t val_block_offset,
                                                                const int32_t* __restrict__ order, const double* __restrict__ dinv,
-                                                               const double* b, double* x, const double* sc) {
+                                                               const double* rhs, const double* gsrc, int apply_dinv, double* x, const double* sc) {
+    // x_i = [D_i^{-1}] (rhs_i - sum_j M_ij gsrc_j).  forward: rhs = b, gsrc = x;  backward: rhs = gsrc = x, with D^{-1};
+    // two-colour fused sweeps: rhs = b, gsrc = b (first) / x (second), both with D^{-1}.
     if (sc && sc[KS_DONE] != 0.0) return;
     __shared__ int32_t s_rp[JB_CHUNK_ROWS + 1];
     extern __shared__ double s_prod[];
@@ -151,15 +153,15 @@ __global__ void __launch_bounds__(256) ilu_sweep_stream_kernel(int c0, int c1, c
         if ((int)threadIdx.x < nr) {
             i = __ldg(order + t0 + threadIdx.x);
 #pragma unroll
-            for (int e = 0; e < BS; e++) v[e] = BACKWARD ? x[(size_t)i * BS + e] : b[(size_t)i * BS + e];
+            for (int e = 0; e < BS; e++) v[e] = rhs[(size_t)i * BS + e];
         }
-        stream_chunk_products<BS, JB_STREAM_U>(t0, nr, ptrT, col, fv, val_block_offset, x, s_rp, s_prod);
+        stream_chunk_products<BS, JB_STREAM_U>(t0, nr, ptrT, col, fv, val_block_offset, gsrc, s_rp, s_prod);
         if ((int)threadIdx.x < nr) {
             double acc[BS];
             stream_row_sum<BS>(threadIdx.x, s_rp, s_prod, acc);
 #pragma unroll
             for (int e = 0; e < BS; e++) v[e] -= acc[e];
-            if (BACKWARD) {
+            if (apply_dinv) {
                 double d[BS * BS], out[BS];
 #pragma unroll
                 for (int q = 0; q < BS * BS; q++) d[q] = __ldg(dinv + (size_t)i * BS * BS + q);
@@ -201,6 +203,23 @@ __global__ void __launch_bounds__(256) ilu_light_level_kernel(int32_t t0, int32_
 }
 
 template <int BS>
+__global__ void __launch_bounds__(256) ilu_iso_kernel(int32_t n, const int32_t* __restrict__ rows, const double* __restrict__ dinv, const double* b,
+                                                      double* x, const double* sc) {
+    if (sc && sc[KS_DONE] != 0.0) return;
+    const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const size_t i = (size_t)__ldg(rows + t);
+    double v[BS], d[BS * BS], out[BS];
+#pragma unroll
+    for (int e = 0; e < BS; e++) v[e] = b[i * BS + e];
+#pragma unroll
+    for (int q = 0; q < BS * BS; q++) d[q] = __ldg(dinv + i * BS * BS + q);
+    blk_mulvec<BS>(d, v, out);
+#pragma unroll
+    for (int e = 0; e < BS; e++) x[i * BS + e] = out[e];
+}
+
+template <int BS>
 static int ilu_apply_stream_t(jb_ilu* F, const double* b, double* x, const double* sc) {
     jb_ctx* ctx = F->csr->ctx;
     ProfScope _ps(ctx, JB_PROF_ILU_APPLY);
@@ -208,11 +227,34 @@ static int ilu_apply_stream_t(jb_ilu* F, const double* b, double* x, const doubl
     const size_t smem = (size_t)JB_CHUNK_CAP * BS * sizeof(double);
     static int per_sm = 0;
     if (per_sm == 0) {
-        cudaFuncSetAttribute(ilu_sweep_stream_kernel<BS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(ilu_sweep_stream_kernel<BS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ilu_sweep_stream_kernel<BS, true>, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        cudaFuncSetAttribute(ilu_sweep_stream_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ilu_sweep_stream_kernel<BS>, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     }
     const int cap = ctx->sm_count * per_sm;
+    if (F->two_colour) {
+        // Two-colour fast path (rows of the second forward level have no U entries, rows of the first have no L entries):
+        //   second colour:  x_B = D_B^{-1} (b_B - L_BR b_R)        (its forward and backward steps fused; y_R = b_R is read in place)
+        //   first colour:   x_R = D_R^{-1} (b_R - U_RB x_B)
+        // two launches instead of four, no copy of b_R, no second pass over x_B; arithmetic identical to the general path.
+        {
+            const int c0 = F->h_levF_chunk[1], c1 = F->h_levF_chunk[2];
+            ilu_sweep_stream_kernel<BS><<<std::max(1, std::min(c1 - c0, cap)), 256, smem, s>>>(c0, c1, F->d_chunksF.p, F->d_LptrT.p, F->d_Lcol.p, F->d_fv.p, 0,
+                                                                                              F->d_forder.p, F->d_dinv.p, b, b, 1, x, sc);
+            JB_CHECK_LAUNCH(ctx);
+        }
+        {
+            const int c0 = F->h_levB_chunk[1], c1 = F->h_levB_chunk[2];
+            ilu_sweep_stream_kernel<BS><<<std::max(1, std::min(c1 - c0, cap)), 256, smem, s>>>(c0, c1, F->d_chunksB.p, F->d_UptrT.p, F->d_Ucol.p, F->d_fv.p,
+                                                                                              (size_t)(F->nL + F->n), F->d_border.p, F->d_dinv.p, b, x, 1, x, sc);
+            JB_CHECK_LAUNCH(ctx);
+        }
+        if (!F->h_iso.empty()) {   // isolated rows: x_i = D_i^{-1} b_i
+            const int32_t ni = (int32_t)F->h_iso.size();
+            ilu_iso_kernel<BS><<<(ni + 255) / 256, 256, 0, s>>>(ni, F->d_iso.p, F->d_dinv.p, b, x, sc);
+            JB_CHECK_LAUNCH(ctx);
+        }
+        return JB_OK;
+    }
     for (int l = 0; l < F->nlevF; l++) {
         const int c0 = F->h_levF_chunk[l], c1 = F->h_levF_chunk[l + 1];
         if (c1 <= c0) continue;
@@ -222,8 +264,8 @@ static int ilu_apply_stream_t(jb_ilu* F, const double* b, double* x, const doubl
             JB_CHECK_LAUNCH(ctx);
             continue;
         }
-        ilu_sweep_stream_kernel<BS, false><<<std::min(c1 - c0, cap), 256, smem, s>>>(c0, c1, F->d_chunksF.p, F->d_LptrT.p, F->d_Lcol.p, F->d_fv.p, 0,
-                                                                                     F->d_forder.p, F->d_dinv.p, b, x, sc);
+        ilu_sweep_stream_kernel<BS><<<std::min(c1 - c0, cap), 256, smem, s>>>(c0, c1, F->d_chunksF.p, F->d_LptrT.p, F->d_Lcol.p, F->d_fv.p, 0,
+                                                                              F->d_forder.p, F->d_dinv.p, b, x, 0, x, sc);
         JB_CHECK_LAUNCH(ctx);
     }
     for (int l = 0; l < F->nlevB; l++) {
@@ -235,8 +277,8 @@ static int ilu_apply_stream_t(jb_ilu* F, const double* b, double* x, const doubl
             JB_CHECK_LAUNCH(ctx);
             continue;
         }
-        ilu_sweep_stream_kernel<BS, true><<<std::min(c1 - c0, cap), 256, smem, s>>>(c0, c1, F->d_chunksB.p, F->d_UptrT.p, F->d_Ucol.p, F->d_fv.p,
-                                                                                    (size_t)(F->nL + F->n), F->d_border.p, F->d_dinv.p, b, x, sc);
+        ilu_sweep_stream_kernel<BS><<<std::min(c1 - c0, cap), 256, smem, s>>>(c0, c1, F->d_chunksB.p, F->d_UptrT.p, F->d_Ucol.p, F->d_fv.p,
+                                                                              (size_t)(F->nL + F->n), F->d_border.p, F->d_dinv.p, x, x, 1, x, sc);
         JB_CHECK_LAUNCH(ctx);
     }
     return JB_OK;

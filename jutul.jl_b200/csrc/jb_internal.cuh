@@ -182,6 +182,9 @@ struct jb_ilu {
     std::vector<int32_t> h_chunksF, h_chunksB;        // stream-kernel chunks (stored-row boundaries), never across a level
     std::vector<int32_t> h_levF_chunk, h_levB_chunk;  // first chunk of each level (nlev+1)
     bool stream_ok = false;
+    bool two_colour = false;                          // 2 forward / 2 backward levels with complementary row sets: fused sweeps
+    std::vector<int32_t> h_iso;                       // rows with neither L nor U entries (two-colour path)
+    DBuf<int32_t> d_iso;
     DBuf<int32_t> d_LptrT, d_UptrT, d_chunksF, d_chunksB;
     // device
     DBuf<int32_t> d_forder, d_border, d_Lstart, d_Lend, d_Ustart, d_Uend, d_Lcol, d_Ucol, d_Lmap, d_Umap, d_Dmap;

@@ -449,6 +449,13 @@ def test_reordered_system_matches_oracle_on_renumbered_mesh(J, O, ctx):
     fg, fo = sim.prec.factors(), ilu.get()
     for k in ("L", "U", "D"):
         assert np.abs(fg[k] - fo[k]).max() <= 1e-10 * np.abs(fo[k]).max()
+    # the two-colour fused sweeps (2 launches) must reproduce ldiv! exactly like the general level-by-level path
+    assert sim.prec.info()["forward_levels"] == 2
+    bb = np.random.default_rng(1).standard_normal(2 * n)
+    xd = ctx.zeros(2 * n)
+    sim.prec.apply(xd, ctx.transfer(bb))
+    xo = ilu.solve(bb)
+    assert np.abs(xd.get() - xo).max() <= 1e-10 * np.abs(xo).max()
     x, st, its, hist = O.bicgstab(n, 2, s2["rowptr"], s2["colidx"], sim.jac.nonzeros(), sim.r.get(), ilu, rtol=1e-8, itmax=300)
     assert abs(rep["linear_iterations"] - its) <= max(2, its // 10)
     assert np.allclose(rep["linear_residuals"][:6], hist[:6], rtol=1e-6)
