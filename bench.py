@@ -151,6 +151,13 @@ def run_b200(args):
         cls = prof.collect()
     kernels = {}
     bytes_of = {"assembly": alg["assembly"], "spmv": alg["spmv"], "ilu_apply": alg["ilu_apply"], "ilu_factor": alg["ilu_factor"]}
+    # two-colour ILU(0): first-colour rows of the operator A*N^-1*w are read off w (csrc/krylov.cu); the SpMV then streams only
+    # the remaining rows' blocks. Algorithmic bytes of that launch: the blocks it does read, the full x and y, and w on the
+    # identity rows.
+    id_chunks, id_rows, id_blocks = sim.krylov.identity_info()
+    if id_rows:
+        nb = nc + 2 * nf
+        bytes_of["spmv"] = (nb - id_blocks) * 36 + 4 * (nc - id_rows + 1) + 2 * nc * 16 + id_rows * 16
     for k, bts in bytes_of.items():
         t, c = cls[k]
         if c:
@@ -220,7 +227,8 @@ def run_b200(args):
                    "l2_policy": "inputs larger than L2 (Jacobian values %.2f GB); no flush needed" % ((nc + 2 * nf) * 32 / 1e9),
                    "parallelism": "1 GPU", "setup_seconds": t_setup,
                    "cell_ordering": args.ordering + (f" ({sim.ncolors} colours = ILU levels)" if sim.ncolors else ""),
-                   "ilu": sim.prec.info()},
+                   "ilu": sim.prec.info(),
+                   "operator_identity_rows": id_rows},
         "newton_iterations_per_step": n_newton / max(args.steps, 1), "converged": all(r[0] for r in results),
         "linear_iterations_per_newton": float(np.mean(lin_its)) if lin_its else None, "linear_iterations": results[0][2],
         "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "kernels": kernels,

@@ -202,6 +202,10 @@ int32_t jb_krylov_destroy(jb_krylov* ks);
 int32_t jb_krylov_solve(jb_krylov* ks, const double* d_r, double* d_dx, double rtol, double atol,
                         int32_t itmax, int32_t min_it, int32_t side, int32_t* iters, double* hist,
                         int32_t hist_cap);
+/* info[0..2] = stream chunks / rows / blocks of the Jacobian whose product in the right-preconditioned operator
+ * A N^{-1} w is read off w (first-colour rows of a two-colour ILU(0), see krylov.cu; 0 when not applicable or
+ * switched off with JB_RB_IDENTITY=0). Valid after the first solve; used for the byte accounting of bench.py. */
+int32_t jb_krylov_info(jb_krylov* ks, int64_t* info);
 
 /* ---- apply_scaling_to_linearized_system! (src/linsolve/default.jl:325-385):
  *      kind 0 none, 1 diagonal (block rows scaled by inv(D_ii)), 2 dt (J, r *= dt). */

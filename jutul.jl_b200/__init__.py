@@ -366,6 +366,13 @@ class GenericKrylov(_Handle):
         check(self.ctx.lib.jb_krylov_create(jac.h, ph, kind, C.byref(h)), self.ctx.h, "jb_krylov_create")
         self.h = h
 
+    def identity_info(self):
+        """(chunks, rows, blocks) of the Jacobian whose product in A*N^-1*w is read off w (two-colour ILU(0),
+        right preconditioning; see csrc/krylov.cu). Valid after the first solve."""
+        info = (C.c_int64 * 3)()
+        check(self.ctx.lib.jb_krylov_info(self.h, info), self.ctx.h, "jb_krylov_info")
+        return int(info[0]), int(info[1]), int(info[2])
+
 
 def linear_solve(krylov, r, dx, rtol=None, atol=None, update_preconditioner=True):
     """linear_solve!(lsys, krylov, ...): solves J x = r, leaves dx = -x. Returns

@@ -31,6 +31,9 @@
 // (src/conservation/conservation.jl:642-649), see SURVEY.md §8(d) / DESIGN.md.
 #include "jb_internal.cuh"
 #include "jb_reduce.cuh"
+#include "jb_tma.cuh"
+#include <algorithm>
+#include <cstddef>
 
 // inv_mu: the kernels multiply by 1/mu instead of dividing (FP64 division is a ~30-instruction sequence)
 struct TPParams { double rho0[2], c[2], mu[2], p0, inv_mu[2]; };
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(JB_ASM_THREADS) twophase_assemble_stream_kerne
             const double mass = pvc * (rho * S);
             double ar = (mass - __ldg(M0 + 2 * c + a)) * inv_dt;
             if (src) ar += __ldg(src + 2 * c + a);
-            double adp = (pvc * (P.c[a] * rho * S)) * inv_dt;
+            double adp = (pvc * ((a ? P.c[1] : P.c[0]) * rho * S)) * inv_dt;
             double ads = (pvc * (rho * dS)) * inv_dt;
             for (int e = s_pos[j] - base; e < s_pos[j + 1] - base; e++) {
                 ar += s_part[a * LD + e];
@@ -260,6 +263,217 @@ __global__ void __launch_bounds__(JB_ASM_THREADS) twophase_assemble_stream_kerne
             }
         }
         __syncthreads();
+    }
+}
+
+// ---- TMA-staged persistent form (default) ---------------------------------------------------------------------
+// Same row-owner arithmetic and the same summation order as the stream kernel above; what changes is how the bytes
+// move. A persistent CTA walks a host-built chunk table (<= 64 cells / <= 448 half-faces per chunk). For every chunk
+// ONE thread issues 1-D bulk copies (cp.async.bulk, jb_tma.cuh) of all contiguous inputs of the chunk — half-face
+// neighbour list, T, sign*gdz, 16-bit Jacobian slots, half-face offsets, diagonal slots, pore volumes, M0 and the
+// chunk's own 32-byte cell records — into one of two shared-memory stages, completing on an mbarrier; the copies of
+// chunk i+1 fly while chunk i is evaluated. The only load a thread still waits for is the 32-byte neighbour-record
+// gather (one 256-bit LDG), issued for all of a thread's half-faces before the first flux is evaluated.
+// Byte diet relative to the stream kernel: Jacobian slot as uint16 offset from the chunk's first row (2 B instead of
+// 4 B per half-face); the two perspectives of a half-face share rho_avg / theta / q (flux_pair); the dense source
+// buffer is read only by chunks that contain a source cell; Jacobian / residual stores are streaming (st.cs) so the
+// cell records stay in L2; the chunk table is ordered so that chunks of different colours that are each other's
+// neighbours are processed at the same time (their records are then fetched from HBM once, not twice).
+#define JB_ASM2_CELLS 64
+#define JB_ASM2_HF 448
+#define JB_ASM2_THREADS 128
+#define JB_ASM2_U 4
+static_assert(JB_ASM2_U * JB_ASM2_THREADS >= JB_ASM2_HF, "one unrolled pass must cover a chunk");
+static_assert(2 * JB_ASM2_CELLS <= JB_ASM2_THREADS, "two threads per cell in the row phase");
+
+struct __align__(16) Asm2Stage {     // every member starts on a 16-byte boundary and can hold the widened window
+    double T[JB_ASM2_HF + 2];
+    double sg[JB_ASM2_HF + 2];
+    double rec[JB_ASM2_CELLS * 4];
+    double M0[JB_ASM2_CELLS * 2];
+    double pv[JB_ASM2_CELLS + 2];
+    int32_t other[JB_ASM2_HF + 4];
+    int32_t hfpos[JB_ASM2_CELLS + 8];
+    int32_t diag[JB_ASM2_CELLS + 4];
+    uint16_t lp[JB_ASM2_HF + 8];
+};
+static_assert(offsetof(Asm2Stage, sg) % 16 == 0 && offsetof(Asm2Stage, rec) % 16 == 0 && offsetof(Asm2Stage, M0) % 16 == 0 &&
+              offsetof(Asm2Stage, pv) % 16 == 0 && offsetof(Asm2Stage, other) % 16 == 0 && offsetof(Asm2Stage, hfpos) % 16 == 0 &&
+              offsetof(Asm2Stage, diag) % 16 == 0 && offsetof(Asm2Stage, lp) % 16 == 0 && sizeof(Asm2Stage) % 16 == 0, "stage alignment");
+
+__device__ __forceinline__ void ld_rec256(const double* __restrict__ rec, int32_t c, double (&o)[4]) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(rec + 4 * (size_t)c));
+}
+
+// Both perspectives of the two-point flux of phase a across one half-face self -> other:
+//   F, dFdp, dFds : flux out of self and its partials w.r.t. (p, Sw) of self  (residual + diagonal block of row self)
+//   Bp, Bs        : -d F_{other->self} / d (p, Sw) of other                      (the entry J[self, other])
+// q_{other->self} = -q exactly (same rho_avg, negated terms), so one theta / q / upwind decision serves both.
+__device__ __forceinline__ void flux_pair(const TPParams& P, int a, double ps, double Ss, double rs, double po, double So, double ro,
+                                          double T, double sg, double& F, double& dFdp, double& dFds, double& Bp, double& Bs) {
+    const double dS = a ? -1.0 : 1.0;
+    const double mob_s = (rs * (Ss * Ss)) * P.inv_mu[a];
+    const double mob_o = (ro * (So * So)) * P.inv_mu[a];
+    const double rho_avg = 0.5 * (rs + ro);
+    const double theta = ps - po + sg * rho_avg;
+    const double q = T * theta;
+    const double dq_s = T * (1.0 + sg * (0.5 * (P.c[a] * rs)));
+    const double dq_o = T * (1.0 + (-sg) * (0.5 * (P.c[a] * ro)));
+    const bool ups = q > 0, upo = q < 0;
+    const double mF = ups ? mob_s : mob_o;   // upstream mobility seen from self (q == 0 / NaN: other, as upw_flux)
+    const double mN = upo ? mob_o : mob_s;   // upstream mobility seen from the neighbour
+    const double u_rho = ups ? rs : ro, u_S = ups ? Ss : So;
+    const double dm_dp = P.c[a] * mF;
+    const double dm_ds = (u_rho * (2.0 * u_S * dS)) * P.inv_mu[a];
+    F = mF * q;
+    dFdp = mF * dq_s;
+    dFds = 0.0;
+    double np = mN * dq_o, ns = 0.0;
+    if (ups) { dFdp += q * dm_dp; dFds = q * dm_ds; }
+    if (upo) { const double qo = -q; np += qo * dm_dp; ns = qo * dm_ds; }
+    Bp = -np;
+    Bs = -ns;
+}
+
+template <bool JAC>
+__global__ void __launch_bounds__(JB_ASM2_THREADS, 4) twophase_assemble_tma_kernel(
+    int nchunks, const Asm2Chunk* __restrict__ table, TPParams P, const int32_t* __restrict__ hf_pos, const int32_t* __restrict__ hf_other,
+    const uint16_t* __restrict__ hf_lp, const double* __restrict__ hf_T, const double* __restrict__ hf_sgdz, const int32_t* __restrict__ diag_pos,
+    const double* __restrict__ rec, const double* __restrict__ pv, const double* __restrict__ M0, const double* __restrict__ src, double inv_dt,
+    double* __restrict__ nz, double* __restrict__ r) {
+    constexpr int NP = JAC ? 6 : 2;
+    constexpr int LD = JB_ASM2_HF + 1;
+    extern __shared__ __align__(128) unsigned char asm2_smem[];
+    Asm2Stage* stage = reinterpret_cast<Asm2Stage*>(asm2_smem);
+    double* s_part = reinterpret_cast<double*>(asm2_smem + 2 * sizeof(Asm2Stage));   // [NP][LD]
+    Asm2Chunk* s_meta = reinterpret_cast<Asm2Chunk*>(s_part + NP * LD + (NP * LD & 1));
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_meta + 2);
+    unsigned char* s_owner = reinterpret_cast<unsigned char*>(s_bar + 2);
+    const int tid = threadIdx.x;
+
+    auto issue = [&](int k, int s) {   // thread 0 only
+        const int4* tp = reinterpret_cast<const int4*>(table + k);
+        const int4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+        Asm2Chunk ci;
+        ci.c0 = t0.x; ci.nr = t0.y; ci.hf0 = t0.z; ci.cnt = t0.w; ci.row0 = t1.x; ci.flags = t1.y; ci.pad0 = 0; ci.pad1 = 0;
+        s_meta[s] = ci;
+        Asm2Stage& S = stage[s];
+        const JbSpan<double> sT(hf_T, ci.hf0, ci.cnt), sG(hf_sgdz, ci.hf0, ci.cnt), sPv(pv, ci.c0, ci.nr);
+        const JbSpan<int32_t> sO(hf_other, ci.hf0, ci.cnt), sHp(hf_pos, ci.c0, ci.nr + 1), sD(diag_pos, ci.c0, ci.nr);
+        const JbSpan<uint16_t> sL(hf_lp, ci.hf0, ci.cnt);
+        const uint32_t bRec = (uint32_t)ci.nr * 32u, bM0 = (uint32_t)ci.nr * 16u;
+        uint32_t total = sT.bytes + sG.bytes + sPv.bytes + sO.bytes + sHp.bytes + bRec + bM0;
+        if (JAC) total += sD.bytes + sL.bytes;
+        jb_mbar_expect_tx(&s_bar[s], total);
+        const uint64_t pol = jb_policy_evict_first();
+        if (sT.bytes) jb_bulk_g2s_hint(S.T, sT.src, sT.bytes, &s_bar[s], pol);
+        if (sG.bytes) jb_bulk_g2s_hint(S.sg, sG.src, sG.bytes, &s_bar[s], pol);
+        if (sO.bytes) jb_bulk_g2s_hint(S.other, sO.src, sO.bytes, &s_bar[s], pol);
+        if (JAC && sL.bytes) jb_bulk_g2s_hint(S.lp, sL.src, sL.bytes, &s_bar[s], pol);
+        if (sHp.bytes) jb_bulk_g2s_hint(S.hfpos, sHp.src, sHp.bytes, &s_bar[s], pol);
+        if (JAC && sD.bytes) jb_bulk_g2s_hint(S.diag, sD.src, sD.bytes, &s_bar[s], pol);
+        if (sPv.bytes) jb_bulk_g2s_hint(S.pv, sPv.src, sPv.bytes, &s_bar[s], pol);
+        if (bM0) jb_bulk_g2s_hint(S.M0, M0 + 2 * (size_t)ci.c0, bM0, &s_bar[s], pol);
+        if (bRec) jb_bulk_g2s(S.rec, rec + 4 * (size_t)ci.c0, bRec, &s_bar[s]);
+    };
+
+    if (tid == 0) {
+        jb_mbar_init(&s_bar[0], 1);
+        jb_mbar_init(&s_bar[1], 1);
+        jb_mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if ((int)blockIdx.x < nchunks) issue(blockIdx.x, 0);
+        if ((int)(blockIdx.x + gridDim.x) < nchunks) issue(blockIdx.x + gridDim.x, 1);
+    }
+    __syncthreads();
+
+    int it = 0;
+    for (int k = blockIdx.x; k < nchunks; k += gridDim.x, it++) {
+        const int s = it & 1;
+        jb_mbar_wait(&s_bar[s], (uint32_t)(it >> 1) & 1u);
+        const Asm2Stage& S = stage[s];
+        const int c0 = s_meta[s].c0, nr = s_meta[s].nr, hf0 = s_meta[s].hf0, cnt = s_meta[s].cnt, row0 = s_meta[s].row0;
+        const int flags = s_meta[s].flags;
+        const int l8 = jb_span_lead<double>((size_t)hf0), l4 = jb_span_lead<int32_t>((size_t)hf0), l2 = jb_span_lead<uint16_t>((size_t)hf0);
+        const int lc4 = jb_span_lead<int32_t>((size_t)c0), lc8 = jb_span_lead<double>((size_t)c0);
+        for (int j = tid; j < nr; j += JB_ASM2_THREADS) {
+            const int e1 = S.hfpos[lc4 + j + 1] - hf0;
+            for (int e = S.hfpos[lc4 + j] - hf0; e < e1; e++) s_owner[e] = (unsigned char)j;
+        }
+        __syncthreads();
+        {
+            double ro[JB_ASM2_U][4];
+            double Tv[JB_ASM2_U], sgv[JB_ASM2_U];
+            int own[JB_ASM2_U];
+            // all neighbour gathers of this thread go out before the first flux is evaluated
+#pragma unroll
+            for (int u = 0; u < JB_ASM2_U; u++) {
+                const int e = tid + u * JB_ASM2_THREADS;
+                if (e < cnt) ld_rec256(rec, S.other[l4 + e], ro[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < JB_ASM2_U; u++) {
+                const int e = tid + u * JB_ASM2_THREADS;
+                if (e < cnt) { Tv[u] = S.T[l8 + e]; sgv[u] = S.sg[l8 + e]; own[u] = s_owner[e]; }
+            }
+#pragma unroll
+            for (int u = 0; u < JB_ASM2_U; u++) {
+                const int e = tid + u * JB_ASM2_THREADS;
+                if (e < cnt) {
+                    const double2 sa = *reinterpret_cast<const double2*>(S.rec + 4 * own[u]);
+                    const double2 sb = *reinterpret_cast<const double2*>(S.rec + 4 * own[u] + 2);
+                    double part[6], blk[4];
+#pragma unroll
+                    for (int a = 0; a < 2; a++) {
+                        const double Ss = a ? 1.0 - sa.y : sa.y, So = a ? 1.0 - ro[u][1] : ro[u][1];
+                        const double rs = a ? sb.y : sb.x, rn = a ? ro[u][3] : ro[u][2];
+                        flux_pair(P, a, sa.x, Ss, rs, ro[u][0], So, rn, Tv[u], sgv[u], part[a], part[2 + a], part[4 + a], blk[a], blk[2 + a]);
+                    }
+                    if (JAC) {
+                        double2* dst = reinterpret_cast<double2*>(nz + ((size_t)row0 + S.lp[l2 + e]) * 4);
+                        __stcs(dst, make_double2(blk[0], blk[1]));
+                        __stcs(dst + 1, make_double2(blk[2], blk[3]));
+                    }
+#pragma unroll
+                    for (int q = 0; q < NP; q++) s_part[q * LD + e] = part[q];
+                }
+            }
+        }
+        __syncthreads();
+        // two threads per cell: thread (j, a) owns equation a -> r[a], d/dp, d/dS; accumulation first, then the half-faces
+        // in conn_pos order (fill_conservation_eq!, src/conservation/conservation.jl:373-430)
+        if (tid < 2 * nr) {
+            const int j = tid >> 1, a = tid & 1;
+            const size_t c = (size_t)c0 + j;
+            const double sw = S.rec[4 * j + 1];
+            const double Sa = a ? 1.0 - sw : sw;
+            const double dS = a ? -1.0 : 1.0;
+            const double rho = S.rec[4 * j + 2 + a];
+            const double pvc = S.pv[lc8 + j];
+            const double mass = pvc * (rho * Sa);
+            double ar = (mass - S.M0[2 * j + a]) * inv_dt;
+            if (flags & 1) ar += __ldg(src + 2 * c + a);
+            double adp = (pvc * ((a ? P.c[1] : P.c[0]) * rho * Sa)) * inv_dt;
+            double ads = (pvc * (rho * dS)) * inv_dt;
+            const int e1 = S.hfpos[lc4 + j + 1] - hf0;
+            for (int e = S.hfpos[lc4 + j] - hf0; e < e1; e++) {
+                ar += s_part[a * LD + e];
+                if (JAC) { adp += s_part[(2 + a) * LD + e]; ads += s_part[(4 + a) * LD + e]; }
+            }
+            r[2 * c + a] = ar;
+            if (JAC) {
+                double* dst = nz + (size_t)S.diag[lc4 + j] * 4;
+                __stcs(dst + a, adp);
+                __stcs(dst + 2 + a, ads);
+            }
+        }
+        __syncthreads();   // stage s and s_part are free again
+        if (tid == 0) {
+            const int k2 = k + 2 * (int)gridDim.x;
+            if (k2 < nchunks) issue(k2, s);
+        }
     }
 }
 
@@ -335,6 +549,60 @@ __global__ void scatter_sources_kernel(i64 nsrc, const int32_t* __restrict__ cel
         for (i64 k = 0; k < nsrc; k++) { src[2 * (size_t)cells[k]] += vals[2 * k]; src[2 * (size_t)cells[k] + 1] += vals[2 * k + 1]; }
 }
 
+// Chunk table of the TMA-staged kernel: cut [0, n_assemble) into chunks, record the 16-bit Jacobian slots, flag chunks
+// holding a source cell, and order the table by min(own position, mean neighbour position) so that chunks that are each
+// other's neighbours (e.g. the two colours of a multicolour numbering) are in flight together. Leaves asm2_ok = false
+// when a cell has more half-faces than a stage holds (the lane-per-half-face kernel takes over).
+static int build_asm2(jb_twophase* m) {
+    jb_tpfa* t = m->t;
+    jb_mesh* mesh = t->mesh;
+    jb_ctx* ctx = mesh->ctx;
+    m->asm2_ok = false;
+    m->h_asm2.clear();
+    const int32_t n_asm = (int32_t)(m->n_assemble >= 0 ? m->n_assemble : mesh->nc);
+    std::vector<uint16_t> lp((size_t)mesh->nhf, 0);
+    std::vector<char> has_src((size_t)mesh->nc, 0);
+    for (int32_t c : m->h_src_cells) has_src[c] = 1;
+    std::vector<double> key;
+    int32_t start = 0;
+    while (start < n_asm) {
+        int32_t end = start;
+        while (end < n_asm && end - start < JB_ASM2_CELLS && mesh->h_hf_pos[end + 1] - mesh->h_hf_pos[start] <= JB_ASM2_HF) end++;
+        if (end == start) return JB_OK;
+        Asm2Chunk ci;
+        ci.c0 = start; ci.nr = end - start; ci.hf0 = mesh->h_hf_pos[start]; ci.cnt = mesh->h_hf_pos[end] - ci.hf0;
+        ci.row0 = t->csr->h_rowptr[start]; ci.flags = 0; ci.pad0 = ci.pad1 = 0;
+        double so = 0.0;
+        for (int32_t i = ci.hf0; i < ci.hf0 + ci.cnt; i++) {
+            const int64_t d = (int64_t)t->h_hf_rowpos[i] - ci.row0;
+            if (d < 0 || d > 65535) return JB_OK;
+            lp[i] = (uint16_t)d;
+            so += mesh->h_hf_other[i];
+        }
+        for (int32_t c = start; c < end; c++) if (has_src[c]) ci.flags |= 1;
+        const double mid = 0.5 * ((double)start + end);
+        key.push_back(ci.cnt > 0 ? std::min(mid, so / ci.cnt) : mid);
+        m->h_asm2.push_back(ci);
+        start = end;
+    }
+    std::vector<int32_t> ord(m->h_asm2.size());
+    for (size_t i = 0; i < ord.size(); i++) ord[i] = (int32_t)i;
+    std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+    std::vector<Asm2Chunk> tab(ord.size());
+    for (size_t i = 0; i < ord.size(); i++) tab[i] = m->h_asm2[ord[i]];
+    m->h_asm2.swap(tab);
+    if (m->h_asm2.empty()) return JB_OK;
+    if (m->d_asm2.upload(m->h_asm2, ctx->stream) != cudaSuccess || m->d_hf_lp.upload(lp, ctx->stream) != cudaSuccess)
+        JB_FAIL(ctx, JB_ERR_ALLOC, "jb_twophase: device allocation failed (assembly chunk table)");
+    m->asm2_ok = true;
+    return JB_OK;
+}
+
+static int asm_variant() {   // JB_ASM_VARIANT: 0/unset = TMA-staged, 1 = stream, 2 = lane-per-half-face (read per call: tests switch it)
+    const char* e = getenv("JB_ASM_VARIANT");
+    return e ? atoi(e) : 0;
+}
+
 static TPParams make_params(const jb_twophase* m) {
     TPParams P;
     P.rho0[0] = m->params[0]; P.rho0[1] = m->params[1]; P.c[0] = m->params[2]; P.c[1] = m->params[3];
@@ -365,7 +633,36 @@ int jb_launch_twophase_assemble(jb_twophase* m, const double* d_M0, double dt, d
     const i64 cells_per_cta = 256 / LPC;
     const int grid = (int)std::max<i64>(1, (nc + cells_per_cta - 1) / cells_per_cta);
     const double* src = m->nsrc > 0 ? m->d_src.p : nullptr;
-    if (!m->h_chunks.empty()) {
+    if (asm_variant() == 0 && m->asm2_ok && ((uintptr_t)d_M0 & 15) == 0) {
+        constexpr int LD = JB_ASM2_HF + 1;
+        const int np = jac ? 6 : 2;
+        const size_t smem = 2 * sizeof(Asm2Stage) + (size_t)(np * LD + (np * LD & 1)) * sizeof(double) + 2 * sizeof(Asm2Chunk) + 2 * sizeof(uint64_t) +
+                            JB_ASM2_HF;
+        static int per_sm2[2] = {0, 0};
+        if (per_sm2[jac] == 0) {
+            if (jac) {
+                cudaFuncSetAttribute(twophase_assemble_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2[1], twophase_assemble_tma_kernel<true>, JB_ASM2_THREADS, smem);
+            } else {
+                cudaFuncSetAttribute(twophase_assemble_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2[0], twophase_assemble_tma_kernel<false>, JB_ASM2_THREADS, smem);
+            }
+            if (per_sm2[jac] < 1) per_sm2[jac] = 1;
+        }
+        const int nchunks = (int)m->h_asm2.size();
+        const int g = std::max(1, std::min(nchunks, ctx->sm_count * per_sm2[jac]));
+        if (jac)
+            twophase_assemble_tma_kernel<true><<<g, JB_ASM2_THREADS, smem, ctx->stream>>>(
+                nchunks, m->d_asm2.p, make_params(m), t->mesh->d_hf_pos.p, t->mesh->d_hf_other.p, m->d_hf_lp.p, m->d_hf_T.p, m->d_hf_sgdz.p,
+                t->csr->d_diag.p, m->d_rec.p, m->d_pv.p, d_M0, src, 1.0 / dt, t->csr->d_val.p, d_r);
+        else
+            twophase_assemble_tma_kernel<false><<<g, JB_ASM2_THREADS, smem, ctx->stream>>>(
+                nchunks, m->d_asm2.p, make_params(m), t->mesh->d_hf_pos.p, t->mesh->d_hf_other.p, m->d_hf_lp.p, m->d_hf_T.p, m->d_hf_sgdz.p,
+                t->csr->d_diag.p, m->d_rec.p, m->d_pv.p, d_M0, src, 1.0 / dt, t->csr->d_val.p, d_r);
+        JB_CHECK_LAUNCH(ctx);
+        return JB_OK;
+    }
+    if (!m->h_chunks.empty() && asm_variant() != 2) {
         // chunks were cut over all local cells; a distributed run assembles the owned prefix only
         int nchunks = (int)m->h_chunks.size() - 1;
         if (m->n_assemble >= 0) nchunks = m->n_chunks_owned;
@@ -476,6 +773,7 @@ int32_t jb_twophase_create(jb_tpfa* t, const double* Tf, const double* gdz, cons
               m->d_face_gdz.upload(fG, s) == cudaSuccess && m->d_pv.upload(hpv, s) == cudaSuccess && m->d_pos_lr.upload(plr, s) == cudaSuccess &&
               m->d_pos_rl.upload(prl, s) == cudaSuccess && m->d_rec.alloc((size_t)mesh->nc * 4) == cudaSuccess;
     if (!ok) { delete m; JB_FAIL(ctx, JB_ERR_ALLOC, "jb_twophase_create: device allocation failed"); }
+    { const int rc = build_asm2(m); if (rc != JB_OK) { delete m; return rc; } }
     *out = m;
     return JB_OK;
 }
@@ -504,7 +802,7 @@ int32_t jb_twophase_set_owned(jb_twophase* m, int64_t n_owned) {
         if (fits) m->h_chunks.push_back((int32_t)mesh->nc); else m->h_chunks.clear();
         if (!m->h_chunks.empty() && m->d_chunks.upload(m->h_chunks, mesh->ctx->stream) != cudaSuccess) return JB_ERR_ALLOC;
     }
-    return JB_OK;
+    return build_asm2(m);
 }
 
 int32_t jb_twophase_set_sources(jb_twophase* m, int64_t nsrc, const int64_t* cells, const double* vals) {
@@ -512,7 +810,7 @@ int32_t jb_twophase_set_sources(jb_twophase* m, int64_t nsrc, const int64_t* cel
     jb_ctx* ctx = m->t->mesh->ctx;
     const i64 nc = m->t->mesh->nc;
     m->nsrc = nsrc;
-    if (nsrc == 0) return JB_OK;
+    if (nsrc == 0) { m->h_src_cells.clear(); return build_asm2(m); }
     std::vector<int32_t> hc(nsrc);
     for (i64 k = 0; k < nsrc; k++) {
         if (cells[k] < 1 || cells[k] > nc) JB_FAIL(ctx, JB_ERR_ARG, "jb_twophase_set_sources: cell out of range");
@@ -526,7 +824,8 @@ int32_t jb_twophase_set_sources(jb_twophase* m, int64_t nsrc, const int64_t* cel
     scatter_sources_kernel<<<1, 32, 0, ctx->stream>>>(nsrc, m->d_src_cells.p, m->d_src_vals.p, m->d_src.p);
     JB_CHECK_LAUNCH(ctx);
     JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return JB_OK;
+    m->h_src_cells = hc;
+    return build_asm2(m);
 }
 
 int32_t jb_twophase_update_state(jb_twophase* m, const double* d_p, const double* d_s) {

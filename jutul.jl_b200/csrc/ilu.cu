@@ -364,6 +364,7 @@ int32_t jb_ilu0_create(jb_csr* A, const int64_t* partition, jb_ilu** out) {
     int rc = jb_ilu_symbolic(F, partition);
     if (rc == JB_OK) rc = jb_ilu_upload(F);
     if (rc != JB_OK) { delete F; JB_FAIL(A->ctx, rc, "jb_ilu0_create: symbolic phase failed (missing diagonal, bad partition or allocation)"); }
+    A->n_ident_chunks = -1;   // identity-chunk flags of the Krylov driver are rebuilt for the new factor
     *out = F;
     return JB_OK;
 }

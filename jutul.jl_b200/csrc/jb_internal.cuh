@@ -91,7 +91,8 @@ struct DBuf {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
-        return cudaMalloc((void**)&p, count * sizeof(T));
+        // 16 B of slack: bulk (TMA) copies read the 16-byte window enclosing an element range (jb_tma.cuh)
+        return cudaMalloc((void**)&p, count * sizeof(T) + 16);
     }
     cudaError_t upload(const std::vector<T>& h, cudaStream_t s) {
         cudaError_t e = alloc(h.size());
@@ -126,6 +127,13 @@ struct jb_csr {
     int n_chunks_int = 0, n_chunks_bnd = 0;
     int split_phase = 0;
     bool has_split = false;
+    // "identity chunks" of the right-preconditioned operator A N^{-1} for a two-colour ILU(0) (krylov.cu): flag per stream chunk,
+    // and the vector w the flagged rows copy (set around a launch by the Krylov driver; nullptr = ordinary product)
+    DBuf<unsigned char> d_ident;
+    int n_ident_chunks = -1;          // -1 = not analysed yet
+    i64 n_ident_rows = 0, n_ident_blocks = 0;
+    const void* ident_for = nullptr;  // the jb_ilu the flags were built for
+    const double* ident_src = nullptr;
 };
 int jb_csr_split_owned(jb_csr* A, i64 n_owned);
 int jb_dist_halo_push_launch(jb_dist* D, double* d_vec, int bs);   // peer-memory path only
@@ -146,6 +154,9 @@ struct jb_perm {
     DBuf<int32_t> d_perm;   // device label (0-based) of caller cell i
 };
 
+// chunk table entry of the TMA-staged assembly kernel (32 B, read as two int4)
+struct Asm2Chunk { int32_t c0, nr, hf0, cnt, row0, flags, pad0, pad1; };
+
 struct jb_twophase {
     jb_tpfa* t;
     jb_perm* perm = nullptr;          // optional caller <-> device renumbering for the host-buffer entry points
@@ -164,6 +175,13 @@ struct jb_twophase {
     std::vector<int32_t> h_chunks;    // cell chunks of the stream assembly kernel
     DBuf<int32_t> d_chunks;
     int n_chunks_owned = 0;
+    // TMA-staged assembly kernel: chunk table (processing order), 16-bit Jacobian slot of each half-face relative to
+    // the first row of its chunk, host copy of the source cells (chunk flags)
+    std::vector<Asm2Chunk> h_asm2;
+    DBuf<Asm2Chunk> d_asm2;
+    DBuf<uint16_t> d_hf_lp;
+    std::vector<int32_t> h_src_cells;
+    bool asm2_ok = false;
     // resident state for the host-facing perform_step
     DBuf<double> d_p, d_s, d_M0, d_r, d_dx;
 };

@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(256) spmv_stream_kernel(int nchunks, const int
                                                           const double* __restrict__ x, double* __restrict__ y, double alpha, double beta,
                                                           const double* __restrict__ u, double* sc, double* partials, unsigned int* counter,
                                                           i64 n_dot, const int32_t* __restrict__ chunk_list, int slot_offset, int total_slots,
-                                                          int finalize) {
+                                                          int finalize, const unsigned char* __restrict__ chunk_ident,
+                                                          const double* __restrict__ ident_src) {
     if (MODE != JB_DOT_NONE) {
         if (sc[KS_DONE] != 0.0) return;
     }
@@ -124,6 +125,23 @@ __global__ void __launch_bounds__(256) spmv_stream_kernel(int nchunks, const int
     for (int k = blockIdx.x; k < nchunks; k += gridDim.x) {
         const int c = chunk_list ? __ldg(chunk_list + k) : k;
         const int t0 = __ldg(chunk_ptr + c), nr = __ldg(chunk_ptr + c + 1) - t0;
+        if (chunk_ident && __ldg(chunk_ident + c)) {
+            // x = N^{-1} w with a two-colour ILU(0): rows of the first colour satisfy (A x)_i = w_i identically
+            // (x_i = D_i^{-1}(w_i - sum_j A_ij x_j), D_i = A_ii), so the product is read off w = ident_src (krylov.cu)
+            if ((int)threadIdx.x < nr) {
+                const size_t row = (size_t)t0 + threadIdx.x;
+#pragma unroll
+                for (int e = 0; e < BS; e++) {
+                    const double v = ident_src[row * BS + e];
+                    y[row * BS + e] = v;
+                    if (MODE != JB_DOT_NONE && (i64)row < n_dot) {
+                        if (MODE == JB_DOT_CV) d0 = fma(__ldg(u + row * BS + e), v, d0);
+                        if (MODE == JB_DOT_TS_TT) { d0 = fma(v, __ldg(u + row * BS + e), d0); d1 = fma(v, v, d1); }
+                    }
+                }
+            }
+            continue;   // CTA-uniform branch, no barrier pending
+        }
         stream_chunk_products<BS, JB_STREAM_U>(t0, nr, rowptr, colidx, val, 0, x, s_rp, s_prod);
         if ((int)threadIdx.x < nr) {
             const size_t row = (size_t)t0 + threadIdx.x;
@@ -181,14 +199,15 @@ static int launch_spmv_stream(jb_csr* A, double alpha, const double* x, double b
         spmv_stream_kernel<BS, MODE><<<grid2, 256, smem, ctx->stream>>>(nwork, A->d_chunks.p, A->d_rowptr.p, A->d_colidx.p, A->d_val.p, x, y, alpha, beta,
                                                                        u, sc, ctx->d_partials, ctx->d_counters, n_dot < 0 ? A->n : n_dot,
                                                                        interior ? A->d_chunks_int.p : A->d_chunks_bnd.p, interior ? 0 : g_int,
-                                                                       interior ? g_int : g_int + grid2, interior ? 0 : 1);
+                                                                       interior ? g_int : g_int + grid2, interior ? 0 : 1,
+                                                                       A->ident_src ? A->d_ident.p : nullptr, A->ident_src);
         JB_CHECK_LAUNCH(ctx);
         return JB_OK;
     }
     const int grid = std::max(1, std::min(nchunks, cap));
     spmv_stream_kernel<BS, MODE><<<grid, 256, smem, ctx->stream>>>(nchunks, A->d_chunks.p, A->d_rowptr.p, A->d_colidx.p, A->d_val.p, x, y, alpha,
                                                                   beta, u, sc, ctx->d_partials, ctx->d_counters, n_dot < 0 ? A->n : n_dot, nullptr, 0,
-                                                                  grid, 1);
+                                                                  grid, 1, A->ident_src ? A->d_ident.p : nullptr, A->ident_src);
     JB_CHECK_LAUNCH(ctx);
     return JB_OK;
 }

@@ -65,7 +65,9 @@ def decompose(N, nc, part, rank, local_order="default"):
         # owned cells that touch a ghost go to the end of their colour: interior rows become contiguous ranges whose SpMV
         # overlaps the halo exchange
         bnd = None
-        if os.environ.get("JB_OVERLAP", "0") == "1":
+        # (the same grouping lets whole chunks of first-colour rows without a ghost coupling qualify as identity rows of
+        # the right-preconditioned operator, csrc/krylov.cu)
+        if os.environ.get("JB_OVERLAP", "0") == "1" or os.environ.get("JB_RB_IDENTITY", "1") != "0":
             bnd = np.zeros(n_owned, dtype=np.int64)
             bnd[g2o[fl[out_r]]] = 1; bnd[g2o[fr[out_l]]] = 1
         perm, ncolors = J.multicolor_ordering(Nin, n_owned, last=bnd)

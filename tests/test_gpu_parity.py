@@ -641,3 +641,50 @@ def test_error_codes_and_bad_arguments(J, ctx):
     disc = J.TwoPointPotentialFlowHardCoded(ctx, np.zeros((0, 2), dtype=np.int64), 1)
     jac = J.tpfa_jacobian(disc, 2)
     assert jac.nnz == 1 and jac.pattern()[1].tolist() == [1]
+
+
+@pytest.mark.parametrize("ordering", [None, "multicolor"])
+def test_assembly_kernel_variants_agree(J, O, ctx, ordering, monkeypatch):
+    """The TMA-staged kernel (default), the register-stream kernel and the lane-per-half-face kernel are three schedules
+    of the same row-owner arithmetic: same summation order, entries equal to rounding of the shared sub-expressions;
+    each is bitwise repeatable. 23x19x17 cells = 117 chunks, so every persistent CTA walks both pipeline stages."""
+    w = J.workloads.unstructured_hex(23, 19, 17)
+    out = {}
+    for v in ("0", "1", "2"):
+        monkeypatch.setenv("JB_ASM_VARIANT", v)
+        sim = J.TwoPhaseSimulator(ctx, w["N"], w["nc"], w["Tf"], w["gdz"], w["pv"], w["params"], ordering=ordering)
+        sim.set_forces(w["src_cells"], w["src_vals"])
+        sim.set_state(w["p0"], w["sw0"])
+        rng = np.random.default_rng(3)
+        sim.p.set(sim.p.get() * (1 + 1e-3 * rng.standard_normal(w["nc"])))
+        sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r)
+        a, b = sim.jac.nonzeros(), sim.r.get()
+        sim.jac.set_nonzeros(np.full_like(a, np.nan)); sim.r.set(np.full_like(b, np.nan))      # every entry must be rewritten
+        sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r)
+        assert np.array_equal(a, sim.jac.nonzeros()) and np.array_equal(b, sim.r.get())
+        sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r, variant="residual")
+        assert np.allclose(sim.r.get(), b, rtol=1e-12, atol=1e-13 * np.abs(b).max())
+        out[v] = (a, b)
+    for v in ("1", "2"):
+        assert np.abs(out[v][0] - out["0"][0]).max() <= 1e-12 * np.abs(out["0"][0]).max()
+        assert np.abs(out[v][1] - out["0"][1]).max() <= 1e-12 * np.abs(out["0"][1]).max()
+
+
+def test_operator_identity_rows(J, O, ctx, monkeypatch):
+    """Two-colour ILU(0), right preconditioning: the first-colour rows of A*N^-1*w are read off w. Same operator, so the
+    solve with the shortcut switched off (JB_RB_IDENTITY=0) takes the same iterations and gives the same increment."""
+    w = J.workloads.unstructured_hex(24, 20, 18)
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("JB_RB_IDENTITY", flag)
+        sim = J.TwoPhaseSimulator(ctx, w["N"], w["nc"], w["Tf"], w["gdz"], w["pv"], w["params"], ordering="multicolor", rtol=1e-8,
+                                  max_linear_iterations=300)
+        sim.set_forces(w["src_cells"], w["src_vals"])
+        sim.set_state(w["p0"], w["sw0"])
+        conv, err, rep = sim.perform_step(w["dt"])
+        chunks, rows, blocks = sim.krylov.identity_info()
+        res[flag] = (rep["linear_iterations"], rep["linear_residuals"], sim.dx.get(), rows)
+    assert res["0"][3] == 0 and res["1"][3] > 0.3 * w["nc"]
+    assert abs(res["1"][0] - res["0"][0]) <= max(2, res["0"][0] // 10)
+    assert np.allclose(res["1"][1][:6], res["0"][1][:6], rtol=1e-6)
+    assert np.linalg.norm(res["1"][2] - res["0"][2]) <= 1e-6 * np.linalg.norm(res["0"][2])
