@@ -309,22 +309,22 @@ __device__ __forceinline__ void ld_rec256(const double* __restrict__ rec, int32_
 //   F, dFdp, dFds : flux out of self and its partials w.r.t. (p, Sw) of self  (residual + diagonal block of row self)
 //   Bp, Bs        : -d F_{other->self} / d (p, Sw) of other                      (the entry J[self, other])
 // q_{other->self} = -q exactly (same rho_avg, negated terms), so one theta / q / upwind decision serves both.
-__device__ __forceinline__ void flux_pair(const TPParams& P, int a, double ps, double Ss, double rs, double po, double So, double ro,
+// ca = compressibility, imu = 1/viscosity of the phase, dS = dS_a/dSw (+1 water, -1 oil).
+__device__ __forceinline__ void flux_pair(double ca, double imu, double dS, double ps, double Ss, double rs, double po, double So, double ro,
                                           double T, double sg, double& F, double& dFdp, double& dFds, double& Bp, double& Bs) {
-    const double dS = a ? -1.0 : 1.0;
-    const double mob_s = (rs * (Ss * Ss)) * P.inv_mu[a];
-    const double mob_o = (ro * (So * So)) * P.inv_mu[a];
+    const double mob_s = (rs * (Ss * Ss)) * imu;
+    const double mob_o = (ro * (So * So)) * imu;
     const double rho_avg = 0.5 * (rs + ro);
     const double theta = ps - po + sg * rho_avg;
     const double q = T * theta;
-    const double dq_s = T * (1.0 + sg * (0.5 * (P.c[a] * rs)));
-    const double dq_o = T * (1.0 + (-sg) * (0.5 * (P.c[a] * ro)));
+    const double dq_s = T * (1.0 + sg * (0.5 * (ca * rs)));
+    const double dq_o = T * (1.0 + (-sg) * (0.5 * (ca * ro)));
     const bool ups = q > 0, upo = q < 0;
     const double mF = ups ? mob_s : mob_o;   // upstream mobility seen from self (q == 0 / NaN: other, as upw_flux)
     const double mN = upo ? mob_o : mob_s;   // upstream mobility seen from the neighbour
     const double u_rho = ups ? rs : ro, u_S = ups ? Ss : So;
-    const double dm_dp = P.c[a] * mF;
-    const double dm_ds = (u_rho * (2.0 * u_S * dS)) * P.inv_mu[a];
+    const double dm_dp = ca * mF;
+    const double dm_ds = (u_rho * (2.0 * u_S * dS)) * imu;
     F = mF * q;
     dFdp = mF * dq_s;
     dFds = 0.0;
@@ -429,7 +429,8 @@ __global__ void __launch_bounds__(JB_ASM2_THREADS, 4) twophase_assemble_tma_kern
                     for (int a = 0; a < 2; a++) {
                         const double Ss = a ? 1.0 - sa.y : sa.y, So = a ? 1.0 - ro[u][1] : ro[u][1];
                         const double rs = a ? sb.y : sb.x, rn = a ? ro[u][3] : ro[u][2];
-                        flux_pair(P, a, sa.x, Ss, rs, ro[u][0], So, rn, Tv[u], sgv[u], part[a], part[2 + a], part[4 + a], blk[a], blk[2 + a]);
+                        flux_pair(P.c[a], P.inv_mu[a], a ? -1.0 : 1.0, sa.x, Ss, rs, ro[u][0], So, rn, Tv[u], sgv[u], part[a], part[2 + a], part[4 + a],
+                                  blk[a], blk[2 + a]);
                     }
                     if (JAC) {
                         double2* dst = reinterpret_cast<double2*>(nz + ((size_t)row0 + S.lp[l2 + e]) * 4);
@@ -473,6 +474,142 @@ __global__ void __launch_bounds__(JB_ASM2_THREADS, 4) twophase_assemble_tma_kern
         if (tid == 0) {
             const int k2 = k + 2 * (int)gridDim.x;
             if (k2 < nchunks) issue(k2, s);
+        }
+    }
+}
+
+// ---- TMA-staged, lane-pair-per-cell form (default) --------------------------------------------------------------
+// Same staging as above, but no shared-memory partials and no CTA barrier in steady state: lane pair (2j, 2j+1) of a warp
+// owns chunk cell j — lane a evaluates equation (phase) a of every half-face of the cell in conn_pos order and keeps
+// r_a, dr_a/dp, dr_a/dSw in registers, so the sums are formed exactly in the order of fill_conservation_eq!
+// (accumulation term first, then the half-faces, src/conservation/conservation.jl:373-430). The pair writes the 2x2
+// off-diagonal block of each half-face with two 16-byte streaming stores (one value exchanged by shuffle). A warp's 16
+// cells run independently of the other warps; a stage is handed back for the next bulk copy by the LAST warp to finish
+// with it (shared-memory counter), so nothing ever waits on a __syncthreads and the phases of different warps overlap.
+// NG = neighbour gathers in flight per lane (the records of NG half-faces are requested before the first flux is
+// evaluated).
+template <bool JAC, int NG, int MINB>
+__global__ void __launch_bounds__(JB_ASM2_THREADS, MINB) twophase_assemble_pair_kernel(
+    int nchunks, const Asm2Chunk* __restrict__ table, TPParams P, const int32_t* __restrict__ hf_pos, const int32_t* __restrict__ hf_other,
+    const uint16_t* __restrict__ hf_lp, const double* __restrict__ hf_T, const double* __restrict__ hf_sgdz, const int32_t* __restrict__ diag_pos,
+    const double* __restrict__ rec, const double* __restrict__ pv, const double* __restrict__ M0, const double* __restrict__ src, double inv_dt,
+    double* __restrict__ nz, double* __restrict__ r) {
+    extern __shared__ __align__(128) unsigned char asm2_smem[];
+    Asm2Stage* stage = reinterpret_cast<Asm2Stage*>(asm2_smem);
+    Asm2Chunk* s_meta = reinterpret_cast<Asm2Chunk*>(asm2_smem + 2 * sizeof(Asm2Stage));
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_meta + 2);
+    int* s_cnt = reinterpret_cast<int*>(s_bar + 2);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARPS = JB_ASM2_THREADS / 32;
+    constexpr int CPW = JB_ASM2_CELLS / NWARPS;   // cells per warp
+    static_assert(CPW * 2 == 32, "one lane pair per cell");
+
+    auto issue = [&](int k, int s) {   // one lane
+        const int4* tp = reinterpret_cast<const int4*>(table + k);
+        const int4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+        Asm2Chunk ci;
+        ci.c0 = t0.x; ci.nr = t0.y; ci.hf0 = t0.z; ci.cnt = t0.w; ci.row0 = t1.x; ci.flags = t1.y; ci.pad0 = 0; ci.pad1 = 0;
+        s_meta[s] = ci;
+        Asm2Stage& S = stage[s];
+        const JbSpan<double> sT(hf_T, ci.hf0, ci.cnt), sG(hf_sgdz, ci.hf0, ci.cnt), sPv(pv, ci.c0, ci.nr);
+        const JbSpan<int32_t> sO(hf_other, ci.hf0, ci.cnt), sHp(hf_pos, ci.c0, ci.nr + 1), sD(diag_pos, ci.c0, ci.nr);
+        const JbSpan<uint16_t> sL(hf_lp, ci.hf0, ci.cnt);
+        const uint32_t bRec = (uint32_t)ci.nr * 32u, bM0 = (uint32_t)ci.nr * 16u;
+        uint32_t total = sT.bytes + sG.bytes + sPv.bytes + sO.bytes + sHp.bytes + bRec + bM0;
+        if (JAC) total += sD.bytes + sL.bytes;
+        jb_mbar_expect_tx(&s_bar[s], total);
+        const uint64_t pol = jb_policy_evict_first();
+        if (sO.bytes) jb_bulk_g2s_hint(S.other, sO.src, sO.bytes, &s_bar[s], pol);
+        if (sHp.bytes) jb_bulk_g2s_hint(S.hfpos, sHp.src, sHp.bytes, &s_bar[s], pol);
+        if (bRec) jb_bulk_g2s(S.rec, rec + 4 * (size_t)ci.c0, bRec, &s_bar[s]);
+        if (sT.bytes) jb_bulk_g2s_hint(S.T, sT.src, sT.bytes, &s_bar[s], pol);
+        if (sG.bytes) jb_bulk_g2s_hint(S.sg, sG.src, sG.bytes, &s_bar[s], pol);
+        if (JAC && sL.bytes) jb_bulk_g2s_hint(S.lp, sL.src, sL.bytes, &s_bar[s], pol);
+        if (JAC && sD.bytes) jb_bulk_g2s_hint(S.diag, sD.src, sD.bytes, &s_bar[s], pol);
+        if (sPv.bytes) jb_bulk_g2s_hint(S.pv, sPv.src, sPv.bytes, &s_bar[s], pol);
+        if (bM0) jb_bulk_g2s_hint(S.M0, M0 + 2 * (size_t)ci.c0, bM0, &s_bar[s], pol);
+    };
+
+    if (tid == 0) {
+        jb_mbar_init(&s_bar[0], 1);
+        jb_mbar_init(&s_bar[1], 1);
+        s_cnt[0] = 0; s_cnt[1] = 0;
+        jb_mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if ((int)blockIdx.x < nchunks) issue(blockIdx.x, 0);
+        if ((int)(blockIdx.x + gridDim.x) < nchunks) issue(blockIdx.x + gridDim.x, 1);
+    }
+    __syncthreads();
+
+    const int jl = lane >> 1, a = lane & 1;
+    const unsigned pairmask = 3u << (lane & ~1);
+    const double dS = a ? -1.0 : 1.0;
+    const double ca = a ? P.c[1] : P.c[0];
+    const double imu = a ? P.inv_mu[1] : P.inv_mu[0];
+    int it = 0;
+    for (int k = blockIdx.x; k < nchunks; k += gridDim.x, it++) {
+        const int s = it & 1;
+        jb_mbar_wait(&s_bar[s], (uint32_t)(it >> 1) & 1u);
+        const Asm2Stage& S = stage[s];
+        const int c0 = s_meta[s].c0, nr = s_meta[s].nr, hf0 = s_meta[s].hf0, row0 = s_meta[s].row0, flags = s_meta[s].flags;
+        const int l8 = jb_span_lead<double>((size_t)hf0), l4 = jb_span_lead<int32_t>((size_t)hf0), l2 = jb_span_lead<uint16_t>((size_t)hf0);
+        const int lc4 = jb_span_lead<int32_t>((size_t)c0), lc8 = jb_span_lead<double>((size_t)c0);
+        const int j = warp * CPW + jl;
+        if (j < nr) {
+            const size_t c = (size_t)c0 + j;
+            const int e0 = S.hfpos[lc4 + j] - hf0, e1 = S.hfpos[lc4 + j + 1] - hf0;
+            const double2 sa = *reinterpret_cast<const double2*>(S.rec + 4 * j);
+            const double ps = sa.x;
+            const double Ss = a ? 1.0 - sa.y : sa.y;
+            const double rs = S.rec[4 * j + 2 + a];
+            const double pvc = S.pv[lc8 + j];
+            // accumulation term (M - M0)/dt with its partials, sources on the diagonal entries (apply_forces!)
+            double ar = (pvc * (rs * Ss) - S.M0[2 * j + a]) * inv_dt;
+            if (flags & 1) ar += __ldg(src + 2 * c + a);
+            double adp = (pvc * (ca * rs * Ss)) * inv_dt;
+            double ads = (pvc * (rs * dS)) * inv_dt;
+            for (int eb = e0; eb < e1; eb += NG) {
+                double ro[NG][4];
+#pragma unroll
+                for (int u = 0; u < NG; u++)
+                    if (eb + u < e1) ld_rec256(rec, S.other[l4 + eb + u], ro[u]);
+#pragma unroll
+                for (int u = 0; u < NG; u++) {
+                    const int e = eb + u;
+                    if (e < e1) {
+                        const double So = a ? 1.0 - ro[u][1] : ro[u][1];
+                        const double rn = a ? ro[u][3] : ro[u][2];
+                        double F, dFdp, dFds, Bp, Bs;
+                        flux_pair(ca, imu, dS, ps, Ss, rs, ro[u][0], So, rn, S.T[l8 + e], S.sg[l8 + e], F, dFdp, dFds, Bp, Bs);
+                        ar += F;
+                        if (JAC) {
+                            adp += dFdp; ads += dFds;
+                            // block (column-major): [Bp_w, Bp_o, Bs_w, Bs_o]; lane 0 stores the first pair, lane 1 the second
+                            const double got = __shfl_xor_sync(pairmask, a ? Bp : Bs, 1);
+                            double2* dst = reinterpret_cast<double2*>(nz + ((size_t)row0 + S.lp[l2 + e]) * 4) + a;
+                            __stcs(dst, a ? make_double2(got, Bs) : make_double2(Bp, got));
+                        }
+                    }
+                }
+            }
+            r[2 * c + a] = ar;
+            if (JAC) {
+                double* dst = nz + (size_t)S.diag[lc4 + j] * 4;
+                __stcs(dst + a, adp);
+                __stcs(dst + 2 + a, ads);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            const int old = atomicAdd(&s_cnt[s], 1);
+            if (old == NWARPS - 1) {     // last warp done with stage s: refill it
+                s_cnt[s] = 0;
+                const int k2 = k + 2 * (int)gridDim.x;
+                if (k2 < nchunks) issue(k2, s);
+            }
         }
     }
 }
@@ -598,7 +735,7 @@ static int build_asm2(jb_twophase* m) {
     return JB_OK;
 }
 
-static int asm_variant() {   // JB_ASM_VARIANT: 0/unset = TMA-staged, 1 = stream, 2 = lane-per-half-face (read per call: tests switch it)
+static int asm_variant() {   // JB_ASM_VARIANT: 0/unset = TMA-staged lane pairs, 3 = TMA-staged CTA form, 1 = stream, 2 = lane-per-half-face (read per call)
     const char* e = getenv("JB_ASM_VARIANT");
     return e ? atoi(e) : 0;
 }
@@ -634,6 +771,31 @@ int jb_launch_twophase_assemble(jb_twophase* m, const double* d_M0, double dt, d
     const int grid = (int)std::max<i64>(1, (nc + cells_per_cta - 1) / cells_per_cta);
     const double* src = m->nsrc > 0 ? m->d_src.p : nullptr;
     if (asm_variant() == 0 && m->asm2_ok && ((uintptr_t)d_M0 & 15) == 0) {
+        // lane-pair-per-cell kernel; JB_ASM_NG picks (neighbour gathers in flight per lane, min CTAs per SM) for experiments
+        const char* eng = getenv("JB_ASM_NG");
+        const int ng = eng ? atoi(eng) : 36;
+        const size_t smem = 2 * sizeof(Asm2Stage) + 2 * sizeof(Asm2Chunk) + 2 * sizeof(uint64_t) + 4 * sizeof(int);
+        const int nchunks = (int)m->h_asm2.size();
+        auto go = [&](auto kern) -> int {
+            int per_sm = 0;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, JB_ASM2_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+            const int g = std::max(1, std::min(nchunks, ctx->sm_count * per_sm));
+            kern<<<g, JB_ASM2_THREADS, smem, ctx->stream>>>(nchunks, m->d_asm2.p, make_params(m), t->mesh->d_hf_pos.p, t->mesh->d_hf_other.p,
+                                                            m->d_hf_lp.p, m->d_hf_T.p, m->d_hf_sgdz.p, t->csr->d_diag.p, m->d_rec.p, m->d_pv.p, d_M0, src,
+                                                            1.0 / dt, t->csr->d_val.p, d_r);
+            JB_CHECK_LAUNCH(ctx);
+            return JB_OK;
+        };
+        if (!jac) return go(twophase_assemble_pair_kernel<false, 6, 4>);
+        if (ng == 6) return go(twophase_assemble_pair_kernel<true, 6, 4>);
+        if (ng == 35) return go(twophase_assemble_pair_kernel<true, 3, 5>);
+        if (ng == 4) return go(twophase_assemble_pair_kernel<true, 4, 5>);
+        if (ng == 27) return go(twophase_assemble_pair_kernel<true, 2, 7>);
+        if (ng == 37) return go(twophase_assemble_pair_kernel<true, 3, 7>);
+        return go(twophase_assemble_pair_kernel<true, 3, 6>);   // measured best at 10M cells (879 us; 6/4: 917, 4/5: 887, 3/5: 909)
+    }
+    if (asm_variant() == 3 && m->asm2_ok && ((uintptr_t)d_M0 & 15) == 0) {
         constexpr int LD = JB_ASM2_HF + 1;
         const int np = jac ? 6 : 2;
         const size_t smem = 2 * sizeof(Asm2Stage) + (size_t)(np * LD + (np * LD & 1)) * sizeof(double) + 2 * sizeof(Asm2Chunk) + 2 * sizeof(uint64_t) +

@@ -367,6 +367,21 @@ int jb_ilu_symbolic(jb_ilu* F, const int64_t* partition) {
         F->two_colour = ok;
         if (!ok) F->h_iso.clear();
     }
+    // stream-form refactorisation of the two-colour case: every update must be "D_i -= m_ik U_ki" (at most one per L entry)
+    F->rb_factor = false;
+    F->h_usrc.clear();
+    if (F->two_colour && A->bs <= 2) {
+        bool ok = true;
+        F->h_usrc.assign((size_t)F->nL, -1);
+        for (i64 r = 0; ok && r < n; r++)
+            for (int32_t li = F->h_Lstart[r]; ok && li < F->h_Lend[r]; li++) {
+                const int32_t u0 = F->h_upd_ptr[li], u1 = F->h_upd_ptr[li + 1];
+                if (u1 - u0 > 1 || (u1 - u0 == 1 && F->h_upd_tgt[u0] != (int32_t)(baseD + r))) ok = false;
+                else if (u1 - u0 == 1) F->h_usrc[li] = F->h_upd_src[u0];
+            }
+        F->rb_factor = ok;
+        if (!ok) F->h_usrc.clear();
+    }
     return JB_OK;
 }
 
@@ -387,6 +402,7 @@ int jb_ilu_upload(jb_ilu* F) {
               F->d_Dmap.upload(F->h_Dmap, s) == cudaSuccess && F->d_upd_ptr.upload(F->h_upd_ptr, s) == cudaSuccess &&
               F->d_upd_tgt.upload(F->h_upd_tgt, s) == cudaSuccess && F->d_upd_src.upload(F->h_upd_src, s) == cudaSuccess;
     ok = ok && (F->h_iso.empty() || F->d_iso.upload(F->h_iso, s) == cudaSuccess);
+    ok = ok && (!F->rb_factor || F->h_usrc.empty() || F->d_usrc.upload(F->h_usrc, s) == cudaSuccess);
     ok = ok && F->d_LptrT.upload(F->h_LptrT, s) == cudaSuccess && F->d_UptrT.upload(F->h_UptrT, s) == cudaSuccess &&
          F->d_chunksF.upload(F->h_chunksF, s) == cudaSuccess && F->d_chunksB.upload(F->h_chunksB, s) == cudaSuccess;
     const size_t b2 = (size_t)F->bs * F->bs;

@@ -18,11 +18,12 @@
 template <int BS>
 __global__ void __launch_bounds__(256) ilu_gather_kernel(i64 nL, i64 n, i64 nU, const int32_t* __restrict__ Lmap,
                                                          const int32_t* __restrict__ Dmap, const int32_t* __restrict__ Umap,
-                                                         const double* __restrict__ A, double* __restrict__ fv) {
+                                                         const double* __restrict__ A, double* __restrict__ fv, i64 first_block) {
     // update_values! (src/StaticCSR/ilu0.jl:83-98): refresh L, D, U from the Jacobian through the stored maps.
+    // first_block = nL skips the L part (the two-colour stream factorisation reads L straight from the Jacobian).
     constexpr int B2 = BS * BS;
     const i64 total = (nL + n + nU) * B2;
-    for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+    for (i64 idx = first_block * B2 + (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
         const i64 blk = idx / B2;
         const int q = (int)(idx % B2);
         int32_t src;
@@ -71,6 +72,67 @@ __global__ void __launch_bounds__(128) ilu_factor_level_kernel(int32_t t0, int32
 #pragma unroll
     for (int q = 0; q < B2; q++) { dinv[(size_t)i * B2 + q] = Di[q]; bad |= !isfinite(Di[q]); }
     if (bad) *status = JB_BAD_PIVOT;
+}
+
+// Two-colour numeric factorisation of the second colour in row-chunk stream form (jb_stream.cuh skeleton). Rows of the
+// second colour have L entries only, towards rows k of the first colour whose D_k^{-1} is final, and the only update of
+// the IKJ elimination is D_i -= m_ik U_ki. All threads stream the chunk's L entries: m_ik = A_ik D_k^{-1} is read from
+// the Jacobian through Lmap (no intermediate copy of L), written to the factor, multiplied with U_ki and parked in shared
+// memory; one thread per row then subtracts the products from A_ii in ascending k (the order of ilu0_factor!,
+// src/StaticCSR/ilu0.jl:108-144) and inverts the block.
+template <int BS>
+__global__ void __launch_bounds__(256) ilu_factor_rb_kernel(int c0, int c1, const int32_t* __restrict__ chunk_ptr, const int32_t* __restrict__ ptrT,
+                                                            const int32_t* __restrict__ Lcol, const int32_t* __restrict__ Lmap,
+                                                            const int32_t* __restrict__ usrc, const int32_t* __restrict__ forder,
+                                                            const int32_t* __restrict__ Dmap, i64 nL, const double* __restrict__ A,
+                                                            double* fv, double* dinv, int32_t* status) {
+    constexpr int B2 = BS * BS;
+    __shared__ int32_t s_rp[JB_CHUNK_ROWS + 1];
+    extern __shared__ double s_prod[];   // B2 doubles per L entry of the chunk
+    for (int c = c0 + blockIdx.x; c < c1; c += gridDim.x) {
+        const int t0 = __ldg(chunk_ptr + c), nr = __ldg(chunk_ptr + c + 1) - t0;
+        for (int j = threadIdx.x; j <= nr; j += blockDim.x) s_rp[j] = __ldg(ptrT + t0 + j);
+        __syncthreads();
+        const int base = s_rp[0], cnt = s_rp[nr] - base;
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+            const size_t li = (size_t)base + e;
+            const int32_t k = __ldcs(Lcol + li), src = __ldcs(Lmap + li), us = __ldcs(usrc + li);
+            double Lik[B2], Dk[B2], m[B2], prod[B2];
+#pragma unroll
+            for (int q = 0; q < B2; q++) { Lik[q] = __ldcs(A + (size_t)src * B2 + q); Dk[q] = dinv[(size_t)k * B2 + q]; }
+            if (us >= 0) {
+                double Ukj[B2];
+#pragma unroll
+                for (int q = 0; q < B2; q++) Ukj[q] = fv[(size_t)us * B2 + q];
+                blk_mul<BS>(Lik, Dk, m);
+                blk_mul<BS>(m, Ukj, prod);
+            } else {
+                blk_mul<BS>(Lik, Dk, m);
+#pragma unroll
+                for (int q = 0; q < B2; q++) prod[q] = 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < B2; q++) { __stcs(fv + li * B2 + q, m[q]); s_prod[(size_t)e * B2 + q] = prod[q]; }
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < nr) {
+            const size_t i = (size_t)__ldg(forder + t0 + threadIdx.x);
+            const size_t dsrc = (size_t)__ldg(Dmap + i);
+            double D[B2], Di[B2];
+#pragma unroll
+            for (int q = 0; q < B2; q++) D[q] = __ldg(A + dsrc * B2 + q);
+            for (int e = s_rp[threadIdx.x] - base; e < s_rp[threadIdx.x + 1] - base; e++) {
+#pragma unroll
+                for (int q = 0; q < B2; q++) D[q] -= s_prod[(size_t)e * B2 + q];
+            }
+            blk_inv<BS>(D, Di);
+            bool bad = false;
+#pragma unroll
+            for (int q = 0; q < B2; q++) { fv[((size_t)nL + i) * B2 + q] = D[q]; dinv[i * B2 + q] = Di[q]; bad |= !isfinite(Di[q]); }
+            if (bad) *status = JB_BAD_PIVOT;
+        }
+        __syncthreads();
+    }
 }
 
 // forward sweep: x_i = b_i - sum_j L_ij x_j  (unit diagonal), rows of one level
@@ -292,7 +354,37 @@ static int ilu_factor_t(jb_ilu* F) {
     JB_CUDA(ctx, cudaMemsetAsync(F->d_status.p, 0, sizeof(int32_t), s));
     const i64 total = (F->nL + F->n + F->nU) * BS * BS;
     int grid = (int)std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 16);
-    ilu_gather_kernel<BS><<<std::max(grid, 1), 256, 0, s>>>(F->nL, F->n, F->nU, F->d_Lmap.p, F->d_Dmap.p, F->d_Umap.p, F->csr->d_val.p, F->d_fv.p);
+    if (BS <= 2 && F->rb_factor && F->two_colour && F->stream_ok && !getenv("JB_ILU_FACTOR_GENERIC")) {
+        // two-colour stream factorisation: D and U from the Jacobian, first colour inverted, second colour in one stream pass
+        constexpr int BSS = BS <= 2 ? BS : 1;
+        ilu_gather_kernel<BS><<<std::max(grid, 1), 256, 0, s>>>(F->nL, F->n, F->nU, F->d_Lmap.p, F->d_Dmap.p, F->d_Umap.p, F->csr->d_val.p, F->d_fv.p,
+                                                                F->nL);
+        JB_CHECK_LAUNCH(ctx);
+        {
+            const int32_t t0 = F->h_levF_ptr[0], t1 = F->h_levF_ptr[1];
+            if (t1 > t0) {
+                ilu_factor_level_kernel<BS><<<(t1 - t0 + 127) / 128, 128, 0, s>>>(t0, t1, F->nL, F->d_forder.p, F->d_Lstart.p, F->d_Lend.p, F->d_Lcol.p,
+                                                                                  F->d_upd_ptr.p, F->d_upd_tgt.p, F->d_upd_src.p, F->d_fv.p, F->d_dinv.p,
+                                                                                  F->d_status.p);
+                JB_CHECK_LAUNCH(ctx);
+            }
+        }
+        const int c0 = F->h_levF_chunk[1], c1 = F->h_levF_chunk[2];
+        if (c1 > c0) {
+            const size_t smem = (size_t)JB_CHUNK_CAP * BSS * BSS * sizeof(double);
+            static int per_sm = 0;
+            if (per_sm == 0) {
+                cudaFuncSetAttribute(ilu_factor_rb_kernel<BSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ilu_factor_rb_kernel<BSS>, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+            }
+            ilu_factor_rb_kernel<BSS><<<std::max(1, std::min(c1 - c0, ctx->sm_count * per_sm)), 256, smem, s>>>(
+                c0, c1, F->d_chunksF.p, F->d_LptrT.p, F->d_Lcol.p, F->d_Lmap.p, F->d_usrc.p, F->d_forder.p, F->d_Dmap.p, F->nL, F->csr->d_val.p,
+                F->d_fv.p, F->d_dinv.p, F->d_status.p);
+            JB_CHECK_LAUNCH(ctx);
+        }
+        return JB_OK;
+    }
+    ilu_gather_kernel<BS><<<std::max(grid, 1), 256, 0, s>>>(F->nL, F->n, F->nU, F->d_Lmap.p, F->d_Dmap.p, F->d_Umap.p, F->csr->d_val.p, F->d_fv.p, 0);
     JB_CHECK_LAUNCH(ctx);
     for (int l = 0; l < F->nlevF; l++) {
         const int32_t t0 = F->h_levF_ptr[l], t1 = F->h_levF_ptr[l + 1];

@@ -203,6 +203,11 @@ struct jb_ilu {
     bool two_colour = false;                          // 2 forward / 2 backward levels with complementary row sets: fused sweeps
     std::vector<int32_t> h_iso;                       // rows with neither L nor U entries (two-colour path)
     DBuf<int32_t> d_iso;
+    // two-colour numeric refactorisation in stream form: per L entry the fv index of the one U block that updates the
+    // diagonal of its row (-1: none); valid when every update of the factorisation is of that kind
+    bool rb_factor = false;
+    std::vector<int32_t> h_usrc;
+    DBuf<int32_t> d_usrc;
     DBuf<int32_t> d_LptrT, d_UptrT, d_chunksF, d_chunksB;
     // device
     DBuf<int32_t> d_forder, d_border, d_Lstart, d_Lend, d_Ustart, d_Uend, d_Lcol, d_Ucol, d_Lmap, d_Umap, d_Dmap;

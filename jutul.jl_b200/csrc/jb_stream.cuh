@@ -109,17 +109,16 @@ __device__ __forceinline__ void stream_row_sum(int j, const int32_t* s_rp, const
 // Host: cut rows [r0, r1) (offsets `ptr`, indexed by stored row) into chunks of <= JB_CHUNK_ROWS rows and
 // <= JB_CHUNK_CAP entries; appends chunk start rows to `chunks` (caller appends the final end).
 // Returns false if a single row exceeds the tile.
-// Rows per chunk: 256 for large row sets; smaller for small ones so that a launch still has >= ~32 chunks per resident
-// CTA (the persistent grid walks the chunks with a static stride; with few chunks per CTA the last partial round is a
-// visible tail — 17 % of an ILU sweep over 0.6M rows, the per-GPU size of the 8-GPU run). JB_CHUNK_ROWS overrides.
+// Rows per chunk: JB_CHUNK_ROWS. Smaller chunks for small row sets (to shorten the tail of the persistent grid) were
+// measured and lose: at 1.26M rows, 64..96-row chunks make the ILU sweeps 44 % and the SpMV 22 % slower than 256-row
+// chunks (per-chunk barriers and row-offset loads dominate). The environment variable JB_CHUNK_ROWS (32..256) is kept
+// for experiments.
 inline int32_t jb_pick_chunk_rows(int64_t nrows) {
+    (void)nrows;
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("JB_CHUNK_ROWS"); forced = e ? atoi(e) : 0; }
     if (forced >= 32 && forced <= JB_CHUNK_ROWS) return forced;
-    int64_t r = (nrows / (32 * 600) + 31) / 32 * 32;
-    if (r < 64) r = 64;
-    if (r > JB_CHUNK_ROWS) r = JB_CHUNK_ROWS;
-    return (int32_t)r;
+    return JB_CHUNK_ROWS;
 }
 inline bool jb_cut_chunks(const std::vector<int32_t>& ptr, int32_t r0, int32_t r1, std::vector<int32_t>& chunks) {
     const int32_t max_rows = jb_pick_chunk_rows((int64_t)r1 - r0);

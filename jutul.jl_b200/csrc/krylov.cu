@@ -3,7 +3,7 @@
 // x0 = 0, c = b, right preconditioning by default (src/linsolve/utils.jl:25),
 // left for the distributed path (ext/JutulPartitionedArraysExt/krylov.jl:60).
 //
-// B200 design: the whole iteration lives on the device. The 19 vector streams
+// B200 design: the whole iteration lives on the device. The 17 vector streams
 // of an iteration are fused into three update kernels; the five inner products
 // are fused into the kernels that produce their operands (<c,v> and <t,s>,<t,t>
 // into the SpMV, <c,r>,<r,r> into the residual update) and reduced
@@ -42,27 +42,27 @@ __global__ void __launch_bounds__(256) bicg_init_kernel(i64 m, const double* __r
     });
 }
 
-// s = r - alpha v ; x += alpha y
+// s = r - alpha v        (x += alpha y is deferred to update2: nothing reads x in between and the termination flag can only
+//                         change in update2, so the two axpys on x run back to back in registers — same rounding, one pass)
 __global__ void __launch_bounds__(256) bicg_update1_kernel(i64 m, const double* sc, const double* __restrict__ r, const double* __restrict__ v,
-                                                           const double* __restrict__ y, double* __restrict__ s, double* __restrict__ x) {
+                                                           double* __restrict__ s) {
     if (sc[KS_DONE] != 0.0) return;
     const double alpha = sc[KS_ALPHA];
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x)
         s[i] = fma(-alpha, __ldg(v + i), __ldg(r + i));
-        x[i] = fma(alpha, __ldg(y + i), x[i]);
-    }
 }
 
-// x += omega z ; r = s - omega t ; rho' = <c,r>, |r| ; beta ; termination
+// x += alpha y ; x += omega z ; r = s - omega t ; rho' = <c,r>, |r| ; beta ; termination
 __global__ void __launch_bounds__(256) bicg_update2_kernel(i64 m, double* sc, const double* __restrict__ s, const double* __restrict__ t,
-                                                           const double* __restrict__ z, const double* __restrict__ c, double* __restrict__ x,
+                                                           const double* __restrict__ y, const double* __restrict__ z,
+                                                           const double* __restrict__ c, double* __restrict__ x,
                                                            double* __restrict__ r, double* hist, int hist_cap, double* partials,
                                                            unsigned int* counter) {
     if (sc[KS_DONE] != 0.0) return;
-    const double omega = sc[KS_OMEGA];
+    const double omega = sc[KS_OMEGA], alpha = sc[KS_ALPHA];
     double d[2] = {0.0, 0.0};
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (i64)gridDim.x * blockDim.x) {
-        x[i] = fma(omega, __ldg(z + i), x[i]);
+        x[i] = fma(omega, __ldg(z + i), fma(alpha, __ldg(y + i), x[i]));
         const double ri = fma(-omega, __ldg(t + i), __ldg(s + i));
         r[i] = ri;
         d[0] = fma(__ldg(c + i), ri, d[0]);
@@ -317,7 +317,7 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
         }
         if ((rc = reduce_fin(1)) != JB_OK) return rc;
         JB_VEC_BEGIN
-        bicg_update1_kernel<<<g, 256, 0, st>>>(m, sc, K->r.p, K->v.p, yv, K->s.p, K->x.p);
+        bicg_update1_kernel<<<g, 256, 0, st>>>(m, sc, K->r.p, K->v.p, K->s.p);
         JB_CHECK_LAUNCH(ctx);
         JB_VEC_END
         double* zv = K->s.p;
@@ -348,7 +348,7 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
         }
         if ((rc = reduce_fin(2)) != JB_OK) return rc;
         JB_VEC_BEGIN
-        bicg_update2_kernel<<<g, 256, 0, st>>>(m, sc, K->s.p, K->t.p, zv, d_b, K->x.p, K->r.p, K->d_hist.p, K->hist_cap, ctx->d_partials,
+        bicg_update2_kernel<<<g, 256, 0, st>>>(m, sc, K->s.p, K->t.p, yv, zv, d_b, K->x.p, K->r.p, K->d_hist.p, K->hist_cap, ctx->d_partials,
                                                ctx->d_counters);
         JB_CHECK_LAUNCH(ctx);
         JB_VEC_END

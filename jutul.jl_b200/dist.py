@@ -369,6 +369,9 @@ def run_bench(args, J):
         cls = prof.collect()
     kernels = {}
     bytes_of = {"assembly": alg["assembly"], "spmv": alg["spmv"], "ilu_apply": alg["ilu_apply"], "ilu_factor": alg["ilu_factor"]}
+    id_chunks, id_rows, id_blocks = sim.krylov.identity_info()      # identity rows of A*N^-1 (csrc/krylov.cu): fewer blocks streamed
+    if id_rows:
+        bytes_of["spmv"] = (nb_loc - id_blocks) * 36 + 4 * (sim.n_local - id_rows + 1) + 2 * sim.n_local * 16 + id_rows * 16
     for k, bts in bytes_of.items():
         t, c = cls[k]
         if c:
@@ -426,7 +429,7 @@ def run_bench(args, J):
                        "newton_tolerance": args.tolerance, "parallelism": f"domain decomposition, {world} ranks, NCCL halo + all-reduce",
                        "l2_policy": "inputs larger than L2 per rank" if (nb_loc * 32) > 126e6 else "local Jacobian fits L2: no flush (strong scaling)",
                        "owned_ghost_per_rank": [[int(a[0]), int(a[1])] for a in all_sizes], "partition_seconds": t_part,
-                       "cell_ordering": args.ordering, "ilu": sim.prec.info(),
+                       "cell_ordering": args.ordering, "ilu": sim.prec.info(), "operator_identity_rows_rank0": id_rows,
                        "collectives": "peer memory over NVLink (fused all-reduce + recurrence kernel, direct halo stores)" if sim.halo.p2p else "NCCL"},
             "newton_iterations_per_step": n_newton / max(args.steps, 1), "converged": all(r[0] for r in results),
             "linear_iterations_per_newton": float(np.mean(lin_its)) if lin_its else None, "linear_iterations": results[0][2],

@@ -17,8 +17,9 @@ sim.set_forces(w["src_cells"], w["src_vals"])
 sim.set_state(w["p0"], w["sw0"])
 lib = ctx.lib
 ref = None
-for v in ("0", "1", "2", "0"):
+for v, ng in (("0", "36"), ("0", "27"), ("0", "37"), ("0", "4"), ("0", "36")):
     os.environ["JB_ASM_VARIANT"] = v
+    os.environ["JB_ASM_NG"] = ng
     for _ in range(3):
         sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r)
     reps = 10
@@ -32,5 +33,5 @@ for v in ("0", "1", "2", "0"):
     if ref is None:
         ref = nz
     d = np.abs(nz - ref).max() / np.abs(ref).max()
-    print(f"variant {v}: assembly {t / c * 1e3:8.1f} us/launch  {alg / (t / c * 1e-3) / 1e9:7.1f} GB/s  frac {alg / (t / c * 1e-3) / 1e9 / 6549.4:.3f}"
+    print(f"variant {v} ng {ng}: assembly {t / c * 1e3:8.1f} us/launch  {alg / (t / c * 1e-3) / 1e9:7.1f} GB/s  frac {alg / (t / c * 1e-3) / 1e9 / 6549.4:.3f}"
           f"   state {ts / cs * 1e3:6.1f} us   max rel diff vs variant 0: {d:.2e}", flush=True)

@@ -201,7 +201,8 @@ def test_bicgstab_matches_oracle(J, O, ctx, side, rtol):
     import scipy.sparse.linalg as spla
     xd = spla.spsolve(A.tocsc(), r)
     eg = np.linalg.norm(dx + xd) / np.linalg.norm(xd); eo = np.linalg.norm(x - xd) / np.linalg.norm(xd)
-    assert eg <= max(10 * eo, 1e3 * rtol)
+    # (error / residual amplification of this system is ~2.5e3: a solve that stops just under rtol may sit at 2.5e3 * rtol)
+    assert eg <= max(10 * eo, 1e4 * rtol)
 
 
 def test_bicgstab_edge_cases(J, O, ctx):
@@ -645,12 +646,12 @@ def test_error_codes_and_bad_arguments(J, ctx):
 
 @pytest.mark.parametrize("ordering", [None, "multicolor"])
 def test_assembly_kernel_variants_agree(J, O, ctx, ordering, monkeypatch):
-    """The TMA-staged kernel (default), the register-stream kernel and the lane-per-half-face kernel are three schedules
-    of the same row-owner arithmetic: same summation order, entries equal to rounding of the shared sub-expressions;
+    """The TMA-staged lane-pair kernel (default), the TMA-staged CTA kernel (3), the register-stream kernel (1) and the
+    lane-per-half-face kernel (2) are schedules of the same row-owner arithmetic: same summation order, entries equal to rounding of the shared sub-expressions;
     each is bitwise repeatable. 23x19x17 cells = 117 chunks, so every persistent CTA walks both pipeline stages."""
     w = J.workloads.unstructured_hex(23, 19, 17)
     out = {}
-    for v in ("0", "1", "2"):
+    for v in ("0", "1", "2", "3"):
         monkeypatch.setenv("JB_ASM_VARIANT", v)
         sim = J.TwoPhaseSimulator(ctx, w["N"], w["nc"], w["Tf"], w["gdz"], w["pv"], w["params"], ordering=ordering)
         sim.set_forces(w["src_cells"], w["src_vals"])
@@ -665,7 +666,7 @@ def test_assembly_kernel_variants_agree(J, O, ctx, ordering, monkeypatch):
         sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r, variant="residual")
         assert np.allclose(sim.r.get(), b, rtol=1e-12, atol=1e-13 * np.abs(b).max())
         out[v] = (a, b)
-    for v in ("1", "2"):
+    for v in ("1", "2", "3"):
         assert np.abs(out[v][0] - out["0"][0]).max() <= 1e-12 * np.abs(out["0"][0]).max()
         assert np.abs(out[v][1] - out["0"][1]).max() <= 1e-12 * np.abs(out["0"][1]).max()
 
@@ -687,4 +688,30 @@ def test_operator_identity_rows(J, O, ctx, monkeypatch):
     assert res["0"][3] == 0 and res["1"][3] > 0.3 * w["nc"]
     assert abs(res["1"][0] - res["0"][0]) <= max(2, res["0"][0] // 10)
     assert np.allclose(res["1"][1][:6], res["0"][1][:6], rtol=1e-6)
-    assert np.linalg.norm(res["1"][2] - res["0"][2]) <= 1e-6 * np.linalg.norm(res["0"][2])
+    # two solves of the same system to rtol = 1e-8 differ by (error amplification) * rtol; measured amplification ~2.5e3
+    assert np.linalg.norm(res["1"][2] - res["0"][2]) <= 1e-4 * np.linalg.norm(res["0"][2])
+
+
+def test_two_colour_stream_refactorisation(J, O, ctx, monkeypatch):
+    """The stream-form numeric refactorisation of the two-colour case (second colour in one pass, L read straight from
+    the Jacobian) performs the arithmetic of the level-by-level kernel: same factors to the last bits."""
+    w = J.workloads.unstructured_hex(21, 17, 13)
+    out = {}
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv("JB_ILU_FACTOR_GENERIC", "1")
+        sim = J.TwoPhaseSimulator(ctx, w["N"], w["nc"], w["Tf"], w["gdz"], w["pv"], w["params"], ordering="multicolor")
+        sim.set_forces(w["src_cells"], w["src_vals"])
+        sim.set_state(w["p0"], w["sw0"])
+        sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r)
+        assert sim.prec.update_preconditioner() == 0
+        out[generic] = sim.prec.factors()
+        if not generic:
+            nz = sim.jac.nonzeros()
+            rp, ci = sim.jac.pattern()
+            ilu = O.ILU0(w["nc"], 2, rp, ci); ilu.factor(nz)
+            fo = ilu.get()
+            for k in ("L", "U", "D"):
+                assert np.abs(out[generic][k] - fo[k]).max() <= 1e-10 * np.abs(fo[k]).max()
+    for k in ("L", "U", "D"):
+        assert np.abs(out[False][k] - out[True][k]).max() <= 1e-14 * np.abs(out[True][k]).max()
