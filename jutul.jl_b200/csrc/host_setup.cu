@@ -7,6 +7,7 @@
 
 #include "jb_internal.cuh"
 #include "jb_stream.cuh"
+#include "jb_stream2.cuh"
 
 static std::string g_err;
 void jb_set_global_error(const std::string& s) { g_err = s; }
@@ -79,6 +80,12 @@ static int csr_finish(jb_ctx* ctx, jb_csr* A) {
     if (jb_cut_chunks(A->h_rowptr, 0, (int32_t)A->n, A->h_chunks)) A->h_chunks.push_back((int32_t)A->n);
     else A->h_chunks.clear();
     if (!A->h_chunks.empty() && A->d_chunks.upload(A->h_chunks, s) != cudaSuccess) return JB_ERR_ALLOC;
+    // TMA-staged SpMV (2x2 blocks)
+    A->h_s2.clear(); A->s2_ok = false;
+    if (A->bs == 2 && A->n > 0 && jb_s2_cut(A->h_rowptr, 0, (int32_t)A->n, A->h_s2)) {
+        if (A->d_s2.upload(A->h_s2, s) != cudaSuccess) return JB_ERR_ALLOC;
+        A->s2_ok = true;
+    }
     if (A->d_rowptr.upload(A->h_rowptr, s) != cudaSuccess || A->d_colidx.upload(A->h_colidx, s) != cudaSuccess ||
         A->d_diag.upload(A->h_diag, s) != cudaSuccess || A->d_val.alloc((size_t)A->nnzb * A->bs * A->bs) != cudaSuccess)
         return JB_ERR_ALLOC;
@@ -353,6 +360,19 @@ int jb_ilu_symbolic(jb_ilu* F, const int64_t* partition) {
     };
     cut(F->h_LptrT, F->h_levF_ptr, F->nlevF, F->h_chunksF, F->h_levF_chunk);
     cut(F->h_UptrT, F->h_levB_ptr, F->nlevB, F->h_chunksB, F->h_levB_chunk);
+    // tables of the TMA-staged sweeps (2x2 blocks), cut per level as well
+    F->s2_ok = (A->bs == 2);
+    auto cut2 = [&](const std::vector<int32_t>& ptrT, const std::vector<int32_t>& lev_ptr, int nlev, std::vector<S2Chunk>& tab,
+                    std::vector<int32_t>& lev_tab) {
+        tab.clear(); lev_tab.assign(nlev + 1, 0);
+        for (int l = 0; l < nlev; l++) {
+            lev_tab[l] = (int32_t)tab.size();
+            if (F->s2_ok && !jb_s2_cut(ptrT, lev_ptr[l], lev_ptr[l + 1], tab)) F->s2_ok = false;
+        }
+        lev_tab[nlev] = (int32_t)tab.size();
+    };
+    if (F->s2_ok) cut2(F->h_LptrT, F->h_levF_ptr, F->nlevF, F->h_s2F, F->h_levF_s2);
+    if (F->s2_ok) cut2(F->h_UptrT, F->h_levB_ptr, F->nlevB, F->h_s2B, F->h_levB_s2);
     // two-colour structure: second forward level == rows without U entries, first forward level == second backward level
     // (no row has both L and U entries; rows with neither — e.g. the decoupled ghost rows of a distributed run — are "isolated")
     F->two_colour = false;
@@ -402,6 +422,7 @@ int jb_ilu_upload(jb_ilu* F) {
               F->d_Dmap.upload(F->h_Dmap, s) == cudaSuccess && F->d_upd_ptr.upload(F->h_upd_ptr, s) == cudaSuccess &&
               F->d_upd_tgt.upload(F->h_upd_tgt, s) == cudaSuccess && F->d_upd_src.upload(F->h_upd_src, s) == cudaSuccess;
     ok = ok && (F->h_iso.empty() || F->d_iso.upload(F->h_iso, s) == cudaSuccess);
+    if (F->s2_ok) ok = ok && (F->h_s2F.empty() || F->d_s2F.upload(F->h_s2F, s) == cudaSuccess) && (F->h_s2B.empty() || F->d_s2B.upload(F->h_s2B, s) == cudaSuccess);
     ok = ok && (!F->rb_factor || F->h_usrc.empty() || F->d_usrc.upload(F->h_usrc, s) == cudaSuccess);
     ok = ok && F->d_LptrT.upload(F->h_LptrT, s) == cudaSuccess && F->d_UptrT.upload(F->h_UptrT, s) == cudaSuccess &&
          F->d_chunksF.upload(F->h_chunksF, s) == cudaSuccess && F->d_chunksB.upload(F->h_chunksB, s) == cudaSuccess;

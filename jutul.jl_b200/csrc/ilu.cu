@@ -14,6 +14,7 @@
 #include "jb_internal.cuh"
 #include "jb_krylov_scalars.cuh"
 #include "jb_stream.cuh"
+#include "jb_stream2.cuh"
 
 template <int BS>
 __global__ void __launch_bounds__(256) ilu_gather_kernel(i64 nL, i64 n, i64 nU, const int32_t* __restrict__ Lmap,
@@ -239,6 +240,58 @@ __global__ void __launch_bounds__(256) ilu_sweep_stream_kernel(int c0, int c1, c
     }
 }
 
+// ---- TMA-staged lane-pair form of the sweeps for 2x2 blocks (default when bs = 2): see jb_stream2.cuh ----
+// x_i = [D_i^{-1}] (rhs_i - sum_j M_ij gsrc_j) over the table entries [c0, c1) of one level.
+__global__ void __launch_bounds__(JB_S2_THREADS, 6) ilu_sweep_s2_kernel(int c0, int c1, const S2Chunk* __restrict__ table,
+                                                                        const int32_t* __restrict__ ptrT, const int32_t* __restrict__ col,
+                                                                        const double* __restrict__ fv, size_t val_block_offset,
+                                                                        const int32_t* __restrict__ order, const double* __restrict__ dinv,
+                                                                        const double* rhs, const double* gsrc, int apply_dinv, double* x,
+                                                                        const double* sc) {
+    if (sc && sc[KS_DONE] != 0.0) return;
+    extern __shared__ __align__(128) unsigned char s2_raw[];
+    S2Smem& sm = *reinterpret_cast<S2Smem*>(s2_raw);
+    s2_prologue(sm, table, c0, c1, ptrT, col, fv, val_block_offset, order);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, jl = lane >> 1, e = lane & 1;
+    const unsigned pairmask = 3u << (lane & ~1);
+    int it = 0;
+    for (int k = c0 + blockIdx.x; k < c1; k += gridDim.x, it++) {
+        const int s = it & 1;
+        jb_mbar_wait(&sm.bar[s], (uint32_t)(it >> 1) & 1u);
+        const S2Stage& S = sm.stage[s];
+        const int t0 = sm.meta[s].t0, nr = sm.meta[s].nr, e0 = sm.meta[s].e0;
+        const int j = warp * 16 + jl;
+        if (j < nr) {
+            const int lrp = jb_span_lead<int32_t>((size_t)t0), lcol = jb_span_lead<int32_t>((size_t)e0);
+            const size_t i = (size_t)S.ord[lrp + j];
+            double v = rhs[i * 2 + e];                 // independent of the products: requested first
+            double da = 0.0, db = 0.0;
+            if (apply_dinv) { da = __ldg(dinv + i * 4 + e); db = __ldg(dinv + i * 4 + 2 + e); }
+            v -= s2_row_sum<6>(S, lcol, S.rp[lrp + j] - e0, S.rp[lrp + j + 1] - e0, e, gsrc);
+            if (apply_dinv) {
+                const double other = __shfl_xor_sync(pairmask, v, 1);
+                const double v0 = e ? other : v, v1 = e ? v : other;
+                v = fma(db, v1, da * v0);               // (D^{-1} v)_e, column-major 2x2
+            }
+            x[i * 2 + e] = v;
+        }
+        s2_release(sm, s, table, k, c1, ptrT, col, fv, val_block_offset, order);
+    }
+}
+static bool ilu_s2_enabled() {
+    const char* e = getenv("JB_STREAM_VARIANT");
+    return !(e && e[0] == '1');
+}
+static int ilu_s2_grid(jb_ctx* ctx, int nchunks) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        cudaFuncSetAttribute(ilu_sweep_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S2Smem));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ilu_sweep_s2_kernel, JB_S2_THREADS, sizeof(S2Smem)) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+    }
+    return std::max(1, std::min(nchunks, ctx->sm_count * per_sm));
+}
+
 // Levels whose rows have no off-diagonal entry inside the block (e.g. the first colour of a multicolour ordering) need no
 // gather at all: x_i = b_i (forward) or x_i = D_i^{-1} x_i (backward). One thread per row, full occupancy.
 template <int BS, bool BACKWARD>
@@ -293,6 +346,31 @@ static int ilu_apply_stream_t(jb_ilu* F, const double* b, double* x, const doubl
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ilu_sweep_stream_kernel<BS>, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     }
     const int cap = ctx->sm_count * per_sm;
+    const bool s2 = BS == 2 && F->s2_ok && ilu_s2_enabled();
+    if (F->two_colour && s2) {
+        {
+            const int c0 = F->h_levF_s2[1], c1 = F->h_levF_s2[2];
+            if (c1 > c0) {
+                ilu_sweep_s2_kernel<<<ilu_s2_grid(ctx, c1 - c0), JB_S2_THREADS, sizeof(S2Smem), s>>>(c0, c1, F->d_s2F.p, F->d_LptrT.p, F->d_Lcol.p, F->d_fv.p, 0,
+                                                                                                   F->d_forder.p, F->d_dinv.p, b, b, 1, x, sc);
+                JB_CHECK_LAUNCH(ctx);
+            }
+        }
+        {
+            const int c0 = F->h_levB_s2[1], c1 = F->h_levB_s2[2];
+            if (c1 > c0) {
+                ilu_sweep_s2_kernel<<<ilu_s2_grid(ctx, c1 - c0), JB_S2_THREADS, sizeof(S2Smem), s>>>(c0, c1, F->d_s2B.p, F->d_UptrT.p, F->d_Ucol.p, F->d_fv.p,
+                                                                                                   (size_t)(F->nL + F->n), F->d_border.p, F->d_dinv.p, b, x, 1, x, sc);
+                JB_CHECK_LAUNCH(ctx);
+            }
+        }
+        if (!F->h_iso.empty()) {   // isolated rows: x_i = D_i^{-1} b_i
+            const int32_t ni = (int32_t)F->h_iso.size();
+            ilu_iso_kernel<BS><<<(ni + 255) / 256, 256, 0, s>>>(ni, F->d_iso.p, F->d_dinv.p, b, x, sc);
+            JB_CHECK_LAUNCH(ctx);
+        }
+        return JB_OK;
+    }
     if (F->two_colour) {
         // Two-colour fast path (rows of the second forward level have no U entries, rows of the first have no L entries):
         //   second colour:  x_B = D_B^{-1} (b_B - L_BR b_R)        (its forward and backward steps fused; y_R = b_R is read in place)
@@ -326,6 +404,13 @@ static int ilu_apply_stream_t(jb_ilu* F, const double* b, double* x, const doubl
             JB_CHECK_LAUNCH(ctx);
             continue;
         }
+        if (s2) {
+            const int a0 = F->h_levF_s2[l], a1 = F->h_levF_s2[l + 1];
+            ilu_sweep_s2_kernel<<<ilu_s2_grid(ctx, a1 - a0), JB_S2_THREADS, sizeof(S2Smem), s>>>(a0, a1, F->d_s2F.p, F->d_LptrT.p, F->d_Lcol.p, F->d_fv.p, 0,
+                                                                                               F->d_forder.p, F->d_dinv.p, b, x, 0, x, sc);
+            JB_CHECK_LAUNCH(ctx);
+            continue;
+        }
         ilu_sweep_stream_kernel<BS><<<std::min(c1 - c0, cap), 256, smem, s>>>(c0, c1, F->d_chunksF.p, F->d_LptrT.p, F->d_Lcol.p, F->d_fv.p, 0,
                                                                               F->d_forder.p, F->d_dinv.p, b, x, 0, x, sc);
         JB_CHECK_LAUNCH(ctx);
@@ -336,6 +421,13 @@ static int ilu_apply_stream_t(jb_ilu* F, const double* b, double* x, const doubl
         const int32_t t0 = F->h_levB_ptr[l], t1 = F->h_levB_ptr[l + 1];
         if (F->h_UptrT[t1] == F->h_UptrT[t0]) {
             ilu_light_level_kernel<BS, true><<<(t1 - t0 + 255) / 256, 256, 0, s>>>(t0, t1, F->d_border.p, F->d_dinv.p, b, x, sc);
+            JB_CHECK_LAUNCH(ctx);
+            continue;
+        }
+        if (s2) {
+            const int a0 = F->h_levB_s2[l], a1 = F->h_levB_s2[l + 1];
+            ilu_sweep_s2_kernel<<<ilu_s2_grid(ctx, a1 - a0), JB_S2_THREADS, sizeof(S2Smem), s>>>(a0, a1, F->d_s2B.p, F->d_UptrT.p, F->d_Ucol.p, F->d_fv.p,
+                                                                                               (size_t)(F->nL + F->n), F->d_border.p, F->d_dinv.p, x, x, 1, x, sc);
             JB_CHECK_LAUNCH(ctx);
             continue;
         }

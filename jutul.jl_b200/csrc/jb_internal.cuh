@@ -103,6 +103,10 @@ struct DBuf {
     }
 };
 
+// chunk table entry of the TMA-staged row-stream kernels (jb_stream2.cuh; 32 B, read as two int4):
+// stored rows [t0, t0+nr), blocks [e0, e0+cnt) of the matrix being streamed; flags bit 0 = identity chunk (SpMV)
+struct S2Chunk { int32_t t0, nr, e0, cnt, flags, pad0, pad1, pad2; };
+
 struct jb_mesh {
     jb_ctx* ctx;
     i64 nc, nf, nhf;
@@ -129,6 +133,11 @@ struct jb_csr {
     bool has_split = false;
     // "identity chunks" of the right-preconditioned operator A N^{-1} for a two-colour ILU(0) (krylov.cu): flag per stream chunk,
     // and the vector w the flagged rows copy (set around a launch by the Krylov driver; nullptr = ordinary product)
+    // TMA-staged SpMV (bs = 2): chunk table, and a copy with the identity chunks flagged
+    std::vector<S2Chunk> h_s2;
+    DBuf<S2Chunk> d_s2, d_s2_ident;
+    int n_s2_ident = 0;               // entries of d_s2_ident (identity chunks are merged, so it is shorter than h_s2)
+    bool s2_ok = false;
     DBuf<unsigned char> d_ident;
     int n_ident_chunks = -1;          // -1 = not analysed yet
     i64 n_ident_rows = 0, n_ident_blocks = 0;
@@ -200,6 +209,11 @@ struct jb_ilu {
     std::vector<int32_t> h_chunksF, h_chunksB;        // stream-kernel chunks (stored-row boundaries), never across a level
     std::vector<int32_t> h_levF_chunk, h_levB_chunk;  // first chunk of each level (nlev+1)
     bool stream_ok = false;
+    // TMA-staged sweeps (bs = 2): chunk tables of the L / U storage, first table entry of each level
+    std::vector<S2Chunk> h_s2F, h_s2B;
+    std::vector<int32_t> h_levF_s2, h_levB_s2;
+    DBuf<S2Chunk> d_s2F, d_s2B;
+    bool s2_ok = false;
     bool two_colour = false;                          // 2 forward / 2 backward levels with complementary row sets: fused sweeps
     std::vector<int32_t> h_iso;                       // rows with neither L nor U entries (two-colour path)
     DBuf<int32_t> d_iso;

@@ -23,6 +23,7 @@
 #include "jb_internal.cuh"
 #include "jb_krylov_scalars.cuh"
 #include "jb_reduce.cuh"
+#include "jb_stream2.cuh"
 
 int jb_launch_ilu_apply_sc(jb_ilu* F, const double* d_b, double* d_x, const double* d_sc);
 
@@ -198,15 +199,49 @@ static int krylov_prepare_ident(jb_krylov* K, i64 n_own) {
         flag[c] = ok ? 1 : 0;
         cnt += ok;
     }
-    if (cnt == 0) return JB_OK;
-    if (A->d_ident.upload(flag, A->ctx->stream) != cudaSuccess) return JB_ERR_ALLOC;
-    A->n_ident_chunks = cnt;
-    A->n_ident_rows = A->n_ident_blocks = 0;
-    for (int c = 0; c < nch; c++)
-        if (flag[c]) {
-            A->n_ident_rows += A->h_chunks[c + 1] - A->h_chunks[c];
-            A->n_ident_blocks += A->h_rowptr[A->h_chunks[c + 1]] - A->h_rowptr[A->h_chunks[c]];
+    // the same analysis on the chunk table of the TMA-staged SpMV (64-row chunks: more of them qualify)
+    int cnt2 = 0;
+    std::vector<S2Chunk> tab2;
+    if (A->s2_ok) {
+        // qualifying chunks that follow each other are merged into identity entries of up to JB_S2_IDENT_ROWS rows: they are
+        // streamed as plain vectors, and an entry should carry about as many bytes as a matrix chunk
+        for (const S2Chunk& ch0 : A->h_s2) {
+            S2Chunk ch = ch0;
+            bool ok = true;
+            for (int32_t i = ch.t0; ok && i < ch.t0 + ch.nr; i++) {
+                const int32_t rowlen = A->h_rowptr[i + 1] - A->h_rowptr[i];
+                ok = i < n_own && F->h_Lend[i] == F->h_Lstart[i] && F->h_Uend[i] - F->h_Ustart[i] == rowlen - 1;
+            }
+            if (ok) {
+                cnt2++;
+                ch.flags |= 1;
+                if (!tab2.empty() && (tab2.back().flags & 1) && tab2.back().t0 + tab2.back().nr == ch.t0 &&
+                    tab2.back().nr + ch.nr <= JB_S2_IDENT_ROWS) {
+                    tab2.back().nr += ch.nr; tab2.back().cnt += ch.cnt;
+                    continue;
+                }
+            }
+            tab2.push_back(ch);
         }
+    }
+    if (cnt == 0 && cnt2 == 0) return JB_OK;
+    if (A->d_ident.upload(flag, A->ctx->stream) != cudaSuccess) return JB_ERR_ALLOC;
+    if (cnt2 > 0 && A->d_s2_ident.upload(tab2, A->ctx->stream) != cudaSuccess) return JB_ERR_ALLOC;
+    A->n_s2_ident = cnt2 > 0 ? (int)tab2.size() : 0;
+    const char* sv = getenv("JB_STREAM_VARIANT");
+    const bool use2 = cnt2 > 0 && !(sv && sv[0] == '1');      // the s2 kernel is the one that runs when its table exists (spmv.cu)
+    A->n_ident_chunks = use2 ? cnt2 : cnt;
+    A->n_ident_rows = A->n_ident_blocks = 0;
+    if (use2) {
+        for (const S2Chunk& ch : tab2)
+            if (ch.flags & 1) { A->n_ident_rows += ch.nr; A->n_ident_blocks += ch.cnt; }
+    } else {
+        for (int c = 0; c < nch; c++)
+            if (flag[c]) {
+                A->n_ident_rows += A->h_chunks[c + 1] - A->h_chunks[c];
+                A->n_ident_blocks += A->h_rowptr[A->h_chunks[c + 1]] - A->h_rowptr[A->h_chunks[c]];
+            }
+    }
     return JB_OK;
 }
 extern "C" int32_t jb_krylov_info(jb_krylov* K, int64_t* info) {

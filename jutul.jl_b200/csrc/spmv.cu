@@ -12,6 +12,7 @@
 #include "jb_krylov_scalars.cuh"
 #include "jb_reduce.cuh"
 #include "jb_stream.cuh"
+#include "jb_stream2.cuh"
 
 template <int BS> struct BlockLoad;
 template <> struct BlockLoad<1> {
@@ -175,6 +176,111 @@ __global__ void __launch_bounds__(256) spmv_stream_kernel(int nchunks, const int
     }
 }
 
+// ---- TMA-staged lane-pair form for 2x2 blocks (default when bs = 2): see jb_stream2.cuh -----------------------------
+template <int MODE>
+__global__ void __launch_bounds__(JB_S2_THREADS, 6) spmv_s2_kernel(int nchunks, const S2Chunk* __restrict__ table, const int32_t* __restrict__ rowptr,
+                                                                   const int32_t* __restrict__ colidx, const double* __restrict__ val,
+                                                                   const double* __restrict__ x, double* __restrict__ y, double alpha, double beta,
+                                                                   const double* __restrict__ u, double* sc, double* partials, unsigned int* counter,
+                                                                   i64 n_dot, const double* __restrict__ ident_src) {
+    if (MODE != JB_DOT_NONE) {
+        if (sc[KS_DONE] != 0.0) return;
+    }
+    extern __shared__ __align__(128) unsigned char s2_raw[];
+    S2Smem& sm = *reinterpret_cast<S2Smem*>(s2_raw);
+    s2_prologue(sm, table, 0, nchunks, rowptr, colidx, val, 0, nullptr);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, jl = lane >> 1, e = lane & 1;
+    double d0 = 0.0, d1 = 0.0;
+    int it = 0;
+    for (int k = blockIdx.x; k < nchunks; k += gridDim.x, it++) {
+        const int s = it & 1;
+        jb_mbar_wait(&sm.bar[s], (uint32_t)(it >> 1) & 1u);
+        const S2Stage& S = sm.stage[s];
+        const int t0 = sm.meta[s].t0, nr = sm.meta[s].nr, e0 = sm.meta[s].e0, flags = sm.meta[s].flags;
+        if (flags & 1) {
+            // x = N^{-1} w with a two-colour ILU(0): (A x)_i = w_i on first-colour rows (krylov.cu) — read it off w.
+            // An identity entry covers up to JB_S2_IDENT_ROWS consecutive rows; the CTA streams them as plain vectors.
+            const size_t base = (size_t)t0 * 2;
+            const int nd = nr * 2;
+            for (int q0 = threadIdx.x; q0 < nd; q0 += JB_S2_THREADS * 4) {
+                double v[4];
+#pragma unroll
+                for (int m = 0; m < 4; m++) { const int q = q0 + m * JB_S2_THREADS; if (q < nd) v[m] = ident_src[base + q]; }
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const int q = q0 + m * JB_S2_THREADS;
+                    if (q < nd) {
+                        y[base + q] = v[m];
+                        if (MODE != JB_DOT_NONE && (i64)((base + q) >> 1) < n_dot) {
+                            if (MODE == JB_DOT_CV) d0 = fma(__ldg(u + base + q), v[m], d0);
+                            if (MODE == JB_DOT_TS_TT) { d0 = fma(v[m], __ldg(u + base + q), d0); d1 = fma(v[m], v[m], d1); }
+                        }
+                    }
+                }
+            }
+            s2_release(sm, s, table, k, nchunks, rowptr, colidx, val, 0, nullptr);
+            continue;
+        }
+        const int j = warp * 16 + jl;
+        if (j < nr) {
+            const size_t row = (size_t)t0 + j;
+            double v;
+            {
+                const int lrp = jb_span_lead<int32_t>((size_t)t0), lcol = jb_span_lead<int32_t>((size_t)e0);
+                const double acc = s2_row_sum<8>(S, lcol, S.rp[lrp + j] - e0, S.rp[lrp + j + 1] - e0, e, x);
+                v = alpha * acc;
+                if (beta != 0.0) v += beta * y[row * 2 + e];
+            }
+            y[row * 2 + e] = v;
+            if (MODE != JB_DOT_NONE && (i64)row < n_dot) {     // inner products run over owned rows only
+                if (MODE == JB_DOT_CV) d0 = fma(__ldg(u + row * 2 + e), v, d0);
+                if (MODE == JB_DOT_TS_TT) { d0 = fma(v, __ldg(u + row * 2 + e), d0); d1 = fma(v, v, d1); }
+            }
+        }
+        s2_release(sm, s, table, k, nchunks, rowptr, colidx, val, 0, nullptr);
+    }
+    if (MODE == JB_DOT_CV) {
+        double r[1] = {d0};
+        grid_reduce_ex<1, OpSum>(r, partials, counter, 0, gridDim.x, true, [=](double(&t)[1]) {
+            sc[KS_SUM0] = t[0];
+            if (sc[KS_DIST] == 0.0) ks_fin_alpha(sc);
+        });
+    } else if (MODE == JB_DOT_TS_TT) {
+        double r[2] = {d0, d1};
+        grid_reduce_ex<2, OpSum>(r, partials, counter, 0, gridDim.x, true, [=](double(&t)[2]) {
+            sc[KS_SUM0] = t[0]; sc[KS_SUM1] = t[1];
+            if (sc[KS_DIST] == 0.0) ks_fin_omega(sc);
+        });
+    }
+}
+
+static bool s2_enabled() {   // JB_STREAM_VARIANT=1 selects the first-generation register-stream kernels (A/B measurements)
+    const char* e = getenv("JB_STREAM_VARIANT");
+    return !(e && e[0] == '1');
+}
+
+template <int MODE>
+static int launch_spmv_s2(jb_csr* A, double alpha, const double* x, double beta, double* y, const double* u, double* sc, i64 n_dot) {
+    jb_ctx* ctx = A->ctx;
+    ProfScope _ps(ctx, JB_PROF_SPMV);
+    const bool ident = A->ident_src != nullptr && A->d_s2_ident.p != nullptr && A->n_s2_ident > 0;
+    const int nchunks = ident ? A->n_s2_ident : (int)A->h_s2.size();
+    const size_t smem = sizeof(S2Smem);
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        cudaFuncSetAttribute(spmv_s2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_s2_kernel<MODE>, JB_S2_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    int cap = ctx->sm_count * per_sm;
+    if (MODE != JB_DOT_NONE && cap > JB_MAX_PARTIALS) cap = JB_MAX_PARTIALS;
+    const int grid = std::max(1, std::min(nchunks, cap));
+    spmv_s2_kernel<MODE><<<grid, JB_S2_THREADS, smem, ctx->stream>>>(nchunks, ident ? A->d_s2_ident.p : A->d_s2.p, A->d_rowptr.p, A->d_colidx.p,
+                                                                    A->d_val.p, x, y, alpha, beta, u, sc, ctx->d_partials, ctx->d_counters,
+                                                                    n_dot < 0 ? A->n : n_dot, ident ? A->ident_src : nullptr);
+    JB_CHECK_LAUNCH(ctx);
+    return JB_OK;
+}
+
 template <int BS, int MODE>
 static int launch_spmv_stream(jb_csr* A, double alpha, const double* x, double beta, double* y, const double* u, double* sc, i64 n_dot) {
     jb_ctx* ctx = A->ctx;
@@ -230,6 +336,7 @@ static int launch_spmv_t(jb_csr* A, double alpha, const double* x, double beta, 
 
 template <int MODE>
 static int launch_spmv_mode(jb_csr* A, double alpha, const double* x, double beta, double* y, const double* u, double* sc, i64 n_dot = -1) {
+    if (A->bs == 2 && A->s2_ok && A->split_phase == 0 && s2_enabled() && x != y) return launch_spmv_s2<MODE>(A, alpha, x, beta, y, u, sc, n_dot);
     if (!A->h_chunks.empty() || n_dot >= 0) {
         if (A->h_chunks.empty()) return JB_ERR_UNSUPPORTED;   // distributed dots need the stream form
         switch (A->bs) {

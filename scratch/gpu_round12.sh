@@ -1,0 +1,7 @@
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -12
+timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/r12_bench_10m.json 2> gpurun_out/r12_bench_10m.err; tail -3 gpurun_out/r12_bench_10m.err
+timeout 300 python bench.py --dims 108,108,108 --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/r12_bench_1p26m.json 2> gpurun_out/r12_b.err; tail -3 gpurun_out/r12_b.err
+JB_STREAM_VARIANT=1 timeout 300 python bench.py --dims 108,108,108 --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/r12_bench_1p26m_gen1.json 2> gpurun_out/r12_c.err; tail -3 gpurun_out/r12_c.err
+python scratch/show.py gpurun_out/r12_bench_10m.json gpurun_out/r12_bench_1p26m.json gpurun_out/r12_bench_1p26m_gen1.json
