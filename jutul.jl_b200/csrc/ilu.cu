@@ -95,25 +95,40 @@ __global__ void __launch_bounds__(256) ilu_factor_rb_kernel(int c0, int c1, cons
         for (int j = threadIdx.x; j <= nr; j += blockDim.x) s_rp[j] = __ldg(ptrT + t0 + j);
         __syncthreads();
         const int base = s_rp[0], cnt = s_rp[nr] - base;
-        for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
-            const size_t li = (size_t)base + e;
-            const int32_t k = __ldcs(Lcol + li), src = __ldcs(Lmap + li), us = __ldcs(usrc + li);
-            double Lik[B2], Dk[B2], m[B2], prod[B2];
+        // two entries per thread in flight: indices first, then the three gathers of both entries, then the arithmetic
+        constexpr int UF = 2;
+        for (int eb = threadIdx.x; eb < cnt; eb += blockDim.x * UF) {
+            int32_t kk[UF], src[UF], us[UF];
+            double Lik[UF][B2], Dk[UF][B2], Ukj[UF][B2];
 #pragma unroll
-            for (int q = 0; q < B2; q++) { Lik[q] = __ldcs(A + (size_t)src * B2 + q); Dk[q] = dinv[(size_t)k * B2 + q]; }
-            if (us >= 0) {
-                double Ukj[B2];
-#pragma unroll
-                for (int q = 0; q < B2; q++) Ukj[q] = fv[(size_t)us * B2 + q];
-                blk_mul<BS>(Lik, Dk, m);
-                blk_mul<BS>(m, Ukj, prod);
-            } else {
-                blk_mul<BS>(Lik, Dk, m);
-#pragma unroll
-                for (int q = 0; q < B2; q++) prod[q] = 0.0;
+            for (int u = 0; u < UF; u++) {
+                const int e = eb + u * blockDim.x;
+                if (e < cnt) { const size_t li = (size_t)base + e; kk[u] = __ldcs(Lcol + li); src[u] = __ldcs(Lmap + li); us[u] = __ldcs(usrc + li); }
             }
 #pragma unroll
-            for (int q = 0; q < B2; q++) { __stcs(fv + li * B2 + q, m[q]); s_prod[(size_t)e * B2 + q] = prod[q]; }
+            for (int u = 0; u < UF; u++) {
+                const int e = eb + u * blockDim.x;
+                if (e < cnt) {
+#pragma unroll
+                    for (int q = 0; q < B2; q++) {
+                        Lik[u][q] = __ldcs(A + (size_t)src[u] * B2 + q);
+                        Dk[u][q] = dinv[(size_t)kk[u] * B2 + q];
+                        Ukj[u][q] = us[u] >= 0 ? fv[(size_t)us[u] * B2 + q] : 0.0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UF; u++) {
+                const int e = eb + u * blockDim.x;
+                if (e < cnt) {
+                    const size_t li = (size_t)base + e;
+                    double m[B2], prod[B2];
+                    blk_mul<BS>(Lik[u], Dk[u], m);
+                    blk_mul<BS>(m, Ukj[u], prod);
+#pragma unroll
+                    for (int q = 0; q < B2; q++) { __stcs(fv + li * B2 + q, m[q]); s_prod[(size_t)e * B2 + q] = us[u] >= 0 ? prod[q] : 0.0; }
+                }
+            }
         }
         __syncthreads();
         if ((int)threadIdx.x < nr) {
