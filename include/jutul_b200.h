@@ -158,6 +158,24 @@ int32_t jb_poisson_assemble(jb_tpfa* t, const double* d_K /*nf*/, const double* 
                             int32_t time_dependent, double dt, int64_t nsrc, const int64_t* src_cells,
                             const double* src_vals, double* d_r);
 
+/* ---- fill_equation_entries! for a GenericAutoDiffCache (src/ad/generic.jl:53-96; update_jacobian_entry!
+ *      src/ad/ad.jl:67-76; insert_residual_value :84-87; cache layout src/core_types/core_types.jl:787-840): the route
+ *      every equation WITHOUT a dedicated device kernel takes — the host (Julia, ForwardDiff) evaluates the entries,
+ *      the library scatters them into the device Jacobian / residual that the device solver then uses.
+ *      vpos[nu+1]: stencil slots of entity i are [vpos[i], vpos[i+1]) (1-based, as cache.vpos); dpos[nu] or NULL:
+ *      slot holding the diagonal entry of entity i (cache.diagonal_positions) — the residual is taken from that slot,
+ *      else from the first slot; positions[(ne*np) x n_slots]: 1-based index into the FLAT nzval of entry
+ *      (eq e, partial d) of slot j at positions[(e-1)*np + d-1 + ne*np*(j-1)] (cache.jacobian_positions, column-major);
+ *      0 = not aligned (skipped). entries: HOST array, memory image of Matrix{Dual{T,Float64,np}}(ne, n_slots):
+ *      (1+np) doubles per entry (value, partials), equation fastest. d_r: device residual, ne x nu, equation fastest,
+ *      written at r_offset + e + ne*i (r_offset in doubles, for equations stacked in one vector). Entries of the
+ *      Jacobian are SET, not accumulated, as the reference does. */
+typedef struct jb_generic jb_generic;
+int32_t jb_generic_create(jb_csr* csr, int32_t ne, int32_t np, int64_t nu, const int64_t* vpos, const int64_t* dpos,
+                          const int64_t* positions, jb_generic** out);
+int32_t jb_generic_destroy(jb_generic* g);
+int32_t jb_generic_fill(jb_generic* g, const double* entries_host, double* d_r, int64_t r_offset);
+
 /* ---- NFVM run-time flux: evaluate_flux / ntpfa_half_flux / compute_r / tpfa_flux (src/NFVM/evaluation.jl:1-88) on
  *      NFVMLinearDiscretization / NFVMNonLinearDiscretization (src/NFVM/types.jl:5-35). Per face: cell pair, T_left,
  *      T_right and the MPFA remainder as a CSR row of (cell, T) (ptr 1-based, nf+1). scheme 0 = linear (L_* only),

@@ -309,6 +309,33 @@ class TwoPhaseConservationLaw(_Handle):
         return r
 
 
+class GenericAutoDiffCacheFill(_Handle):
+    """fill_equation_entries!(nz, r, model, cache::GenericAutoDiffCache) (src/ad/generic.jl:53-96) for equations that the
+    host evaluates: the cache's vpos / diagonal_positions / jacobian_positions are uploaded once, every fill ships the
+    entries (memory image of Matrix{Dual}(ne, n_slots)) and scatters them into the device Jacobian and residual."""
+
+    _destroy = "jb_generic_destroy"
+
+    def __init__(self, jac, ne, npartials, vpos, jacobian_positions, diagonal_positions=None):
+        self.ctx, self.jac, self.ne, self.np = jac.ctx, jac, int(ne), int(npartials)
+        vpos = np.ascontiguousarray(vpos, dtype=i64)
+        pos = np.ascontiguousarray(jacobian_positions, dtype=i64).ravel()
+        dpos = None if diagonal_positions is None else np.ascontiguousarray(diagonal_positions, dtype=i64)
+        self.nu = vpos.shape[0] - 1
+        self.nslots = int(vpos[-1] - 1)
+        assert pos.shape[0] == self.nslots * self.ne * self.np
+        h = C.c_void_p()
+        check(self.ctx.lib.jb_generic_create(jac.h, self.ne, self.np, self.nu, _pi(vpos), _pi(dpos), _pi(pos), C.byref(h)), self.ctx.h,
+              "jb_generic_create")
+        self.h = h
+
+    def fill(self, entries, r, r_offset=0):
+        e = np.ascontiguousarray(entries, dtype=f64).ravel()
+        assert e.shape[0] == self.nslots * self.ne * (1 + self.np)
+        check(self.ctx.lib.jb_generic_fill(self.h, _pd(e), _dp(r), int(r_offset)), self.ctx.h, "jb_generic_fill")
+        return r
+
+
 class ILUZeroPreconditioner(_Handle):
     """ILU(0) on the block-CSR Jacobian; `partition` (1-based labels) gives the block-Jacobi form."""
 

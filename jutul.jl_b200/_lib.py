@@ -63,6 +63,9 @@ PROTOTYPES = {
     "jb_heat_pattern": (I32, [P, I64, I64, PP]),
     "jb_heat_assemble": (I32, [P, I64, I64, F64, F64, F64, P, P, P]),
     "jb_poisson_assemble": (I32, [P, P, P, P, I32, F64, I64, PI64, PF64, P]),
+    "jb_generic_create": (I32, [P, I32, I32, I64, PI64, PI64, PI64, PP]),
+    "jb_generic_destroy": (I32, [P]),
+    "jb_generic_fill": (I32, [P, PF64, P, I64]),
     "jb_nfvm_create": (I32, [P, I64, I64, I32, PI64, PI64, PF64, PF64, PI64, PI64, PF64, PF64, PF64, PI64, PI64, PF64, PP]),
     "jb_nfvm_destroy": (I32, [P]),
     "jb_nfvm_evaluate_flux": (I32, [P, P, I64, I64, P]),

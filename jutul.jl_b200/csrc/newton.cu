@@ -337,6 +337,91 @@ int32_t jb_poisson_assemble(jb_tpfa* t, const double* d_K, const double* d_U, co
 
 }  // extern "C"
 
+// ---- fill_equation_entries! for a GenericAutoDiffCache (src/ad/generic.jl:53-96) ---------------------------------------
+// One thread per (slot, equation): the entry's value goes to the residual when the slot is the residual slot of its
+// entity (diagonal_positions, else the first slot), each partial is SET at its aligned position of the flat nzval.
+struct jb_generic {
+    jb_csr* csr;
+    int ne, np;
+    i64 nu, nslots;
+    DBuf<int32_t> d_slot_entity;   // entity of slot j, or -1 when the slot does not feed the residual ... stored as (entity << 1) | is_residual
+    DBuf<int64_t> d_pos;           // 0-based flat nzval index, -1 = not aligned
+    DBuf<double> d_entries;
+    double* h_stage = nullptr;     // pinned staging of the entries
+};
+__global__ void __launch_bounds__(256) generic_fill_kernel(i64 nslots, int ne, int np, const int32_t* __restrict__ slot_entity,
+                                                           const int64_t* __restrict__ pos, const double* __restrict__ entries,
+                                                           double* __restrict__ nz, double* __restrict__ r) {
+    const i64 total = nslots * ne;
+    for (i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (i64)gridDim.x * blockDim.x) {
+        const i64 j = t / ne;
+        const int e = (int)(t % ne);
+        const double* a = entries + (size_t)t * (1 + np);       // (j*ne + e) * (1 + np)
+        const int32_t se = __ldg(slot_entity + j);
+        if (se & 1) r[(size_t)(se >> 1) * ne + e] = a[0];
+        for (int d = 0; d < np; d++) {
+            const int64_t q = __ldg(pos + (size_t)j * ne * np + (size_t)e * np + d);
+            if (q >= 0) nz[q] = a[1 + d];
+        }
+    }
+}
+
+extern "C" {
+int32_t jb_generic_create(jb_csr* A, int32_t ne, int32_t np, int64_t nu, const int64_t* vpos, const int64_t* dpos, const int64_t* positions,
+                          jb_generic** out) {
+    if (!A || !vpos || !positions || !out || ne < 1 || np < 1 || nu < 0) return JB_ERR_ARG;
+    jb_ctx* ctx = A->ctx;
+    if (vpos[0] != 1) JB_FAIL(ctx, JB_ERR_ARG, "jb_generic_create: vpos must start at 1");
+    const i64 nslots = vpos[nu] - 1;
+    const i64 nzlen = A->nnzb * A->bs * A->bs;
+    std::vector<int32_t> se((size_t)nslots, 0);
+    for (i64 i = 0; i < nu; i++) {
+        if (vpos[i + 1] < vpos[i]) JB_FAIL(ctx, JB_ERR_ARG, "jb_generic_create: vpos must be non-decreasing");
+        i64 rs = -1;
+        if (dpos) {
+            rs = dpos[i] - 1;
+            if (rs < vpos[i] - 1 || rs >= vpos[i + 1] - 1) JB_FAIL(ctx, JB_ERR_ARG, "jb_generic_create: diagonal position outside the entity's slots");
+        } else if (vpos[i + 1] > vpos[i]) rs = vpos[i] - 1;
+        for (i64 j = vpos[i] - 1; j < vpos[i + 1] - 1; j++) se[j] = (int32_t)((i << 1) | (j == rs ? 1 : 0));
+    }
+    std::vector<int64_t> hp((size_t)nslots * ne * np);
+    for (size_t q = 0; q < hp.size(); q++) {
+        if (positions[q] < 0 || positions[q] > nzlen) JB_FAIL(ctx, JB_ERR_ARG, "jb_generic_create: Jacobian position out of range");
+        hp[q] = positions[q] - 1;
+    }
+    jb_generic* g = new jb_generic();
+    g->csr = A; g->ne = ne; g->np = np; g->nu = nu; g->nslots = nslots;
+    const size_t nent = (size_t)nslots * ne * (1 + np);
+    bool ok = g->d_slot_entity.upload(se, ctx->stream) == cudaSuccess && g->d_pos.upload(hp, ctx->stream) == cudaSuccess &&
+              g->d_entries.alloc(std::max<size_t>(nent, 1)) == cudaSuccess &&
+              cudaMallocHost((void**)&g->h_stage, std::max<size_t>(nent, 1) * sizeof(double)) == cudaSuccess;
+    if (!ok) { jb_generic_destroy(g); JB_FAIL(ctx, JB_ERR_ALLOC, "jb_generic_create: allocation failed"); }
+    *out = g;
+    return JB_OK;
+}
+int32_t jb_generic_destroy(jb_generic* g) {
+    if (g && g->h_stage) cudaFreeHost(g->h_stage);
+    delete g;
+    return JB_OK;
+}
+int32_t jb_generic_fill(jb_generic* g, const double* entries_host, double* d_r, int64_t r_offset) {
+    if (!g || !entries_host || !d_r || r_offset < 0) return JB_ERR_ARG;
+    jb_ctx* ctx = g->csr->ctx;
+    const size_t nent = (size_t)g->nslots * g->ne * (1 + g->np);
+    if (nent == 0) return JB_OK;
+    memcpy(g->h_stage, entries_host, nent * sizeof(double));
+    JB_CUDA(ctx, cudaMemcpyAsync(g->d_entries.p, g->h_stage, nent * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        ProfScope _ps(ctx, JB_PROF_ASSEMBLY);
+        generic_fill_kernel<<<sgrid(ctx, g->nslots * g->ne), 256, 0, ctx->stream>>>(g->nslots, g->ne, g->np, g->d_slot_entity.p, g->d_pos.p,
+                                                                                  g->d_entries.p, g->csr->d_val.p, d_r + r_offset);
+        JB_CHECK_LAUNCH(ctx);
+    }
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+}  // extern "C"
+
 // ---- cell renumbering between the caller's numbering and the device numbering (jb_order_multicolor) ----
 template <int BS>
 __global__ void __launch_bounds__(256) permute_kernel(i64 n, const int32_t* __restrict__ perm, const double* __restrict__ src,

@@ -250,6 +250,28 @@ function convergence_criterion(model::B200Model, storage, eq::ConservationLaw, s
     return (AbsMax = (errors = e, names = ("water", "oil")),)
 end
 
+# ------------------------------------------------------------------------------------------------ generic-cache equations
+# fill_equation_entries!(nz, r, model, cache::GenericAutoDiffCache) (src/ad/generic.jl:53-96) for every equation that has no
+# device kernel: ForwardDiff fills cache.entries on the host as usual; the tables (vpos, diagonal_positions,
+# jacobian_positions) go to the device once, each fill ships the entries and scatters them into the device system.
+mutable struct B200GenericFill
+    handle::Ptr{Cvoid}
+end
+function B200GenericFill(A::B200Matrix, cache::Jutul.GenericAutoDiffCache)
+    nu, ne, np = Jutul.ad_dims(cache)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    dpos = isnothing(cache.diagonal_positions) ? Ptr{Int64}(C_NULL) : pointer(Vector{Int64}(cache.diagonal_positions))
+    check(ccall((:jb_generic_create, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
+                A.handle, ne, np, nu, Vector{Int64}(cache.vpos), dpos, Matrix{Int64}(cache.jacobian_positions), h), A.ctx.handle)
+    g = B200GenericFill(h[])
+    finalizer(x -> ccall((:jb_generic_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle), g)
+    return g
+end
+function fill_equation_entries!(g::B200GenericFill, d_r::Ptr{Float64}, cache::Jutul.GenericAutoDiffCache; r_offset = 0)
+    e = reinterpret(Float64, vec(cache.entries))     # (value, partials...) per Dual, equation fastest
+    check(ccall((:jb_generic_fill, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), g.handle, e, d_r, r_offset))
+end
+
 # partition(N, np, weights; partitioner = MetisPartitioner()) (src/partitioning.jl:244-307)
 function partition_metis(N::Matrix{Int64}, nc::Int, k::Int; weights = nothing)
     p = zeros(Int64, nc)

@@ -362,3 +362,60 @@ def partition_linear(m, n):
     p = np.zeros(n, dtype=i64)
     lib().orc_partition_linear(_ci(m), _ci(n), _I(p))
     return p
+
+
+# ------------------------------------------------------------------ generic-cache equations (src/ad/generic.jl)
+def generic_fill(ne, npart, vpos, dpos, positions, entries, nz, r, r_offset=0):
+    """fill_equation_entries_impl! (src/ad/generic.jl:61-96), plain loops. vpos (nu+1), dpos (nu or None) and positions
+    ((ne*np) x n_slots, column-major flat, 0 = not aligned) are 1-based like the cache's; entries is the memory image of
+    Matrix{Dual}(ne, n_slots): shape (n_slots, ne, 1+np). nz (flat nzval) and r (ne x nu, equation fastest) are updated
+    in place: Jacobian entries are SET (update_jacobian_inner!, src/ad/ad.jl:74-76)."""
+    nu = len(vpos) - 1
+    E = np.asarray(entries, dtype=f64).reshape(-1, ne, 1 + npart)
+    P = np.asarray(positions, dtype=i64).reshape(-1, ne * npart)          # [slot][(e-1)*np + d-1]
+    for i in range(nu):
+        rs = (dpos[i] if dpos is not None else vpos[i])
+        for jno, j in enumerate(range(vpos[i], vpos[i + 1])):
+            fill_residual = (j == rs) if dpos is not None else (jno == 0)
+            for e in range(ne):
+                a = E[j - 1, e]
+                if fill_residual:
+                    r[r_offset + e + ne * i] = a[0]
+                for d in range(npart):
+                    q = P[j - 1, e * npart + d]
+                    if q > 0:
+                        nz[q - 1] = a[1 + d]
+    return nz, r
+
+
+def generic_cache_heat(nx, ny, hx, hy, dt, T, T0, rowptr, colidx):
+    """What the reference holds for SimpleHeatEquation in its GenericAutoDiffCache after update_equation_in_entity!
+    (src/applications/test_systems/heat_2d/heat_2d.jl:7-49) evaluated with the local perspective of every stencil cell
+    (src/ad/local_ad.jl:54-79): per cell the unique stencil cells (aliases of a tiny periodic grid merged, as the
+    sparsity tracing does), per slot the value of the equation and its partial w.r.t. T of that slot's cell, and the
+    aligned positions in the CSR Jacobian (find_sparse_position, src/equations.jl:140-188). Returns
+    (vpos, dpos, positions, entries) in the layout of generic_fill."""
+    nc = nx * ny
+    T = np.asarray(T, dtype=f64); T0 = np.asarray(T0, dtype=f64)
+    vpos = [1]; dpos = []; pos = []; ent = []
+    for c in range(nc):
+        i, j = c % nx, c // nx
+        L = (i - 1) % nx + j * nx; R = (i + 1) % nx + j * nx
+        U = i + ((j - 1) % ny) * nx; D = i + ((j + 1) % ny) * nx
+        d2x = (T[L] - 2 * T[c] + T[R]) / hx ** 2
+        d2y = (T[U] - 2 * T[c] + T[D]) / hy ** 2
+        val = (T[c] - T0[c]) / dt - (d2x + d2y)
+        part = {}
+        for cell, w in ((c, 1.0 / dt + 2.0 / hx ** 2 + 2.0 / hy ** 2), (L, -1.0 / hx ** 2), (R, -1.0 / hx ** 2), (U, -1.0 / hy ** 2),
+                        (D, -1.0 / hy ** 2)):
+            part[cell] = part.get(cell, 0.0) + w
+        for cell in sorted(part):
+            if cell == c:
+                dpos.append(len(ent) + 1)
+            row = colidx[rowptr[c] - 1: rowptr[c + 1] - 1]
+            k = int(np.nonzero(row == cell + 1)[0][0])
+            pos.append(rowptr[c] + k)          # 1-based flat index (scalar Jacobian: block index == nzval index)
+            ent.append((val, part[cell]))
+        vpos.append(len(ent) + 1)
+    return (np.array(vpos, dtype=i64), np.array(dpos, dtype=i64), np.array(pos, dtype=i64).reshape(-1, 1),
+            np.array(ent, dtype=f64).reshape(-1, 1, 2))

@@ -1,0 +1,42 @@
+"""GPU parity of the pieces either side of the hot path: equations evaluated on the host and filled
+into the device system through their GenericAutoDiffCache. Runs after test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dims", [(37, 29), (2, 3)])
+def test_generic_cache_fill_matches_dedicated_heat_kernel(J, O, ctx, dims):
+    """Host-evaluated entries of SimpleHeatEquation scattered by jb_generic_fill == the dedicated device assembly == oracle;
+    the device BiCGStab then solves the system filled that way."""
+    nx, ny = dims
+    sim = J.HeatSimulator(ctx, nx, ny, 3.0, 2.0, rtol=1e-10)
+    rng = np.random.default_rng(9)
+    T = rng.uniform(0, 100, nx * ny); T0 = rng.uniform(0, 100, nx * ny)
+    sim.T.set(T); sim.T0.set(T0)
+    sim.assemble(0.25)
+    nz_dev, r_dev = sim.jac.nonzeros(), sim.r.get()
+    rowptr, colidx = sim.jac.pattern()
+    vpos, dpos, pos, ent = O.generic_cache_heat(nx, ny, 3.0 / nx, 2.0 / ny, 0.25, T, T0, rowptr, colidx)
+    fill = J.GenericAutoDiffCacheFill(sim.jac, 1, 1, vpos, pos, dpos)
+    sim.jac.set_nonzeros(np.full_like(nz_dev, np.nan)); sim.r.set(np.full_like(r_dev, np.nan))
+    fill.fill(ent, sim.r)
+    nz_o = np.full_like(nz_dev, np.nan); r_o = np.full_like(r_dev, np.nan)
+    O.generic_fill(1, 1, vpos, dpos, pos, ent, nz_o, r_o)
+    assert np.array_equal(sim.jac.nonzeros(), nz_o) and np.array_equal(sim.r.get(), r_o)      # a scatter: bit-exact
+    assert np.allclose(nz_o, nz_dev, rtol=1e-13) and np.allclose(r_o, r_dev, rtol=1e-12, atol=1e-12)
+    ok, its, hist, st = J.linear_solve(sim.krylov, sim.r, sim.dx)
+    assert ok and hist[-1] <= 1e-9 * hist[0] + 1e-12
+
+
+def test_generic_cache_fill_bad_tables(J, ctx):
+    A = J.build_sparse_matrix(ctx, [1, 1, 2, 2], [1, 2, 1, 2], 2, 1)
+    with pytest.raises(J.JutulB200Error):
+        J.GenericAutoDiffCacheFill(A, 1, 1, [1, 2, 3], [1, 99])            # position outside nzval
+    with pytest.raises(J.JutulB200Error):
+        J.GenericAutoDiffCacheFill(A, 1, 1, [1, 2, 3], [1, 4], [2, 2])     # diagonal slot outside the entity's slots
+    f = J.GenericAutoDiffCacheFill(A, 1, 1, [1, 3, 5], [1, 2, 3, 4], [1, 4])
+    r = ctx.zeros(2)
+    f.fill(np.array([[10.0, 1.0], [10.0, 2.0], [20.0, 3.0], [20.0, 4.0]]), r)
+    assert np.array_equal(A.nonzeros(), [1.0, 2.0, 3.0, 4.0]) and np.array_equal(r.get(), [10.0, 20.0])

@@ -1,6 +1,7 @@
 """Pins the CPU oracle against the reference's own golden vectors / known answers
 (SURVEY.md §8(c)). No GPU."""
 import numpy as np
+import pytest
 import scipy.sparse.linalg as spla
 
 from conftest import to_scipy
@@ -130,3 +131,23 @@ def test_heat_jacobian_and_residual_identity(O, J):
     assert np.allclose(r2, r + A @ d, rtol=1e-12, atol=1e-12)
     diag = 1.0 / dt + 2 / hx ** 2 + 2 / hy ** 2
     assert np.allclose(A.diagonal(), diag)
+
+
+@pytest.mark.parametrize("dims", [(5, 4), (2, 3), (1, 1)])
+def test_generic_cache_fill_reproduces_heat_assembly(O, dims):
+    """fill_equation_entries! on the GenericAutoDiffCache of SimpleHeatEquation gives the Jacobian and residual of the
+    dedicated heat assembly (two routes to the same LinearizedSystem; periodic aliasing on tiny grids merged)."""
+    nx, ny = dims
+    I, J = O.heat_pattern(nx, ny)
+    rowptr, colidx = O.csr_from_coo(I, J, nx * ny)
+    rng = np.random.default_rng(4)
+    T = rng.uniform(0, 100, nx * ny); T0 = rng.uniform(0, 100, nx * ny)
+    nz_ref, r_ref = O.assemble_heat(nx, ny, 0.7, 1.3, 0.5, T, T0, rowptr, colidx)
+    vpos, dpos, pos, ent = O.generic_cache_heat(nx, ny, 0.7, 1.3, 0.5, T, T0, rowptr, colidx)
+    nz = np.full(colidx.shape[0], np.nan); r = np.full(nx * ny, np.nan)
+    O.generic_fill(1, 1, vpos, dpos, pos, ent, nz, r)
+    assert np.allclose(nz, nz_ref, rtol=1e-13, atol=0) and np.allclose(r, r_ref, rtol=1e-12, atol=1e-12)
+    # without diagonal positions the residual comes from the first slot of each entity: same value in every slot
+    nz2 = np.zeros_like(nz); r2 = np.zeros_like(r)
+    O.generic_fill(1, 1, vpos, None, pos, ent, nz2, r2)
+    assert np.array_equal(nz2, nz) and np.array_equal(r2, r)
