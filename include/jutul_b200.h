@@ -220,6 +220,11 @@ int32_t jb_krylov_destroy(jb_krylov* ks);
 int32_t jb_krylov_solve(jb_krylov* ks, const double* d_r, double* d_dx, double rtol, double atol,
                         int32_t itmax, int32_t min_it, int32_t side, int32_t* iters, double* hist,
                         int32_t hist_cap);
+/* GMRES options (kind 1): memory (Krylov.jl default 20), restart (Jutul's serial call passes restart = false and lets
+ * the basis grow, src/linsolve/krylov.jl:212-238; its distributed call passes restart = true,
+ * ext/JutulPartitionedArraysExt/krylov.jl:67-74), flexible = 1 selects Krylov.jl fgmres! (right preconditioning, the
+ * preconditioned basis Z is kept and x = Z y). */
+int32_t jb_krylov_set_gmres(jb_krylov* ks, int32_t memory, int32_t restart, int32_t flexible);
 /* info[0..2] = stream chunks / rows / blocks of the Jacobian whose product in the right-preconditioned operator
  * A N^{-1} w is read off w (first-colour rows of a two-colour ILU(0), see krylov.cu; 0 when not applicable or
  * switched off with JB_RB_IDENTITY=0). Valid after the first solve; used for the byte accounting of bench.py. */

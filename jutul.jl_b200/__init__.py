@@ -380,9 +380,9 @@ class GenericKrylov(_Handle):
     _destroy = "jb_krylov_destroy"
 
     def __init__(self, jac, solver="bicgstab", preconditioner=None, relative_tolerance=1e-3, absolute_tolerance=None,
-                 max_iterations=100, min_iterations=1, precond_side="right"):
+                 max_iterations=100, min_iterations=1, precond_side="right", memory=20, restart=False):
         self.ctx, self.jac, self.preconditioner = jac.ctx, jac, preconditioner
-        kind = {"bicgstab": 0, "gmres": 1}[solver]
+        kind = {"bicgstab": 0, "gmres": 1, "fgmres": 1}[solver]
         self.rtol = relative_tolerance
         self.atol = 1e-12 if absolute_tolerance is None else absolute_tolerance
         self.max_iterations, self.min_iterations = max_iterations, min_iterations
@@ -392,6 +392,8 @@ class GenericKrylov(_Handle):
         ph = preconditioner.h if preconditioner is not None else None
         check(self.ctx.lib.jb_krylov_create(jac.h, ph, kind, C.byref(h)), self.ctx.h, "jb_krylov_create")
         self.h = h
+        if kind == 1:
+            check(self.ctx.lib.jb_krylov_set_gmres(h, int(memory), int(bool(restart)), int(solver == "fgmres")), self.ctx.h, "jb_krylov_set_gmres")
 
     def identity_info(self):
         """(chunks, rows, blocks) of the Jacobian whose product in A*N^-1*w is read off w (two-colour ILU(0),

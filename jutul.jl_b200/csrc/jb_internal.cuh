@@ -257,8 +257,11 @@ struct jb_krylov {
     bool overlap = false;      // interior SpMV overlapped with the halo exchange (JB_OVERLAP=1)
     jb_dist* dist = nullptr;   // distributed solve: dots over owned rows + all-reduce, halo exchange before each SpMV
     // gmres: Arnoldi basis (grows on demand), packed Hessenberg/R columns, Givens c/s, z, y
-    std::vector<double*> gm_V;
-    DBuf<double*> gm_Vptr;
+    std::vector<double*> gm_V, gm_Z;  // Z_j = N^{-1} v_j (fgmres only)
+    DBuf<double*> gm_Vptr, gm_Zptr;
+    int gm_memory = 20;               // Krylov.jl default memory
+    bool gm_restart = false;          // Jutul's serial call: restart = false; its distributed call: true
+    bool gm_flexible = false;         // fgmres!
     DBuf<double> gm_R, gm_cs;
 };
 

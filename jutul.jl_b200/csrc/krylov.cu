@@ -155,6 +155,7 @@ int32_t jb_krylov_destroy(jb_krylov* K) {
         if (K->ev[0]) cudaEventDestroy(K->ev[0]);
         if (K->ev[1]) cudaEventDestroy(K->ev[1]);
         for (double* p : K->gm_V) cudaFree(p);
+        for (double* p : K->gm_Z) cudaFree(p);
     }
     delete K;
     return JB_OK;

@@ -280,7 +280,7 @@ def bicgstab(n, bs, rowptr, colidx, nz, b, ilu=None, side="right", rtol=1e-3, at
     return x, st, iters.value, hist[: iters.value + 1].copy()
 
 
-def gmres(n, bs, rowptr, colidx, nz, b, ilu=None, side="right", rtol=1e-3, atol=1e-12, itmax=100, memory=20, restart=False):
+def gmres(n, bs, rowptr, colidx, nz, b, ilu=None, side="right", rtol=1e-3, atol=1e-12, itmax=100, memory=20, restart=False, flexible=False):
     x = np.zeros(n * bs)
     hist = np.zeros(itmax + 2)
     iters = C.c_int64(0)
@@ -288,7 +288,7 @@ def gmres(n, bs, rowptr, colidx, nz, b, ilu=None, side="right", rtol=1e-3, atol=
     h = ilu.h if ilu is not None else None
     lib().orc_gmres.restype = C.c_int
     st = lib().orc_gmres(_ci(n), C.c_int(bs), _I(rowptr), _I(colidx), _D(_ad(nz)), h, C.c_int(s), _D(_ad(b)), _D(x), _cd(rtol), _cd(atol),
-                         _ci(itmax), _ci(memory), C.c_int(int(restart)), C.byref(iters), _D(hist), _ci(hist.shape[0]))
+                         _ci(itmax), _ci(memory), C.c_int(int(restart)), C.c_int(int(flexible)), C.byref(iters), _D(hist), _ci(hist.shape[0]))
     return x, st, iters.value, hist[: iters.value + 1].copy()
 
 

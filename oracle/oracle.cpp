@@ -931,11 +931,14 @@ static void sym_givens(double a, double b, double* c, double* s, double* rho) {
     else { double t = b / a; *c = sgn(a) / std::sqrt(1 + t * t); *s = *c * t; *rho = a / *c; }
 }
 int orc_gmres(i64 n, int bs, const i64* rowptr, const i64* colidx, const double* nz, void* ilu, int side, const double* b, double* x,
-              double rtol, double atol, i64 itmax, i64 memory, int restart, i64* iters, double* hist, i64 hist_cap) {
+              double rtol, double atol, i64 itmax, i64 memory, int restart, int flexible, i64* iters, double* hist, i64 hist_cap) {
+    // flexible != 0: Krylov.jl fgmres! — right preconditioning with the preconditioned basis Z_j = N^{-1} v_j kept, x = x0 + Z y
     const i64 m = n * bs;
     auto A = [&](const double* in, double* out) { orc_spmv(n, bs, rowptr, colidx, nz, 1.0, in, 0.0, out); };
     auto P = [&](const double* in, double* out) { orc_ilu0_solve(ilu, in, out); };
     const bool left = (side == 1 && ilu), right = (side == 0 && ilu);
+    const bool flex = flexible != 0 && right;
+    std::vector<std::vector<double>> Z;
     std::vector<double> r0(m), w(m), q(m), p(m), xr(m, 0.0);
     for (i64 i = 0; i < m; i++) x[i] = 0.0;
     if (left) P(b, r0.data()); else vcopy(m, b, r0.data());
@@ -970,6 +973,7 @@ int orc_gmres(i64 n, int bs, const i64* rowptr, const i64* colidx, const double*
             }
             const double* pv = V[inner - 1].data();
             if (right) { P(V[inner - 1].data(), p.data()); pv = p.data(); }
+            if (flex) { if ((i64)Z.size() < inner) Z.emplace_back(m, 0.0); Z[inner - 1] = p; }
             A(pv, w.data());
             if (left) P(w.data(), q.data()); else vcopy(m, w.data(), q.data());
             for (i64 i = 1; i <= inner; i++) {
@@ -1009,8 +1013,8 @@ int orc_gmres(i64 n, int bs, const i64* rowptr, const i64* colidx, const double*
         double* xt = restart ? xr.data() : x;
         if (!restart) { /* x accumulates V*y directly; with right preconditioning N is applied to the whole sum */ }
         std::vector<double> acc(m, 0.0);
-        for (i64 i = 1; i <= inner; i++) vaxpy(m, y[i - 1], V[i - 1].data(), acc.data());
-        if (right) { P(acc.data(), p.data()); for (i64 i = 0; i < m; i++) acc[i] = p[i]; }
+        for (i64 i = 1; i <= inner; i++) vaxpy(m, y[i - 1], flex ? Z[i - 1].data() : V[i - 1].data(), acc.data());
+        if (right && !flex) { P(acc.data(), p.data()); for (i64 i = 0; i < m; i++) acc[i] = p[i]; }
         if (restart) { for (i64 i = 0; i < m; i++) x[i] += acc[i]; }
         else { for (i64 i = 0; i < m; i++) xt[i] = acc[i]; }
         inner_itmax -= inner; iter += inner; tired = iter >= itmax;

@@ -199,6 +199,31 @@ def test_gmres_solves(O, J, side, restart):
         assert abs(np.linalg.norm(r - A @ x) - hist[-1]) <= 1e-6 * hist[0]
 
 
+@pytest.mark.parametrize("restart", [False, True])
+def test_fgmres_equals_right_preconditioned_gmres(O, J, restart):
+    """Krylov.jl fgmres! with a FIXED preconditioner spans the same spaces as right-preconditioned gmres!: same residual
+    history to rounding, same solution; the restarted distributed form (left preconditioning, restart = true,
+    ext/JutulPartitionedArraysExt/krylov.jl:67-74) solves the same system in more iterations."""
+    w, s, M0, p, nz, r = _twophase_system(O, J)
+    n = w["nc"]
+    O.scale_diagonal(n, 2, s["rowptr"], s["colidx"], nz, r)
+    A = to_scipy(n, 2, s["rowptr"], s["colidx"], nz)
+    ilu = O.ILU0(n, 2, s["rowptr"], s["colidx"]); ilu.factor(nz)
+    kw = dict(rtol=1e-7, itmax=600, memory=40, restart=restart)
+    xg, stg, itg, hg = O.gmres(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, side="right", **kw)
+    xf, stf, itf, hf = O.gmres(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, side="right", flexible=True, **kw)
+    assert stg == 0 and stf == 0 and abs(itg - itf) <= 1
+    m = min(len(hg), len(hf))
+    assert np.allclose(hg[:m], hf[:m], rtol=1e-6, atol=1e-12 * hg[0])
+    assert np.linalg.norm(xg - xf) <= 1e-7 * np.linalg.norm(xg)
+    xl, stl, itl, hl = O.gmres(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, side="left", rtol=1e-7, itmax=600, memory=40, restart=True)
+    xd = spla.spsolve(A.tocsc(), r)
+    assert stl == 0 and np.linalg.norm(xl - xd) <= 1e-5 * np.linalg.norm(xd)
+    if restart:
+        x20, st20, it20, h20 = O.gmres(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, side="right", rtol=1e-7, itmax=600, memory=600, restart=True)
+        assert itg >= it20          # a short memory never beats the full basis
+
+
 def _nfvm_case(rng, nc=50, nf=120, nph=2, max_mpfa=5):
     left = rng.integers(1, nc + 1, nf); right = (left + rng.integers(0, nc - 1, nf)) % nc + 1
 
