@@ -34,6 +34,7 @@
 #include "jb_tma.cuh"
 #include <algorithm>
 #include <cstddef>
+#include <map>
 
 // inv_mu: the kernels multiply by 1/mu instead of dividing (FP64 division is a ~30-instruction sequence)
 struct TPParams { double rho0[2], c[2], mu[2], p0, inv_mu[2]; };
@@ -777,9 +778,12 @@ int jb_launch_twophase_assemble(jb_twophase* m, const double* d_M0, double dt, d
         const size_t smem = 2 * sizeof(Asm2Stage) + 2 * sizeof(Asm2Chunk) + 2 * sizeof(uint64_t) + 4 * sizeof(int);
         const int nchunks = (int)m->h_asm2.size();
         auto go = [&](auto kern) -> int {
-            int per_sm = 0;
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, JB_ASM2_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+            static std::map<const void*, int> occ;     // resident CTAs per SM of each instantiation (queried once)
+            int& per_sm = occ[(const void*)kern];
+            if (per_sm == 0) {
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, JB_ASM2_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+            }
             const int g = std::max(1, std::min(nchunks, ctx->sm_count * per_sm));
             kern<<<g, JB_ASM2_THREADS, smem, ctx->stream>>>(nchunks, m->d_asm2.p, make_params(m), t->mesh->d_hf_pos.p, t->mesh->d_hf_other.p,
                                                             m->d_hf_lp.p, m->d_hf_T.p, m->d_hf_sgdz.p, t->csr->d_diag.p, m->d_rec.p, m->d_pv.p, d_M0, src,
