@@ -210,6 +210,13 @@ int32_t jb_ilu0_info(jb_ilu* ilu, int64_t* info);
 int32_t jb_ilu0_get(jb_ilu* ilu, int64_t* Lptr, int64_t* Lcol, double* L, int64_t* Uptr, int64_t* Ucol,
                     double* U, double* Dinv);
 
+/* ---- DiagonalPreconditioner family (src/linsolve/precond/diagonal.jl:8-49): kind 1 = JacobiPreconditioner
+ *      (D_i = w inv(A_ii), jacobi.jl:15-18, w = 2/3 in the reference), kind 2 = SPAI0Preconditioner
+ *      (D_i = inv(sum_k |A_ik|_F^2) A_ii, spai.jl:42-62). Returns the same handle type as jb_ilu0_create: update with
+ *      jb_ilu0_update, apply with jb_ilu0_apply, hand to jb_krylov_create, release with jb_ilu0_destroy;
+ *      jb_ilu0_get(.., Dinv) returns the blocks D_i (L / U pointers must be NULL). */
+int32_t jb_diag_precond_create(jb_csr* csr, int32_t kind, double w, jb_ilu** out);
+
 /* ---- GenericKrylov + linear_solve! (src/linsolve/krylov.jl:34-47,71-182):
  *      kind 0 = bicgstab, 1 = gmres (Krylov.jl operation order); side 0 = right (N),
  *      1 = left (M), -1 = no preconditioner. Solves J x = r and leaves d_dx = -x

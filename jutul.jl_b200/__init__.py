@@ -374,6 +374,37 @@ class ILUZeroPreconditioner(_Handle):
         return dict(L=L, U=U, D=D, Lptr=Lptr, Lcol=Lcol, Uptr=Uptr, Ucol=Ucol)
 
 
+class _DiagonalPreconditioner(ILUZeroPreconditioner):
+    """DiagonalPreconditioner family (src/linsolve/precond/diagonal.jl): same interface as ILUZeroPreconditioner
+    (update_preconditioner, apply, usable by GenericKrylov); factors() returns the blocks D_i only."""
+
+    _kind = 0
+
+    def __init__(self, jac, w=1.0):
+        self.ctx, self.jac = jac.ctx, jac
+        h = C.c_void_p()
+        check(self.ctx.lib.jb_diag_precond_create(jac.h, self._kind, float(w), C.byref(h)), self.ctx.h, "jb_diag_precond_create")
+        self.h = h
+
+    def factors(self):
+        D = np.zeros(self.jac.n * self.jac.bs ** 2)
+        check(self.ctx.lib.jb_ilu0_get(self.h, None, None, None, None, None, None, _pd(D)), self.ctx.h, "jb_ilu0_get")
+        return dict(D=D)
+
+
+class JacobiPreconditioner(_DiagonalPreconditioner):
+    """JacobiPreconditioner(w = 2/3) (src/linsolve/precond/jacobi.jl)."""
+    _kind = 1
+
+    def __init__(self, jac, w=2.0 / 3.0):
+        super().__init__(jac, w)
+
+
+class SPAI0Preconditioner(_DiagonalPreconditioner):
+    """SPAI0Preconditioner() (src/linsolve/precond/spai.jl)."""
+    _kind = 2
+
+
 class GenericKrylov(_Handle):
     """GenericKrylov(solver; preconditioner, rtol, atol, max_iterations, min_iterations, precond_side)."""
 

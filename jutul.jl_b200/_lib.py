@@ -77,6 +77,7 @@ PROTOTYPES = {
     "jb_ilu0_apply": (I32, [P, P, P]),
     "jb_ilu0_info": (I32, [P, PI64]),
     "jb_ilu0_get": (I32, [P, PI64, PI64, PF64, PI64, PI64, PF64, PF64]),
+    "jb_diag_precond_create": (I32, [P, I32, F64, PP]),
     "jb_krylov_create": (I32, [P, P, I32, PP]),
     "jb_krylov_destroy": (I32, [P]),
     "jb_krylov_solve": (I32, [P, P, P, F64, F64, I32, I32, I32, PI32, PF64, I32]),

@@ -527,6 +527,7 @@ static int ilu_apply_t(jb_ilu* F, const double* b, double* x, const double* sc) 
 }
 
 int jb_launch_ilu_factor(jb_ilu* F) {
+    if (F->diag_kind != 0) return jb_launch_diag_factor(F);
     switch (F->bs) {
         case 1: return ilu_factor_t<1>(F);
         case 2: return ilu_factor_t<2>(F);
@@ -536,6 +537,7 @@ int jb_launch_ilu_factor(jb_ilu* F) {
     return JB_ERR_UNSUPPORTED;
 }
 int jb_launch_ilu_apply_sc(jb_ilu* F, const double* d_b, double* d_x, const double* d_sc) {
+    if (F->diag_kind != 0) return jb_launch_diag_apply(F, d_b, d_x, d_sc);   // Jacobi / SPAI(0) behind the same handle
     if (F->stream_ok) {
         switch (F->bs) {
             case 1: return ilu_apply_stream_t<1>(F, d_b, d_x, d_sc);
@@ -599,6 +601,11 @@ int32_t jb_ilu0_get(jb_ilu* F, int64_t* Lptr, int64_t* Lcol, double* L, int64_t*
     if (!F) return JB_ERR_ARG;
     jb_ctx* ctx = F->csr->ctx;
     const int b2 = F->bs * F->bs;
+    if (F->diag_kind != 0) {   // diagonal preconditioner: only the blocks D_i exist
+        if (Lptr || Lcol || L || Uptr || Ucol || U) JB_FAIL(ctx, JB_ERR_ARG, "jb_ilu0_get: a diagonal preconditioner has no L / U factors");
+        if (Dinv) JB_CUDA(ctx, cudaMemcpy(Dinv, F->d_dinv.p, (size_t)F->n * b2 * sizeof(double), cudaMemcpyDeviceToHost));
+        return JB_OK;
+    }
     std::vector<double> fv((size_t)(F->nL + F->n + F->nU) * b2);
     JB_CUDA(ctx, cudaMemcpyAsync(fv.data(), F->d_fv.p, fv.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (Dinv) JB_CUDA(ctx, cudaMemcpyAsync(Dinv, F->d_dinv.p, (size_t)F->n * b2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -200,6 +200,8 @@ struct jb_ilu {
     i64 n, nL, nU;
     int bs;
     int nlevF, nlevB;
+    int diag_kind = 0;                // 0: ILU(0); 1: Jacobi, 2: SPAI(0) (diagprec.cu) — only d_dinv / d_status are used then
+    double diag_w = 1.0;
     // host symbolic data (0-based)
     std::vector<int32_t> h_forder, h_border, h_levF_ptr, h_levB_ptr;
     std::vector<int32_t> h_Lstart, h_Lend, h_Ustart, h_Uend;      // per row, offsets into L / U storage
@@ -276,6 +278,8 @@ int jb_ilu_symbolic(jb_ilu* F, const int64_t* partition);
 int jb_ilu_upload(jb_ilu* F);
 int jb_launch_ilu_factor(jb_ilu* F);
 int jb_launch_ilu_apply(jb_ilu* F, const double* d_b, double* d_x);
+int jb_launch_diag_factor(jb_ilu* F);
+int jb_launch_diag_apply(jb_ilu* F, const double* d_b, double* d_x, const double* d_sc);
 
 int jb_launch_twophase_state(jb_twophase* m, const double* d_p, const double* d_s);
 int jb_launch_twophase_assemble(jb_twophase* m, const double* d_M0, double dt, double* d_r, bool jac);

@@ -419,3 +419,45 @@ def generic_cache_heat(nx, ny, hx, hy, dt, T, T0, rowptr, colidx):
         vpos.append(len(ent) + 1)
     return (np.array(vpos, dtype=i64), np.array(dpos, dtype=i64), np.array(pos, dtype=i64).reshape(-1, 1),
             np.array(ent, dtype=f64).reshape(-1, 1, 2))
+
+
+# ------------------------------------------------------------------ diagonal preconditioners (src/linsolve/precond)
+def _block_rows(n, bs, rowptr, colidx, nz):
+    b2 = bs * bs
+    V = np.asarray(nz, dtype=f64).reshape(-1, b2)
+    for i in range(n):
+        yield i, range(rowptr[i] - 1, rowptr[i + 1] - 1), V
+
+
+def jacobi_factor(n, bs, rowptr, colidx, nz, w=2.0 / 3.0):
+    """JacobiPreconditioner (src/linsolve/precond/jacobi.jl:15-18): D_i = w * inv(A_ii), blocks column-major like nzval."""
+    D = np.zeros((n, bs * bs))
+    for i, ks, V in _block_rows(n, bs, rowptr, colidx, nz):
+        for k in ks:
+            if colidx[k] == i + 1:
+                Aii = V[k].reshape(bs, bs).T                     # column-major block -> [row, col]
+                D[i] = (w * np.linalg.inv(Aii)).T.ravel()
+    return D.ravel()
+
+
+def spai0_factor(n, bs, rowptr, colidx, nz):
+    """SPAI0Preconditioner on a StaticSparsityMatrixCSR (src/linsolve/precond/spai.jl:42-62):
+    D_row = inv(sum over the row's entries of the squared Frobenius norm) * A_ii."""
+    D = np.zeros((n, bs * bs))
+    for i, ks, V in _block_rows(n, bs, rowptr, colidx, nz):
+        norm_sum = 0.0
+        Aii = np.zeros(bs * bs)
+        for k in ks:
+            for v in V[k]:
+                norm_sum += v * v
+            if colidx[k] == i + 1:
+                Aii = V[k]
+        D[i] = (1.0 / norm_sum) * Aii
+    return D.ravel()
+
+
+def diagonal_apply(D, y, bs):
+    """apply!(x, ::DiagonalPreconditioner, y) (src/linsolve/precond/diagonal.jl:31-49): x_i = D_i * y_i per block."""
+    n = y.shape[0] // bs
+    Dm = np.asarray(D, dtype=f64).reshape(n, bs, bs).transpose(0, 2, 1)      # [row, col]
+    return np.einsum("nij,nj->ni", Dm, np.asarray(y, dtype=f64).reshape(n, bs)).ravel()

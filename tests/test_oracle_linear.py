@@ -259,3 +259,29 @@ def test_nfvm_evaluate_flux_oracle(O):
     tot = np.abs(rl) + np.abs(rr)
     mu_l = np.where(tot < 1e-10, 0.5, np.abs(rr) / np.where(tot == 0, 1, tot)); mu_r = np.where(tot < 1e-10, 0.5, np.abs(rl) / np.where(tot == 0, 1, tot))
     assert np.allclose(qm, mu_l * q_l - mu_r * q_r, rtol=1e-13, atol=1e-13)
+
+
+def test_diagonal_preconditioners(O, J):
+    """Jacobi (w * inv(A_ii)) and SPAI(0) (inv(|row|_F^2) * A_ii) as the reference defines them
+    (src/linsolve/precond/jacobi.jl:15-18, spai.jl:42-62); both are exact inverses of a (block-)diagonal matrix up to
+    their definition: Jacobi with w = 1 inverts block-diagonal A, SPAI(0) of a scalar diagonal matrix is 1/a."""
+    w, s, M0, p, nz, r = _twophase_system(O, J, dims=(4, 3, 2))
+    n = w["nc"]
+    A = to_scipy(n, 2, s["rowptr"], s["colidx"], nz).toarray()
+    D = O.jacobi_factor(n, 2, s["rowptr"], s["colidx"], nz, w=1.0)
+    y = np.random.default_rng(2).standard_normal(2 * n)
+    x = O.diagonal_apply(D, y, 2)
+    for c in range(n):
+        blk = A[2 * c:2 * c + 2, 2 * c:2 * c + 2]
+        assert np.allclose(blk @ x[2 * c:2 * c + 2], y[2 * c:2 * c + 2], rtol=1e-9)
+    D23 = O.jacobi_factor(n, 2, s["rowptr"], s["colidx"], nz)
+    assert np.allclose(D23, (2.0 / 3.0) * D)
+    # SPAI(0): row-wise minimiser of |I - M A|_F over diagonal-block-scaled M = d_i * A_ii / ... (definition check)
+    S = O.spai0_factor(n, 2, s["rowptr"], s["colidx"], nz)
+    for c in range(n):
+        row = A[2 * c:2 * c + 2, :]
+        assert np.allclose(S.reshape(n, 4)[c].reshape(2, 2).T, row[:, 2 * c:2 * c + 2] / (row ** 2).sum(), rtol=1e-12)
+    # scalar diagonal matrix: SPAI(0) = 1/a
+    rp = np.arange(1, 6, dtype=np.int64); ci = np.arange(1, 5, dtype=np.int64); a = np.array([2.0, -4.0, 0.5, 10.0])
+    assert np.allclose(O.spai0_factor(4, 1, rp, ci, a), 1.0 / a)
+    assert np.allclose(O.diagonal_apply(O.jacobi_factor(4, 1, rp, ci, a, w=1.0), a, 1), np.ones(4))
