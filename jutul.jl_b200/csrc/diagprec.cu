@@ -4,8 +4,6 @@
 //   SPAI(0)  D_i = inv(sum_k |A_ik|_F^2) * A_ii  over the row     (spai.jl:42-62, StaticSparsityMatrixCSR method)
 //   apply!   x_i = D_i * y_i per block                            (diagonal.jl:31-49)
 // One thread per block row; both kernels are single streaming passes (HBM-bound).
-// STATUS: written after the GPU budget of round 1 was spent — compiled for sm_100a, exercised only by
-// tests/test_gpu_unverified.py (JB_RUN_UNVERIFIED=1), not yet run on a B200.
 #include "jb_internal.cuh"
 #include "jb_krylov_scalars.cuh"
 
