@@ -170,6 +170,23 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_kind,
                 "algorithmic_bytes_per_launch": bytes_of[dom]}
+    # the plain SpMV over ALL rows (jb_spmv = mul!(y, A, x)), against the unmodified SURVEY §8(d) byte formula: the number to
+    # compare with other SpMV implementations (the solver's own launches above skip the identity rows)
+    try:
+        xs = ctx.transfer(np.random.default_rng(0).standard_normal(2 * nc)); ys = ctx.zeros(2 * nc)
+        for _ in range(3):
+            sim.jac.mul(ys, xs)
+        with J.DeviceProfile(ctx) as prof2:
+            for _ in range(20):
+                sim.jac.mul(ys, xs)
+            t2, c2 = prof2.collect()["spmv"]
+        if c2:
+            g2 = alg["spmv"] * c2 / (t2 * 1e-3) / 1e9
+            kernels["spmv_all_rows"] = {"ms_per_launch": t2 / c2, "launches": c2, "achieved_gbs": g2, "frac": g2 / peak,
+                                        "algorithmic_bytes_per_launch": alg["spmv"]}
+        del xs, ys
+    except Exception as exc:      # an extra line of evidence must never cost the bench line
+        kernels["spmv_all_rows"] = {"error": str(exc)[:200]}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
