@@ -285,3 +285,37 @@ def test_diagonal_preconditioners(O, J):
     rp = np.arange(1, 6, dtype=np.int64); ci = np.arange(1, 5, dtype=np.int64); a = np.array([2.0, -4.0, 0.5, 10.0])
     assert np.allclose(O.spai0_factor(4, 1, rp, ci, a), 1.0 / a)
     assert np.allclose(O.diagonal_apply(O.jacobi_factor(4, 1, rp, ci, a, w=1.0), a, 1), np.ones(4))
+
+
+def test_two_colour_operator_identity(O, J):
+    """The claim behind the identity rows of the device SpMV (csrc/krylov.cu): with a two-colour numbering and ILU(0),
+    x = N^{-1} w satisfies (A x)_i = w_i on every first-colour row (no L entries, all couplings kept in U), because
+    U_ij = A_ij and D_i = A_ii there. Checked with the oracle's own ILU(0) and SpMV on the renumbered system; the
+    deviation is rounding, amplified by the conditioning of the 2x2 diagonal blocks."""
+    w = J.workloads.unstructured_hex(9, 8, 7)
+    n = w["nc"]
+    perm, ncol = J.multicolor_ordering(w["N"], n)
+    assert ncol == 2
+    w2 = dict(w)
+    w2["N"] = perm[w["N"] - 1]
+    for k in ("pv", "p0", "sw0"):
+        a = np.empty_like(w[k]); a[perm - 1] = w[k]; w2[k] = a
+    w2["src_cells"] = perm[w["src_cells"] - 1]
+    s = oracle_system(O, w2)
+    M0 = O.mass_2ph(w2["pv"], w2["params"], w2["p0"], w2["sw0"])
+    rng = np.random.default_rng(8)
+    p = w2["p0"] * (1 + 1e-3 * rng.standard_normal(n))
+    nz, r = O.assemble_2ph(s["hf"], s["diag_pos"], s["hf_pos"], w2["Tf"], w2["gdz"], w2["pv"], w2["params"], p, w2["sw0"], M0, w2["dt"],
+                           s["colidx"].shape[0], w2["src_cells"], w2["src_vals"])
+    ilu = O.ILU0(n, 2, s["rowptr"], s["colidx"]); ilu.factor(nz)
+    f = ilu.get()
+    first = np.diff(f["Lptr"]) == 0                      # rows without L entries = first colour
+    assert first.sum() >= n // 2 - 1 and np.all(np.diff(f["Uptr"])[first] == np.diff(s["rowptr"])[first] - 1)
+    wv = rng.standard_normal(2 * n)
+    x = ilu.solve(wv)
+    Ax = O.spmv(n, 2, s["rowptr"], s["colidx"], nz, x)
+    rows = np.repeat(first, 2)
+    A = to_scipy(n, 2, s["rowptr"], s["colidx"], nz)
+    scale = (abs(A) @ np.abs(x))[rows]                   # |A||x|: what rounding in the product is relative to
+    assert np.all(np.abs(Ax[rows] - wv[rows]) <= 1e-12 * scale + 1e-300)
+    assert np.abs(Ax[~rows] - wv[~rows]).max() > 1e-3 * np.abs(wv).max()      # the second colour is NOT an identity
