@@ -42,3 +42,43 @@ def test_multicolor_ordering_is_a_proper_colouring(J):
     split = max(k for k in range(1, w["nc"] + 1) if sizes[k - 1] == 0)
     assert split >= w["nc"] // 2 - 1
     assert np.all((N2[:, 0] <= split) != (N2[:, 1] <= split))
+
+
+def test_decompose_numbers_boundary_cells_last_in_each_colour(J, monkeypatch):
+    """Distributed local numbering (dist.decompose, multicolour order): owned cells first and coloured properly; owned
+    cells that touch a ghost sit at the END of their colour, so the rows before them form contiguous runs without ghost
+    couplings — what lets whole stream chunks qualify as identity rows of the right-preconditioned operator on every rank
+    (csrc/krylov.cu) and what the interior/boundary SpMV split uses."""
+    from jutul_b200 import dist as D
+    monkeypatch.delenv("JB_RB_IDENTITY", raising=False)
+    monkeypatch.delenv("JB_OVERLAP", raising=False)
+    w = J.workloads.unstructured_hex(12, 10, 8)
+    nc = w["nc"]
+    part = J.partition(w["N"], 3, weights=w["Tf"], nc=nc)
+    for rank in range(3):
+        plan = D.decompose(w["N"], nc, part, rank, "multicolor")
+        no, nl = plan["n_owned"], plan["n_local"]
+        assert np.array_equal(np.sort(plan["owned"]), np.nonzero(np.asarray(part) - 1 == rank)[0])
+        Nl = plan["N_local"] - 1
+        owned_face = (Nl[:, 0] < no) & (Nl[:, 1] < no)
+        touches_ghost = np.zeros(nl, dtype=bool)
+        gf = ~owned_face
+        touches_ghost[Nl[gf, 0]] = True; touches_ghost[Nl[gf, 1]] = True
+        touches_ghost[no:] = False
+        # colours: maximal label ranges without an internal owned face
+        lo = np.minimum(Nl[owned_face, 0], Nl[owned_face, 1]); hi = np.maximum(Nl[owned_face, 0], Nl[owned_face, 1])
+        ncol = plan["ncolors"]
+        assert ncol is not None and ncol >= 2
+        # inside every colour the boundary cells come last: once a ghost-touching owned cell appears, no interior cell follows
+        # (checked on the colour ranges reported by the proper-colouring property: no owned face inside a range)
+        bounds = sorted(set([0, no] + [int(k) for k in np.nonzero(np.diff(touches_ghost[:no].astype(int)) == -1)[0] + 1]))
+        assert len(bounds) - 1 <= ncol + 1        # at most one interior->boundary->interior transition per colour
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            seg = touches_ghost[a:b]
+            first_b = int(np.argmax(seg)) if seg.any() else len(seg)
+            assert np.all(seg[first_b:])          # boundary cells form the tail of the segment
+            inside = (lo >= a) & (hi < b)
+            assert not inside.any()               # and the segment is a colour: no owned face inside it
+    monkeypatch.setenv("JB_RB_IDENTITY", "0")
+    plan0 = D.decompose(w["N"], nc, part, 0, "multicolor")
+    assert np.array_equal(np.sort(plan0["owned"]), np.sort(D.decompose(w["N"], nc, part, 0, "default")["owned"]))
