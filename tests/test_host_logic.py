@@ -82,3 +82,31 @@ def test_decompose_numbers_boundary_cells_last_in_each_colour(J, monkeypatch):
     monkeypatch.setenv("JB_RB_IDENTITY", "0")
     plan0 = D.decompose(w["N"], nc, part, 0, "multicolor")
     assert np.array_equal(np.sort(plan0["owned"]), np.sort(D.decompose(w["N"], nc, part, 0, "default")["owned"]))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU restatement on the host cores) prints ONE JSON line that carries the keys of the
+    bench contract, on the same metric / unit / config keys as the GPU arm; ranks != 0 print nothing."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--dims", "12,10,8", "--steps", "1", "--warmup", "0",
+           "--reference-budget", "5"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "newton_iterations_per_sec" and d["unit"] == "newton_it/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64" and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["value"] > 0 and d["newton_iterations_per_step"] >= 1
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out1 = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert out1.returncode == 0 and out1.stdout.strip() == ""
