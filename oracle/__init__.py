@@ -461,3 +461,34 @@ def diagonal_apply(D, y, bs):
     n = y.shape[0] // bs
     Dm = np.asarray(D, dtype=f64).reshape(n, bs, bs).transpose(0, 2, 1)      # [row, col]
     return np.einsum("nij,nj->ni", Dm, np.asarray(y, dtype=f64).reshape(n, bs)).ravel()
+
+
+# ------------------------------------------------------------------ MultiModel Schur complement (src/linsolve/multimodel.jl)
+# [B C; D E] [x; y] = [a; b] with the eliminated groups (wells, ...) in E: the Krylov solver sees S = B - sum_i C_i E_i^{-1} D_i.
+# B is any object with a @-product (scipy sparse / ndarray); C_i, D_i, E_i are small (dense or sparse) blocks.
+def _esolve(E, v):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    return spla.spsolve(sp.csc_matrix(E), v) if sp.issparse(E) else np.linalg.solve(np.asarray(E), v)
+
+
+def schur_prepare(a, C, E, b):
+    """prepare_linear_solve! (multimodel.jl:17-33): a -= sum_i C_i (E_i \\ b_i), in place."""
+    for Ci, Ei, bi in zip(C, E, b):
+        a -= Ci @ _esolve(Ei, bi)
+    return a
+
+
+def schur_mul(B, C, D, E, x, alpha=1.0, beta=0.0, res=None):
+    """schur_mul! (multimodel.jl:150-160): res <- beta res + alpha (B x - sum_i C_i (E_i \\ (D_i x)))."""
+    out = alpha * (B @ x) + (0.0 if res is None or beta == 0.0 else beta * res)
+    for Ci, Di, Ei in zip(C, D, E):
+        out = out - alpha * (Ci @ _esolve(Ei, Di @ x))
+    return out
+
+
+def schur_dx_update(D, E, b, dx_from_solver):
+    """update_dx_from_vector! / schur_dx_update! (multimodel.jl:97-137): x = -dx_from_solver; y_i = E_i \\ (D_i dx - b_i)."""
+    x = -np.asarray(dx_from_solver, dtype=f64)
+    y = [_esolve(Ei, Di @ dx_from_solver - bi) for Di, Ei, bi in zip(D, E, b)]
+    return x, y

@@ -319,3 +319,36 @@ def test_two_colour_operator_identity(O, J):
     scale = (abs(A) @ np.abs(x))[rows]                   # |A||x|: what rounding in the product is relative to
     assert np.all(np.abs(Ax[rows] - wv[rows]) <= 1e-12 * scale + 1e-300)
     assert np.abs(Ax[~rows] - wv[~rows]).max() > 1e-3 * np.abs(wv).max()      # the second colour is NOT an identity
+
+
+def test_schur_complement_reduction(O, J):
+    """MultiModel :schur_apply (src/linsolve/multimodel.jl:17-160): reduce the right-hand side, solve with the operator
+    B - C E^-1 D, recover the eliminated unknowns — equals the direct solve of the full 2x2 block system, with Jutul's
+    sign convention dx = -(J \\ r)."""
+    w, s, M0, p, nz, r = _twophase_system(O, J, dims=(5, 4, 3))
+    n = w["nc"]
+    B = to_scipy(n, 2, s["rowptr"], s["colidx"], nz).tocsr()
+    rng = np.random.default_rng(12)
+    sizes = [3, 5]                                          # two eliminated groups (e.g. two wells)
+    sc = abs(B).max()
+    C = [sc * 1e-2 * rng.standard_normal((2 * n, m)) * (rng.random((2 * n, m)) < 0.05) for m in sizes]
+    D = [sc * 1e-2 * rng.standard_normal((m, 2 * n)) * (rng.random((m, 2 * n)) < 0.05) for m in sizes]
+    E = [sc * (np.eye(m) + 0.1 * rng.standard_normal((m, m))) for m in sizes]
+    a = r.copy(); b = [sc * rng.standard_normal(m) for m in sizes]
+    import scipy.sparse as sp
+    full = sp.bmat([[B, sp.csr_matrix(C[0]), sp.csr_matrix(C[1])], [sp.csr_matrix(D[0]), sp.csr_matrix(E[0]), None],
+                    [sp.csr_matrix(D[1]), None, sp.csr_matrix(E[1])]]).tocsc()
+    z = spla.spsolve(full, np.concatenate([a] + b))
+    a_red = O.schur_prepare(a.copy(), C, E, b)
+    S = spla.LinearOperator((2 * n, 2 * n), matvec=lambda v: O.schur_mul(B, C, D, E, v))
+    dx_solver, info = spla.gmres(S, a_red, rtol=1e-13, atol=0.0, restart=200, maxiter=5)
+    assert info == 0
+    x, y = O.schur_dx_update(D, E, b, dx_solver)
+    assert np.linalg.norm(x + z[: 2 * n]) <= 1e-8 * np.linalg.norm(z[: 2 * n])
+    off = 2 * n
+    for yi, m in zip(y, sizes):
+        assert np.linalg.norm(yi + z[off: off + m]) <= 1e-8 * max(np.linalg.norm(z[off: off + m]), 1e-30)
+        off += m
+    # alpha / beta form of the operator
+    v = rng.standard_normal(2 * n); res0 = rng.standard_normal(2 * n)
+    assert np.allclose(O.schur_mul(B, C, D, E, v, alpha=2.0, beta=-0.5, res=res0), 2.0 * O.schur_mul(B, C, D, E, v) - 0.5 * res0, rtol=1e-12)
