@@ -492,3 +492,15 @@ def schur_dx_update(D, E, b, dx_from_solver):
     x = -np.asarray(dx_from_solver, dtype=f64)
     y = [_esolve(Ei, Di @ dx_from_solver - bi) for Di, Ei, bi in zip(D, E, b)]
     return x, y
+
+
+# ------------------------------------------------------------------ load-balanced intervals (src/partitioning.jl:310-336)
+def load_balanced_endpoint(block_index, nvals, nblocks):
+    """Endpoint of interval `block_index` when nvals is cut into nblocks, the first (nvals mod nblocks) blocks one wider."""
+    width, remainder = divmod(nvals, nblocks)
+    return min(min(block_index, remainder) + width * block_index, nvals)
+
+
+def load_balanced_interval(b, n, m):
+    """1-based inclusive (start, stop) of block b in 1..m (src/partitioning.jl:332-336)."""
+    return load_balanced_endpoint(b - 1, n, m) + 1, load_balanced_endpoint(b, n, m)

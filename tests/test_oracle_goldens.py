@@ -151,3 +151,46 @@ def test_generic_cache_fill_reproduces_heat_assembly(O, dims):
     nz2 = np.zeros_like(nz); r2 = np.zeros_like(r)
     O.generic_fill(1, 1, vpos, None, pos, ent, nz2, r2)
     assert np.array_equal(nz2, nz) and np.array_equal(r2, r)
+
+
+def test_load_balanced_endpoint_properties(O):
+    """test/utils.jl:10-30, verbatim: endpoints, block widths floor/ceil(n/m), exact cover."""
+    for n in range(1, 101):
+        for m in range(1, n + 1):
+            assert O.load_balanced_endpoint(0, n, m) == 0 and O.load_balanced_endpoint(m, n, m) == n
+            count = 0
+            for i in range(1, m + 1):
+                start, stop = O.load_balanced_endpoint(i - 1, n, m), O.load_balanced_endpoint(i, n, m)
+                assert start < stop
+                assert stop - start in (n // m, -(-n // m))
+                count += stop - start
+            assert count == n
+    assert O.load_balanced_interval(2, 10, 3) == (5, 7)
+    # partition_linear (src/partitioning.jl:12-18) as shipped in the library: ceil(i / (n / m))
+    assert O.partition_linear(3, 10).tolist() == [1, 1, 1, 2, 2, 2, 3, 3, 3, 3]
+
+
+def test_scalar_and_multimodel_known_answers(O):
+    """ScalarTestSystem: (X - X0)/dt - f = 0 from X0 = 0, f = 1, dt = 1 gives X = 1 (test/test_systems/scalar.jl:14-22);
+    two of them with forces +1 / -1 and the skew-symmetric ScalarTestCrossTerm (X_T - X_S) give XA = 1/3, XB = -1/3
+    (test/test_systems/multimodel.jl:4-37) — through the generic-cache fill and, for the grouped form, the Schur
+    reduction with Jutul's sign convention dx = -(J \\ r)."""
+    dt, X0 = 1.0, 0.0
+    # single model: one entity, one slot, one equation, one partial
+    vpos = np.array([1, 2]); pos = np.array([[1]]); dpos = np.array([1])
+    ent = np.array([[[(X0 - X0) / dt - 1.0, 1.0 / dt]]])          # value after apply_forces! (diag_part -= force), partial
+    nz = np.zeros(1); r = np.zeros(1)
+    O.generic_fill(1, 1, vpos, dpos, pos, ent, nz, r)
+    assert X0 - r[0] / nz[0] == 1.0
+    # multimodel, groups = [1, 2]: B = dA/dXA, C = dA/dXB, D = dB/dXA, E = dB/dXB at X = 0
+    XA = XB = 0.0
+    rA = (XA - 0.0) / dt - 1.0 + (XA - XB); rB = (XB - 0.0) / dt + 1.0 - (XA - XB)
+    B = np.array([[1.0 / dt + 1.0]]); C = [np.array([[-1.0]])]; D = [np.array([[-1.0]])]; E = [np.array([[1.0 / dt + 1.0]])]
+    a = O.schur_prepare(np.array([rA]), C, E, [np.array([rB])])
+    S = O.schur_mul(B, C, D, E, np.array([1.0]))
+    dx_solver = a / S                                              # what the Krylov solver returns for the 1x1 operator
+    x, y = O.schur_dx_update(D, E, [np.array([rB])], dx_solver)
+    assert np.isclose(XA + x[0], 1.0 / 3.0, rtol=1e-15) and np.isclose(XB + y[0][0], -1.0 / 3.0, rtol=1e-15)
+    # ungrouped (single sparse matrix): the same answer from the full 2x2 system
+    Jm = np.array([[2.0, -1.0], [-1.0, 2.0]])
+    assert np.allclose(-np.linalg.solve(Jm, [rA, rB]), [1.0 / 3.0, -1.0 / 3.0])
