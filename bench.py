@@ -78,6 +78,14 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """Threads the CPU arm uses: every core this process may run on, whatever OMP_NUM_THREADS says (torchrun pins it to 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def parse_dims(s):
     d = [int(x) for x in s.split(",")]
     assert len(d) == 3
@@ -117,18 +125,41 @@ def run_b200(args):
     sim.set_forces(w["src_cells"], w["src_vals"])
     sim.set_state(w["p0"], w["sw0"])
     dt = w["dt"]
-    p_init, s_init = ctx.transfer(sim.p.get()), ctx.transfer(sim.s.get())   # resident copies of the initial state
+    p_init, s_init = ctx.transfer(sim.p.get()), ctx.transfer(sim.s.get())   # resident copies of the state at the start of a step
+    unconverged = [0]
 
     def step(solve=True):
         conv, e, rep = sim.perform_step(dt, solve=solve)
+        if "linear_warning" in rep:
+            unconverged[0] += 1
         return conv, rep.get("linear_iterations", 0)
 
     def timestep():
-        sim.p.copy_from(p_init); sim.s.copy_from(s_init)       # device-to-device; M0 stays that of the initial state
-        return run_timestep(step)
+        """One implicit timestep. Default: the simulation ADVANCES (update_after_step!, src/models.jl:983-1011: state0 <- state,
+        M0 recomputed), so step k of the run is report step k of the simulation. --fixed-state re-solves the first step."""
+        if args.fixed_state:
+            sim.p.copy_from(p_init); sim.s.copy_from(s_init)   # device-to-device; M0 stays that of the initial state
+            return run_timestep(step)
+        res = run_timestep(step)
+        if res[0]:
+            sim.update_before_step()
+        else:                                                    # no timestep cutting on this path: restart from the last good state
+            sim.p.copy_from(p_init); sim.s.copy_from(s_init)
+        p_init.copy_from(sim.p); s_init.copy_from(sim.s)
+        return res
+
+    def mark():
+        """Remember the simulation state so that the roofline and e2e passes re-run the same timesteps as the timed region."""
+        return ctx.transfer(sim.p.get()), ctx.transfer(sim.s.get())
+
+    def rewind(saved):
+        sim.p.copy_from(saved[0]); sim.s.copy_from(saved[1]); p_init.copy_from(saved[0]); s_init.copy_from(saved[1])
+        sim.update_before_step()
 
     for _ in range(args.warmup):
         timestep()
+    start_state = mark()
+    unconverged[0] = 0
     launches0 = ctx.launch_count
     clocks = ClockSampler(local_rank); clocks.start()
     J.timer_start(ctx)
@@ -143,6 +174,8 @@ def run_b200(args):
     # ---- roofline pass: the same steps with per-kernel-class CUDA-event timing on the launching stream
     alg = J.workloads.algorithmic_bytes(nc, nf, 2)
     peak, peak_kind = measured_peak()
+    n_unconverged = unconverged[0]
+    rewind(start_state)
     with J.DeviceProfile(ctx) as prof:
         J.timer_start(ctx)
         for _ in range(max(1, min(args.steps, 3))):
@@ -196,26 +229,44 @@ def run_b200(args):
 
     # ---- e2e: the reference-facing perform_step call with HOST (pinned-size) buffers: H2D of p, s, M0 and D2H of p, s
     #      inside every Newton iteration
+    rewind(start_state)
     p0_h, s0_h, M0_src = sim.download(p_init), sim.download(s_init, 2), sim.download(sim.M0, 2)   # caller's numbering
     # the buffers handed to the API live in pinned host memory
     p_h, s_h, M0_h = ctx.pinned_empty(nc), ctx.pinned_empty(2 * nc), ctx.pinned_empty(2 * nc)
     p_h[:] = p0_h; s_h[:] = s0_h; M0_h[:] = M0_src
     h2d = d2h = 0
+    first_of_step = [True]
 
     def step_host(solve=True):
         nonlocal h2d, d2h
-        st, conv, its, err = sim.perform_step_host(p_h, s_h, M0_h, dt)
-        h2d += nc * 5 * 8
+        # state0 is constant within a timestep: its masses M0 go up with the first Newton iteration of the step only
+        send_M0 = first_of_step[0]
+        first_of_step[0] = False
+        st, conv, its, err = sim.perform_step_host(p_h, s_h, M0_h if send_M0 else None, dt)
+        h2d += nc * (5 if send_M0 else 3) * 8
         d2h += (0 if conv else nc * 3 * 8) + 16
         return conv, its
 
     def timestep_host():
-        p_h[:] = p0_h; s_h[:] = s0_h
-        return run_timestep(step_host)
+        """The host owns the state: the buffers go in and come back every Newton iteration; between steps the host advances
+        state0 (M0 of the new state is produced on the device and read back: update_after_step!)."""
+        first_of_step[0] = True
+        if args.fixed_state:
+            p_h[:] = p0_h; s_h[:] = s0_h
+            return run_timestep(step_host)
+        nonlocal h2d, d2h
+        res = run_timestep(step_host)
+        sim.upload(sim.p, p_h); sim.upload(sim.s, s_h, 2); sim.update_before_step()
+        M0_h[:] = sim.download(sim.M0, 2)
+        h2d += nc * 3 * 8; d2h += nc * 2 * 8
+        return res
 
-    timestep_host()
+    if args.fixed_state:
+        timestep_host()      # warm the entry point (allocations); the advancing run must not consume a timestep for it
+    else:
+        first_of_step[0] = True; step_host(solve=False); p_h[:] = p0_h; s_h[:] = s0_h
     h2d = d2h = 0
-    n_e2e_steps = max(1, min(args.steps, 3))
+    n_e2e_steps = max(1, args.steps if args.e2e_steps <= 0 else args.e2e_steps)
     t0 = time.perf_counter()
     J.timer_start(ctx)
     res2 = [timestep_host() for _ in range(n_e2e_steps)]
@@ -224,7 +275,9 @@ def run_b200(args):
     nn2 = sum(r[1] for r in res2)
     e2e = {"value": nn2 / wall2, "unit": UNIT, "h2d_bytes_per_step": int(h2d / n_e2e_steps), "d2h_bytes_per_step": int(d2h / n_e2e_steps),
            "ms_per_step": 1e3 * wall2 / n_e2e_steps, "newton_iterations_per_step": nn2 / n_e2e_steps,
-           "api": "jb_twophase_perform_step_host (pinned host p, s, M0 in; p, s, errors out) once per Newton iteration"}
+           "api": "jb_twophase_perform_step_host (pinned host p, s in and p, s, errors out once per Newton iteration; M0 of state0 in "
+                  "with the first iteration of a timestep only)", "steps": n_e2e_steps,
+           "same_timesteps_as_value": True}
 
     # ---- cpu_baseline: bounded sample of the same workload on the host cores (oracle = CPU restatement)
     cpu = None
@@ -248,6 +301,9 @@ def run_b200(args):
                    "operator_identity_rows": id_rows},
         "newton_iterations_per_step": n_newton / max(args.steps, 1), "converged": all(r[0] for r in results),
         "linear_iterations_per_newton": float(np.mean(lin_its)) if lin_its else None, "linear_iterations": results[0][2],
+        "linear_solves": len(lin_its), "linear_solves_unconverged": n_unconverged,
+        "timestepping": "fixed state (every step re-solves report step 1)" if args.fixed_state else
+                        f"advancing: warm-up = report steps 1..{args.warmup}, timed = report steps {args.warmup + 1}..{args.warmup + args.steps}",
         "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "kernels": kernels,
         "hbm_gbs": {k: kernels[k]["achieved_gbs"] for k in ("assembly", "spmv") if k in kernels},
         "cpu_baseline": cpu,
@@ -272,7 +328,8 @@ def cpu_partition(J, w, threads):
 
 def cpu_sample(args, J, w, n_newton, n_assemblies, lin_total):
     import oracle as O
-    threads = O.num_threads()
+    threads = host_threads()
+    O.set_num_threads(threads)
     nc = w["nc"]
     s = oracle_setup(O, w)
     part, nblk = cpu_partition(J, w, threads)
@@ -313,18 +370,19 @@ def run_reference(args):
     nx, ny, nz = args.dims
     w = J.workloads.unstructured_hex(nx, ny, nz)
     nc, nf = w["nc"], w["nf"]
-    threads = O.num_threads()
+    threads = host_threads()          # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
+    O.set_num_threads(threads)
     s = oracle_setup(O, w)
     part, nblk = cpu_partition(J, w, threads)
     ilu = O.ILU0(nc, 2, s["rowptr"], s["colidx"], part)
     state = {}
 
     p_init = w["p0"].copy(); sat_init = np.stack([w["sw0"], 1 - w["sw0"]], axis=1).ravel().copy()
-    M0 = O.mass_2ph(w["pv"], w["params"], p_init, w["sw0"])
+    state["M0"] = O.mass_2ph(w["pv"], w["params"], p_init, w["sw0"])
 
     def step(solve=True):
         nz, r = O.assemble_2ph(s["hf"], s["diag_pos"], s["hf_pos"], w["Tf"], w["gdz"], w["pv"], w["params"], state["p"],
-                               state["sat"][0::2].copy(), M0, w["dt"], s["colidx"].shape[0], w["src_cells"], w["src_vals"])
+                               state["sat"][0::2].copy(), state["M0"], w["dt"], s["colidx"].shape[0], w["src_cells"], w["src_vals"])
         if np.all(O.maxabs_rows(r, 2) <= args.tolerance):
             return True, 0
         if not solve:
@@ -335,10 +393,6 @@ def run_reference(args):
         O.update_scalar(state["p"], dx, dx_stride=2)
         O.update_fraction_pair(state["sat"], dx[1:], abs_max=0.2, dx_stride=2)
         return False, its
-
-    def timestep():
-        state["p"] = p_init.copy(); state["sat"] = sat_init.copy()
-        return run_timestep(step)
 
     # Bounded sample: Newton iterations of the same timestep(s) are run one by one until --steps timesteps are done or the
     # wall-clock budget is exhausted (a 10M-cell Newton iteration is ~100 s on 16 cores); value = solved iterations / time.
@@ -365,6 +419,9 @@ def run_reference(args):
         if not partial:
             done += 1
             converged_all = converged_all and conv
+            if conv and not args.fixed_state:      # the simulation advances like the GPU arm's: state0 <- state
+                p_init = state["p"].copy(); sat_init = state["sat"].copy()
+                state["M0"] = O.mass_2ph(w["pv"], w["params"], p_init, sat_init[0::2].copy())
     el = time.perf_counter() - t0
     value = n_newton / el
     sample = (f"{n_newton} full Newton iterations ({done} complete timestep(s) of --steps {args.steps}"
@@ -380,7 +437,9 @@ def run_reference(args):
                                   f"({nc + 2 * nf} blocks), ILU(0)-BiCGStab rtol={args.rtol:g} (right precond.)",
                       "cells": nc, "faces": nf, "block_size": 2, "linear_rtol": args.rtol, "max_linear_iterations": args.max_linear_iterations,
                       "newton_tolerance": args.tolerance, "parallelism": f"{threads} OpenMP threads on the host",
-                      "note": "CPU restatement of the reference algorithm (oracle/); the Julia reference cannot run in this image"},
+                      "note": "CPU restatement of the reference algorithm (oracle/); the Julia reference cannot run in this image. "
+                              "libjutul_b200.so is loaded for the workload generator and the METIS partition only (host code, no GPU); "
+                              "all arithmetic of this arm is the oracle's"},
            "newton_iterations_per_step": n_newton / max(done, 1), "converged": bool(converged_all and not partial),
            "linear_iterations_per_newton": float(np.mean(lin)) if lin else None, "linear_iterations": results[0][2],
            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -401,9 +460,22 @@ def main():
     ap.add_argument("--ordering", default="multicolor", choices=["multicolor", "given"],
                     help="device cell numbering: multicolor (internal renumbering, default) or given (the mesh's own numbering)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fixed-state", action="store_true",
+                    help="re-solve report step 1 from the initial state every step instead of advancing the simulation")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timesteps of the e2e pass (default: --steps)")
+    ap.add_argument("--config", default=None, choices=["c2", "c3", "c5"],
+                    help="BASELINE.json configs: c2 = 100^3 cells, defaults; c3 = 100^3 cells, ILU(0)-BiCGStab to 1e-8 (itmax 1000); "
+                         "c5 = 216^3 cells, 50 implicit timesteps")
     ap.add_argument("--reference-budget", type=float, default=150.0, help="wall-clock budget (s) of the --impl reference timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.config in ("c2", "c3"):
+        args.dims = [100, 100, 100]
+    if args.config == "c3":
+        args.rtol, args.max_linear_iterations = 1e-8, 1000
+    if args.config == "c5":
+        args.steps = 50
+        args.e2e_steps = args.e2e_steps or 3
     if args.impl == "reference":
         run_reference(args)
     else:

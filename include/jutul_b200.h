@@ -36,6 +36,8 @@ extern "C" {
 #define JB_BREAKDOWN 2     /* rho == 0, alpha == 0 or NaN */
 #define JB_BAD_PIVOT 3     /* zero / non-finite ILU pivot */
 #define JB_NONFINITE 4     /* non-finite dx or residual */
+#define JB_BAD_SOLVE 5     /* unconverged linear solve whose final residual exceeds the initial one: the reference's
+                              error("Bad linear solve") (src/linsolve/krylov.jl:161-172) */
 #define JB_ERR_CUDA -1
 #define JB_ERR_ARG -2
 #define JB_ERR_ALLOC -3
@@ -108,6 +110,12 @@ int32_t jb_csr_get(jb_csr* csr, int64_t* rowptr /*n+1*/, int64_t* colidx /*nnz*/
 int32_t jb_csr_values_get(jb_csr* csr, double* nzval /*nnz*bs*bs*/);
 int32_t jb_csr_values_set(jb_csr* csr, const double* nzval);
 double* jb_csr_values_ptr(jb_csr* csr); /* device pointer to nonzeros(jac) */
+/* The library keeps a generation counter of the Jacobian values: every entry point that writes them (assembly, generic
+ * fill, scaling, values_set, unit_diagonalize) bumps it and jb_ilu0_update records it. A caller that writes through
+ * jb_csr_values_ptr must call jb_csr_values_modified afterwards. The Krylov driver uses shortcuts that are exact only for
+ * a preconditioner factored from the current values (identity rows of A*N^-1, csrc/krylov.cu) only when the generations
+ * match; a lagged preconditioner (apply!/linear_solve! without update_preconditioner!) takes the full SpMV. */
+int32_t jb_csr_values_modified(jb_csr* csr);
 
 /* ---- alignment: align_to_jacobian! / half_face_flux_cells_alignment! /
  *      diagonal_alignment! (src/conservation/conservation.jl:143-216,
@@ -313,6 +321,10 @@ int32_t jb_twophase_set_owned(jb_twophase* m, int64_t n_owned);
  *      state buffers: uploads p, s, M0, runs update_state_dependents! + update_linearized_system!
  *      + check_convergence (+ solve_and_update! when not converged), downloads the new p, s.
  *      errors[2] = max|r| per equation before the solve. converged = errors <= tol.
+ *      M0 == NULL keeps the masses of the previous call resident on the device (state0 is constant within a timestep:
+ *      pass M0 with the first Newton iteration of a step only). Return: JB_OK; JB_NOT_CONVERGED / JB_BREAKDOWN (the
+ *      update was still applied, as the reference does after a warning); JB_BAD_PIVOT, JB_BAD_SOLVE, JB_NONFINITE (no
+ *      update applied: the reference throws / cuts the step).
  *      This is the reference-facing end-to-end call timed as `e2e` by bench.py. */
 int32_t jb_twophase_perform_step_host(jb_twophase* m, jb_ilu* ilu, jb_krylov* ks, double* p /*nc*/,
                                       double* s /*2nc*/, const double* M0 /*2nc*/, double dt, double tol,

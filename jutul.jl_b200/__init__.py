@@ -21,7 +21,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import JB_BAD_PIVOT, JB_BREAKDOWN, JB_NONFINITE, JB_NOT_CONVERGED, JB_OK, JutulB200Error, check
+from ._lib import JB_BAD_PIVOT, JB_BAD_SOLVE, JB_BREAKDOWN, JB_NONFINITE, JB_NOT_CONVERGED, JB_OK, JutulB200Error, check
 
 i64 = np.int64
 f64 = np.float64
@@ -434,14 +434,23 @@ class GenericKrylov(_Handle):
         return int(info[0]), int(info[1]), int(info[2])
 
 
-def linear_solve(krylov, r, dx, rtol=None, atol=None, update_preconditioner=True):
+def linear_solve(krylov, r, dx, rtol=None, atol=None, update_preconditioner=True, status_reduce=None):
     """linear_solve!(lsys, krylov, ...): solves J x = r, leaves dx = -x. Returns
-    (ok, iterations, residual_history, status)."""
+    (ok, iterations, residual_history, status).
+
+    Failure policy of the reference (src/linsolve/krylov.jl:161-172): a failed factorisation or an unsolved system whose
+    final residual exceeds the initial one raises (the caller must never apply a stale dx); any other unsolved system
+    (itmax reached, breakdown) is returned with ok = False and the increment is still applied by the caller.
+    status_reduce: distributed runs pass a max-reduction over the ranks so that every rank takes the same decision
+    (a rank that skipped the solve would stop advancing the collectives' epochs and stall its peers)."""
     ctx = krylov.ctx
     if krylov.preconditioner is not None and update_preconditioner:
         st = krylov.preconditioner.update_preconditioner()
+        if status_reduce is not None:
+            st = int(status_reduce(st))
         if st != JB_OK:
-            return False, 0, np.zeros(0), st
+            raise JutulB200Error(f"update_preconditioner!: zero or non-finite pivot in the ILU(0) factorisation (status {st}); "
+                                 "the Newton increment was not computed")
     side = -1 if krylov.preconditioner is None else (0 if krylov.precond_side == "right" else 1)
     cap = krylov.max_iterations + 2
     hist = np.zeros(cap)

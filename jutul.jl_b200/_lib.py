@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "csrc", "libjutul_b200.so")
 
-JB_OK, JB_NOT_CONVERGED, JB_BREAKDOWN, JB_BAD_PIVOT, JB_NONFINITE = 0, 1, 2, 3, 4
+JB_OK, JB_NOT_CONVERGED, JB_BREAKDOWN, JB_BAD_PIVOT, JB_NONFINITE, JB_BAD_SOLVE = 0, 1, 2, 3, 4, 5
 
 P = C.c_void_p
 PP = C.POINTER(C.c_void_p)
@@ -49,6 +49,7 @@ PROTOTYPES = {
     "jb_csr_values_get": (I32, [P, PF64]),
     "jb_csr_values_set": (I32, [P, PF64]),
     "jb_csr_values_ptr": (P, [P]),
+    "jb_csr_values_modified": (I32, [P]),
     "jb_tpfa_create": (I32, [P, P, PP]),
     "jb_tpfa_destroy": (I32, [P]),
     "jb_tpfa_positions": (I32, [P, PI64, PI64]),

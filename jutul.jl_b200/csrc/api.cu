@@ -167,7 +167,7 @@ int32_t jb_twophase_set_permutation(jb_twophase* m, jb_perm* p) {
 int32_t jb_twophase_perform_step_host(jb_twophase* m, jb_ilu* ilu, jb_krylov* ks, double* p, double* s, const double* M0, double dt, double tol,
                                       double rtol, double atol, int32_t itmax, double dp_abs_max, double ds_abs_max, double* errors,
                                       int32_t* converged, int32_t* lin_iters) {
-    if (!m || !ks || !p || !s || !M0 || !errors || !converged || !lin_iters) return JB_ERR_ARG;
+    if (!m || !ks || !p || !s || !errors || !converged || !lin_iters) return JB_ERR_ARG;
     jb_ctx* ctx = m->t->mesh->ctx;
     cudaStream_t st = ctx->stream;
     const i64 nc = m->t->mesh->nc;
@@ -176,6 +176,7 @@ int32_t jb_twophase_perform_step_host(jb_twophase* m, jb_ilu* ilu, jb_krylov* ks
                   m->d_r.alloc(2 * nc) == cudaSuccess && m->d_dx.alloc(2 * nc) == cudaSuccess;
         if (!ok) JB_FAIL(ctx, JB_ERR_ALLOC, "jb_twophase_perform_step_host: allocation failed");
     }
+    if (!M0 && !m->M0_resident) JB_FAIL(ctx, JB_ERR_ARG, "jb_twophase_perform_step_host: M0 == NULL but no masses are resident yet");
     int rc;
     if (m->perm) {
         // host arrays are in the caller's numbering: stage, then renumber on the device
@@ -185,13 +186,16 @@ int32_t jb_twophase_perform_step_host(jb_twophase* m, jb_ilu* ilu, jb_krylov* ks
         if ((rc = jb_launch_permute(ctx, pm, nc, 1, m->d_stage.p, m->d_p.p, 0)) != JB_OK) return rc;
         JB_CUDA(ctx, cudaMemcpyAsync(m->d_stage.p, s, 2 * nc * sizeof(double), cudaMemcpyHostToDevice, st));
         if ((rc = jb_launch_permute(ctx, pm, nc, 2, m->d_stage.p, m->d_s.p, 0)) != JB_OK) return rc;
-        JB_CUDA(ctx, cudaMemcpyAsync(m->d_stage.p, M0, 2 * nc * sizeof(double), cudaMemcpyHostToDevice, st));
-        if ((rc = jb_launch_permute(ctx, pm, nc, 2, m->d_stage.p, m->d_M0.p, 0)) != JB_OK) return rc;
+        if (M0) {
+            JB_CUDA(ctx, cudaMemcpyAsync(m->d_stage.p, M0, 2 * nc * sizeof(double), cudaMemcpyHostToDevice, st));
+            if ((rc = jb_launch_permute(ctx, pm, nc, 2, m->d_stage.p, m->d_M0.p, 0)) != JB_OK) return rc;
+        }
     } else {
         JB_CUDA(ctx, cudaMemcpyAsync(m->d_p.p, p, nc * sizeof(double), cudaMemcpyHostToDevice, st));
         JB_CUDA(ctx, cudaMemcpyAsync(m->d_s.p, s, 2 * nc * sizeof(double), cudaMemcpyHostToDevice, st));
-        JB_CUDA(ctx, cudaMemcpyAsync(m->d_M0.p, M0, 2 * nc * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (M0) JB_CUDA(ctx, cudaMemcpyAsync(m->d_M0.p, M0, 2 * nc * sizeof(double), cudaMemcpyHostToDevice, st));
     }
+    if (M0) m->M0_resident = true;
     rc = jb_launch_twophase_state(m, m->d_p.p, m->d_s.p);
     if (rc != JB_OK) return rc;
     rc = jb_launch_twophase_assemble(m, m->d_M0.p, dt, m->d_r.p, true);
@@ -211,9 +215,13 @@ int32_t jb_twophase_perform_step_host(jb_twophase* m, jb_ilu* ilu, jb_krylov* ks
         if (rc != JB_OK) return rc;
     }
     int iters = 0;
-    rc = jb_krylov_dispatch(ks, m->d_r.p, m->d_dx.p, rtol, atol, itmax, 1, ilu ? 0 : -1, &iters, nullptr, 0, &status);
+    std::vector<double> hist((size_t)std::max(itmax, 0) + 2, 0.0);
+    rc = jb_krylov_dispatch(ks, m->d_r.p, m->d_dx.p, rtol, atol, itmax, 1, ilu ? 0 : -1, &iters, hist.data(), (int)hist.size(), &status);
     if (rc != JB_OK) return rc;
     *lin_iters = iters;
+    // the reference's failure policy (src/linsolve/krylov.jl:161-172): an unsolved system whose final residual exceeds the
+    // initial one is an error, anything else unsolved is a warning and the increment is applied
+    if (status != JB_OK && iters > 1 && (size_t)iters < hist.size() && hist[0] > 0.0 && hist[iters] / hist[0] > 1.0) return JB_BAD_SOLVE;
     // update_primary_variables! (src/models.jl:928-953): dx is bs x nc; pressure row 0, saturation row 1
     rc = jb_launch_update_scalar(ctx, m->d_p.p, m->d_dx.p, 2, nc, 1.0, dp_abs_max, NAN, NAN, NAN, NAN);
     if (rc != JB_OK) return rc;

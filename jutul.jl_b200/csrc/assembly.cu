@@ -771,6 +771,7 @@ int jb_launch_twophase_assemble(jb_twophase* m, const double* d_M0, double dt, d
     const i64 cells_per_cta = 256 / LPC;
     const int grid = (int)std::max<i64>(1, (nc + cells_per_cta - 1) / cells_per_cta);
     const double* src = m->nsrc > 0 ? m->d_src.p : nullptr;
+    if (jac) jb_csr_touch(t->csr);
     if (asm_variant() == 0 && m->asm2_ok && ((uintptr_t)d_M0 & 15) == 0) {
         // lane-pair-per-cell kernel; JB_ASM_NG picks (neighbour gathers in flight per lane, min CTAs per SM) for experiments
         const char* eng = getenv("JB_ASM_NG");
@@ -876,6 +877,7 @@ int jb_launch_twophase_assemble_faces(jb_twophase* m, const double* d_M0, double
     jb_ctx* ctx = t->mesh->ctx;
     const i64 nc = t->mesh->nc, nf = t->mesh->nf;
     const double* src = m->nsrc > 0 ? m->d_src.p : nullptr;
+    jb_csr_touch(t->csr);
     ProfScope _ps(ctx, JB_PROF_ASSEMBLY);
     twophase_acc_kernel<<<grid_for(ctx, nc, 256, 16), 256, 0, ctx->stream>>>(nc, make_params(m), reinterpret_cast<const double4*>(m->d_rec.p),
                                                                              m->d_pv.p, d_M0, src, dt, t->csr->d_diag.p, t->csr->d_val.p, d_r);

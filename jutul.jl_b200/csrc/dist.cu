@@ -208,6 +208,9 @@ static int p2p_halo_launch(jb_dist* D, double* d_vec, int bs, int which = 3) {
 int jb_dist_allreduce_fin_launch(jb_dist* D, double* d_buf, int n, int op_max, int fin_which, double* sc, double* hist, int hist_cap) {
     jb_ctx* ctx = D->comm->ctx;
     if (!D->p2p) return JB_ERR_UNSUPPORTED;
+    // one slot of the peer table holds JB_P2P_NRED doubles per (parity, rank): a longer vector would run into the next rank's
+    // slot and into the epoch words
+    if (n < 1 || n > JB_P2P_NRED) JB_FAIL(ctx, JB_ERR_ARG, "p2p all-reduce: at most JB_P2P_NRED values per exchange");
     ProfScope _ps(ctx, JB_PROF_OTHER);
     const unsigned long long epoch = ++D->ar_epoch;
     p2p_allreduce_kernel<<<1, 32, 0, ctx->stream>>>(D->d_peer_sym.p, D->comm->rank, D->comm->world, epoch, d_buf, n, op_max, fin_which, sc, hist,
@@ -395,8 +398,12 @@ int32_t jb_dist_allreduce(jb_dist* D, double* vals, int32_t n, int32_t op) {
     jb_ctx* ctx = D->comm->ctx;
     memcpy(ctx->h_pinned + 64, vals, n * sizeof(double));
     JB_CUDA(ctx, cudaMemcpyAsync(ctx->d_scalars + 32, ctx->h_pinned + 64, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = jb_dist_allreduce_launch(D, ctx->d_scalars + 32, n, op);
-    if (rc != JB_OK) return rc;
+    // the peer-memory exchange carries JB_P2P_NRED values per epoch: longer vectors go in pieces (every rank cuts alike)
+    const int piece = D->p2p ? JB_P2P_NRED : n;
+    for (int k0 = 0; k0 < n; k0 += piece) {
+        int rc = jb_dist_allreduce_launch(D, ctx->d_scalars + 32 + k0, std::min(piece, n - k0), op);
+        if (rc != JB_OK) return rc;
+    }
     JB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 64, ctx->d_scalars + 32, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     memcpy(vals, ctx->h_pinned + 64, n * sizeof(double));

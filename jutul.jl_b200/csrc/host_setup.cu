@@ -195,11 +195,17 @@ int32_t jb_csr_values_get(jb_csr* A, double* nz) {
 }
 int32_t jb_csr_values_set(jb_csr* A, const double* nz) {
     if (!A || !nz) return JB_ERR_ARG;
+    jb_csr_touch(A);
     JB_CUDA(A->ctx, cudaMemcpyAsync(A->d_val.p, nz, A->d_val.n * sizeof(double), cudaMemcpyHostToDevice, A->ctx->stream));
     JB_CUDA(A->ctx, cudaStreamSynchronize(A->ctx->stream));
     return JB_OK;
 }
 double* jb_csr_values_ptr(jb_csr* A) { return A ? A->d_val.p : nullptr; }
+int32_t jb_csr_values_modified(jb_csr* A) {
+    if (!A) return JB_ERR_ARG;
+    jb_csr_touch(A);
+    return JB_OK;
+}
 
 // ---------------------------------------------------------------- alignment
 static inline int32_t find_in_row(const jb_csr* A, int32_t row, int32_t col) {

@@ -527,6 +527,7 @@ static int ilu_apply_t(jb_ilu* F, const double* b, double* x, const double* sc) 
 }
 
 int jb_launch_ilu_factor(jb_ilu* F) {
+    F->factored_gen = F->csr->val_gen;   // the factors now belong to this generation of Jacobian values
     if (F->diag_kind != 0) return jb_launch_diag_factor(F);
     switch (F->bs) {
         case 1: return ilu_factor_t<1>(F);

@@ -143,7 +143,12 @@ struct jb_csr {
     i64 n_ident_rows = 0, n_ident_blocks = 0;
     const void* ident_for = nullptr;  // the jb_ilu the flags were built for
     const double* ident_src = nullptr;
+    // generation of the values in d_val: bumped by every entry point that writes the Jacobian (assembly, fill, scaling,
+    // values_set, unit_diagonalize). jb_ilu records the generation it was factored from; shortcuts that are exact only for a
+    // preconditioner built from the CURRENT values (identity rows of A N^-1, krylov.cu) are taken only when the two match.
+    uint64_t val_gen = 1;
 };
+inline void jb_csr_touch(jb_csr* A) { if (A) A->val_gen++; }
 int jb_csr_split_owned(jb_csr* A, i64 n_owned);
 int jb_dist_halo_push_launch(jb_dist* D, double* d_vec, int bs);   // peer-memory path only
 int jb_dist_halo_pull_launch(jb_dist* D, double* d_vec, int bs);
@@ -193,6 +198,7 @@ struct jb_twophase {
     bool asm2_ok = false;
     // resident state for the host-facing perform_step
     DBuf<double> d_p, d_s, d_M0, d_r, d_dx;
+    bool M0_resident = false;
 };
 
 struct jb_ilu {
@@ -231,6 +237,7 @@ struct jb_ilu {
     DBuf<double> d_fv;     // [L | D | U] blocks
     DBuf<double> d_dinv;   // inverted diagonal blocks
     DBuf<int32_t> d_status;
+    uint64_t factored_gen = 0;        // jb_csr::val_gen at the last numeric factorisation (0: never factored)
     cudaGraphExec_t apply_graph = nullptr;
     const double* graph_b = nullptr;
     double* graph_x = nullptr;

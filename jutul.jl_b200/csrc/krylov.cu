@@ -272,7 +272,9 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
     if (itmax > K->hist_cap - 2) itmax = K->hist_cap - 2;
     double* sc = K->d_sc.p;
     if (right) { const int rci = krylov_prepare_ident(K, n_own); if (rci != JB_OK) return rci; }
-    const bool ident = right && A->n_ident_chunks > 0 && A->ident_for == (const void*)F;
+    // the identity rows are exact only for factors built from the Jacobian's CURRENT values: a lagged preconditioner
+    // (update_preconditioner = false, or values written after jb_ilu0_update) falls back to the full SpMV
+    const bool ident = right && A->n_ident_chunks > 0 && A->ident_for == (const void*)F && F->factored_gen == A->val_gen;
 
     double h_sc[KS_SIZE];
     memset(h_sc, 0, sizeof(h_sc));

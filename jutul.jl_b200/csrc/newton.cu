@@ -251,6 +251,7 @@ int32_t jb_scale_system(jb_csr* A, double* d_r, int32_t kind, double dt) {
     if (!A || !d_r) return JB_ERR_ARG;
     jb_ctx* ctx = A->ctx;
     if (kind == 0) return JB_OK;
+    jb_csr_touch(A);
     if (kind == 2) {
         const i64 nv = A->nnzb * A->bs * A->bs, nr = A->n * A->bs;
         scale_kernel<<<sgrid(ctx, nv), 256, 0, ctx->stream>>>(nv, dt, A->d_val.p); JB_CHECK_LAUNCH(ctx);
@@ -272,6 +273,7 @@ int32_t jb_scale_system(jb_csr* A, double* d_r, int32_t kind, double dt) {
 int32_t jb_unit_diagonalize_ghosts(jb_csr* A, double* d_r, int64_t n_owned) {
     if (!A || !d_r || n_owned < 0 || n_owned > A->n) return JB_ERR_ARG;
     jb_ctx* ctx = A->ctx;
+    jb_csr_touch(A);
     const i64 ng = A->n - n_owned;
     if (ng == 0) return JB_OK;
     const int g = sgrid(ctx, ng);
@@ -302,6 +304,7 @@ int32_t jb_heat_pattern(jb_ctx* ctx, int64_t nx, int64_t ny, jb_csr** out) {
 int32_t jb_heat_assemble(jb_csr* A, int64_t nx, int64_t ny, double hx, double hy, double dt, const double* d_T, const double* d_T0, double* d_r) {
     if (!A || !d_T || !d_T0 || !d_r || A->bs != 1 || A->n != nx * ny || !(dt > 0)) return JB_ERR_ARG;
     jb_ctx* ctx = A->ctx;
+    jb_csr_touch(A);
     heat_assemble_kernel<<<sgrid(ctx, A->n), 256, 0, ctx->stream>>>(nx, ny, hx, hy, dt, d_T, d_T0, A->d_rowptr.p, A->d_colidx.p, A->d_val.p, d_r);
     JB_CHECK_LAUNCH(ctx);
     JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -312,6 +315,7 @@ int32_t jb_poisson_assemble(jb_tpfa* t, const double* d_K, const double* d_U, co
     if (!t || !d_K || !d_U || !d_r || t->csr->bs != 1 || (time_dependent && (!d_U0 || !(dt > 0)))) return JB_ERR_ARG;
     jb_ctx* ctx = t->mesh->ctx;
     const i64 nc = t->mesh->nc;
+    jb_csr_touch(t->csr);
     DBuf<double> src, sv;
     DBuf<int32_t> scell;
     if (nsrc > 0) {
@@ -409,6 +413,7 @@ int32_t jb_generic_fill(jb_generic* g, const double* entries_host, double* d_r, 
     jb_ctx* ctx = g->csr->ctx;
     const size_t nent = (size_t)g->nslots * g->ne * (1 + g->np);
     if (nent == 0) return JB_OK;
+    jb_csr_touch(g->csr);
     memcpy(g->h_stage, entries_host, nent * sizeof(double));
     JB_CUDA(ctx, cudaMemcpyAsync(g->d_entries.p, g->h_stage, nent * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     {

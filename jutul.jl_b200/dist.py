@@ -279,8 +279,13 @@ class DistTwoPhaseSimulator:
         converged = bool(np.all(e <= self.tolerance))
         if converged or not solve:
             return converged, e, rep
-        ok, its, hist, st = J.linear_solve(self.krylov, self.r, self.dx)
+        # the refactorisation status is max-reduced so that all ranks abort together (a rank that skipped the solve would
+        # stall the peers' collectives)
+        ok, its, hist, st = J.linear_solve(self.krylov, self.r, self.dx,
+                                           status_reduce=lambda v: self.halo.allreduce([float(v)], "max")[0])
         rep["linear_iterations"], rep["linear_status"], rep["linear_residuals"] = its, st, hist
+        if not ok:
+            rep["linear_warning"] = f"Linear solver: status {st} after {its} iterations"
         J.update_primary_variable(self.ctx, self.p, self.dx, self.n_owned, dx_stride=2, abs_max=self.dp_abs_max)
         J.unit_update_pairs(self.ctx, self.s, self.dx.offset(1), self.n_owned, dx_stride=2, abs_max=self.ds_abs_max)
         self.halo.exchange(self.p, 1); self.halo.exchange(self.s, 2)                        # parray_synchronize_primary_variables

@@ -135,6 +135,9 @@ class TwoPhaseSimulator:
         rep["linear_iterations"] = its
         rep["linear_status"] = st
         rep["linear_residuals"] = hist
+        if not ok:   # the reference warns (verbose) and goes on with the increment it has (src/linsolve/krylov.jl:161-172)
+            rep["linear_warning"] = (f"Linear solver: status {st} after {its} iterations, rel. residual "
+                                     f"{hist[-1] / hist[0] if len(hist) and hist[0] > 0 else float('nan'):.3e} (rtol {self.krylov.rtol:g})")
         J.update_primary_variable(self.ctx, self.p, self.dx, self.nc, dx_stride=2, abs_max=self.dp_abs_max)
         J.unit_update_pairs(self.ctx, self.s, self.dx.offset(1), self.nc, dx_stride=2, abs_max=self.ds_abs_max)
         rep["update_time"] = time.perf_counter() - t3
@@ -166,14 +169,19 @@ class TwoPhaseSimulator:
 
     # -- reference-facing end-to-end call with host buffers (bench `e2e`) ------------------------
     def perform_step_host(self, p, s, M0, dt):
+        """One Newton iteration with host buffers. M0 = None keeps the masses of the previous call resident (state0 is
+        constant within a timestep: pass it with the first Newton iteration only). Raises on the conditions the reference
+        throws on (bad pivot, bad linear solve)."""
         lib = self.ctx.lib
         errors = np.zeros(2); conv = C.c_int32(0); its = C.c_int32(0)
         st = check(lib.jb_twophase_perform_step_host(
             self.law.h, self.prec.h, self.krylov.h, p.ctypes.data_as(_lib.PF64), s.ctypes.data_as(_lib.PF64),
-            M0.ctypes.data_as(_lib.PF64), float(dt), float(self.tolerance), float(self.krylov.rtol), float(self.krylov.atol),
+            None if M0 is None else M0.ctypes.data_as(_lib.PF64), float(dt), float(self.tolerance), float(self.krylov.rtol), float(self.krylov.atol),
             int(self.krylov.max_iterations), float("nan") if self.dp_abs_max is None else float(self.dp_abs_max),
             float("nan") if self.ds_abs_max is None else float(self.ds_abs_max), errors.ctypes.data_as(_lib.PF64), C.byref(conv),
             C.byref(its)), self.ctx.h, "jb_twophase_perform_step_host")
+        if st in (_lib.JB_BAD_PIVOT, _lib.JB_BAD_SOLVE):
+            raise _lib.JutulB200Error(f"perform_step!: {'bad ILU(0) pivot' if st == _lib.JB_BAD_PIVOT else 'Bad linear solve'} (status {st})")
         return st, bool(conv.value), its.value, errors
 
 

@@ -741,16 +741,39 @@ static void vaxpby(i64 n, double a, const double* x, double b, double* y) {
 #pragma omp parallel for schedule(static)
     for (i64 i = 0; i < n; i++) y[i] = a * x[i] + b * y[i];
 }
-static void vcopy(i64 n, const double* x, double* y) { memcpy(y, x, n * sizeof(double)); }
+static void vcopy(i64 n, const double* x, double* y) {
+#pragma omp parallel for schedule(static)
+    for (i64 i = 0; i < n; i++) y[i] = x[i];
+}
+// Work vector whose pages are first touched by the threads that will stream them (static schedule, like every loop above):
+// std::vector would zero-fill from one thread and pin all pages to that thread's NUMA node.
+struct PVec {
+    double* p;
+    explicit PVec(i64 n) : p(static_cast<double*>(::operator new(sizeof(double) * (size_t)(n > 0 ? n : 1)))) {
+#pragma omp parallel for schedule(static)
+        for (i64 i = 0; i < n; i++) p[i] = 0.0;
+    }
+    ~PVec() { ::operator delete(p); }
+    PVec(const PVec&) = delete;
+    PVec& operator=(const PVec&) = delete;
+    double* data() { return p; }
+};
 
 int orc_bicgstab(i64 n, int bs, const i64* rowptr, const i64* colidx, const double* nz, void* ilu, int side,
                  const double* b, double* x, double rtol, double atol, i64 itmax, i64 min_it,
                  i64* iters, double* hist, i64 hist_cap) {
     const i64 m = n * bs;
-    std::vector<double> r(m), p(m), v(m, 0.0), s(m, 0.0), y(m), z(m), q(m), t(m), d(m);
+    const bool left = (side == 1 && ilu), right = (side == 0 && ilu);
+    // Krylov.jl's workspace aliases q = v, d = t when M is the identity and y = p, z = s when N is (bicgstab.jl: `MisI`,
+    // `NisI`): no copies are made for an absent preconditioner. Same here — the arithmetic is unchanged.
+    PVec r(m), p(m), v(m), s(m), t(m), yb(right ? m : 0), zb(right ? m : 0), qb(left ? m : 0), db(left ? m : 0);
+    double* const y = right ? yb.data() : p.data();
+    double* const z = right ? zb.data() : s.data();
+    double* const q = left ? qb.data() : v.data();
+    double* const d = left ? db.data() : t.data();
     auto A = [&](const double* in, double* out) { orc_spmv(n, bs, rowptr, colidx, nz, 1.0, in, 0.0, out); };
     auto P = [&](const double* in, double* out) { orc_ilu0_solve(ilu, in, out); };
-    const bool left = (side == 1 && ilu), right = (side == 0 && ilu);
+#pragma omp parallel for schedule(static)
     for (i64 i = 0; i < m; i++) x[i] = 0.0;
     if (left) P(b, r.data()); else vcopy(m, b, r.data());
     vcopy(m, r.data(), p.data());
@@ -772,18 +795,18 @@ int orc_bicgstab(i64 n, int bs, const i64* rowptr, const i64* colidx, const doub
     while (!(solved || tired || breakdown || user_exit)) {
         iter++;
         rho = next_rho;
-        if (right) P(p.data(), y.data()); else vcopy(m, p.data(), y.data());
-        A(y.data(), q.data());
-        if (left) P(q.data(), v.data()); else vcopy(m, q.data(), v.data());
+        if (right) P(p.data(), y);
+        A(y, q);
+        if (left) P(q, v.data());
         alpha = rho / vdot(m, b, v.data());
         vcopy(m, r.data(), s.data());
         vaxpy(m, -alpha, v.data(), s.data());
-        vaxpy(m, alpha, y.data(), x);
-        if (right) P(s.data(), z.data()); else vcopy(m, s.data(), z.data());
-        A(z.data(), d.data());
-        if (left) P(d.data(), t.data()); else vcopy(m, d.data(), t.data());
+        vaxpy(m, alpha, y, x);
+        if (right) P(s.data(), z);
+        A(z, d);
+        if (left) P(d, t.data());
         omega = vdot(m, t.data(), s.data()) / vdot(m, t.data(), t.data());
-        vaxpy(m, omega, z.data(), x);
+        vaxpy(m, omega, z, x);
         vcopy(m, s.data(), r.data());
         vaxpy(m, -omega, t.data(), r.data());
         next_rho = vdot(m, b, r.data());
