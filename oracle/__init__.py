@@ -247,6 +247,13 @@ class ILU0:
     def factor(self, nz):
         return lib().orc_ilu0_factor(self.h, _D(_ad(nz)))
 
+    def set_level_schedule(self, on=True, max_levels=64):
+        """Run the triangular solves level by level (rows of a dependency level concurrently). Bitwise the same result as the
+        sequential sweep; only worth it for orderings with few levels. Returns the number of levels (0: refused)."""
+        f = lib().orc_ilu0_set_level_schedule
+        f.restype = C.c_int64
+        return int(f(self.h, C.c_int(1 if on else 0), _ci(max_levels)))
+
     def solve(self, b, x=None):
         if x is None:
             x = np.zeros_like(b)

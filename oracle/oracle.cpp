@@ -541,6 +541,12 @@ struct OrcIlu {
     std::vector<std::vector<i64>> active;   // rows (0-based) per block, ascending
     std::vector<i64> Lptr, Lcol, Lmap, Uptr, Ucol, Umap, Dmap;
     std::vector<double> L, U, D;
+    // Optional execution schedule of the triangular solves (orc_ilu0_set_level_schedule): rows grouped by dependency level.
+    // Rows of a level only read rows of earlier levels, so running a level's rows concurrently performs, row by row, exactly
+    // the operations of the sequential sweep of ilu_solve! (same operands, same order inside the row): bitwise the same x.
+    // It exists so that the checker finishes in seconds on orderings with few levels (multicolour); it is not a different
+    // algorithm, and tests/test_oracle_linear.py pins the bit-equality against the sequential sweep.
+    std::vector<std::vector<i64>> levF, levB;
 };
 
 static void blk_inv(int bs, const double* A, double* B) {
@@ -686,10 +692,67 @@ void orc_ilu0_get(void* h, double* L, double* U, double* D, i64* Lptr, i64* Lcol
     if (Lcol) for (size_t i = 0; i < F->Lcol.size(); i++) Lcol[i] = F->Lcol[i] + 1;
     if (Ucol) for (size_t i = 0; i < F->Ucol.size(); i++) Ucol[i] = F->Ucol[i] + 1;
 }
+// Build (on != 0) or drop the level schedule; returns the number of forward levels (0 when the schedule is refused:
+// more than max_levels levels would make the per-level barriers dominate).
+i64 orc_ilu0_set_level_schedule(void* h, int on, i64 max_levels) {
+    OrcIlu* F = (OrcIlu*)h;
+    F->levF.clear(); F->levB.clear();
+    if (!on) return 0;
+    const i64 n = F->n;
+    std::vector<i64> lf(n, 0), lb(n, 0);
+    i64 nf = 0, nb = 0;
+    for (i64 i = 0; i < n; i++) {
+        i64 l = 0;
+        for (i64 j = F->Lptr[i]; j < F->Lptr[i + 1]; j++) l = std::max(l, lf[F->Lcol[j]] + 1);
+        lf[i] = l; nf = std::max(nf, l + 1);
+    }
+    for (i64 i = n - 1; i >= 0; i--) {
+        i64 l = 0;
+        for (i64 j = F->Uptr[i]; j < F->Uptr[i + 1]; j++) l = std::max(l, lb[F->Ucol[j]] + 1);
+        lb[i] = l; nb = std::max(nb, l + 1);
+    }
+    if (nf > max_levels || nb > max_levels) return 0;
+    F->levF.resize(nf); F->levB.resize(nb);
+    for (i64 i = 0; i < n; i++) { F->levF[lf[i]].push_back(i); F->levB[lb[i]].push_back(i); }
+    return nf;
+}
+static void ilu0_solve_levels(OrcIlu* F, const double* b, double* x) {
+    const int bs = F->bs, b2 = bs * bs;
+    for (const auto& rows : F->levF) {
+        const i64 nr = (i64)rows.size();
+#pragma omp parallel for schedule(static)
+        for (i64 q = 0; q < nr; q++) {
+            const i64 i = rows[q];
+            double v[ORC_MAXBS], t[ORC_MAXBS];
+            for (int e = 0; e < bs; e++) v[e] = b[i * bs + e];
+            for (i64 j = F->Lptr[i]; j < F->Lptr[i + 1]; j++) {
+                blk_mulvec(bs, &F->L[j * b2], x + F->Lcol[j] * bs, t);
+                for (int e = 0; e < bs; e++) v[e] -= t[e];
+            }
+            for (int e = 0; e < bs; e++) x[i * bs + e] = v[e];
+        }
+    }
+    for (const auto& rows : F->levB) {
+        const i64 nr = (i64)rows.size();
+#pragma omp parallel for schedule(static)
+        for (i64 q = 0; q < nr; q++) {
+            const i64 i = rows[q];
+            double v[ORC_MAXBS], t[ORC_MAXBS];
+            for (int e = 0; e < bs; e++) v[e] = x[i * bs + e];
+            for (i64 j = F->Uptr[i]; j < F->Uptr[i + 1]; j++) {
+                blk_mulvec(bs, &F->U[j * b2], x + F->Ucol[j] * bs, t);
+                for (int e = 0; e < bs; e++) v[e] -= t[e];
+            }
+            blk_mulvec(bs, &F->D[i * b2], v, t);
+            for (int e = 0; e < bs; e++) x[i * bs + e] = t[e];
+        }
+    }
+}
 // ldiv!(x, LU, b): forward with unit diagonal, then backward with inverted D.
 void orc_ilu0_solve(void* h, const double* b, double* x) {
     OrcIlu* F = (OrcIlu*)h;
     const int bs = F->bs, b2 = bs * bs;
+    if (!F->levF.empty()) { ilu0_solve_levels(F, b, x); return; }
 #pragma omp parallel for schedule(dynamic, 1)
     for (i64 blk = 0; blk < F->nblocks; blk++) {
         const auto& act = F->active[blk];

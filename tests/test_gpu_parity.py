@@ -715,3 +715,51 @@ def test_two_colour_stream_refactorisation(J, O, ctx, monkeypatch):
                 assert np.abs(out[generic][k] - fo[k]).max() <= 1e-10 * np.abs(fo[k]).max()
     for k in ("L", "U", "D"):
         assert np.abs(out[False][k] - out[True][k]).max() <= 1e-14 * np.abs(out[True][k]).max()
+
+
+@pytest.mark.gpu
+def test_config3_one_million_cells_newton_iterate(J, O, ctx):
+    """BASELINE.json config 3 at full size: 100^3 = 1M-cell permuted hex grid, one Newton iteration with ILU(0)-BiCGStab to
+    1e-8 (the product path: internal multicolour renumbering, TMA-staged kernels). The oracle runs the same elimination order
+    (the problem relabelled with the same permutation on the host), so the two Krylov solves see the same operator; parity of
+    the Newton iterate <= 1e-8, iteration counts within 10 %, first residuals to 1e-6."""
+    w = J.workloads.unstructured_hex(100, 100, 100)
+    n = w["nc"]
+    sim = J.TwoPhaseSimulator(ctx, w["N"], n, w["Tf"], w["gdz"], w["pv"], w["params"], rtol=1e-8, max_linear_iterations=1000,
+                              ordering="multicolor")
+    sim.set_forces(w["src_cells"], w["src_vals"])
+    sim.set_state(w["p0"], w["sw0"])
+    conv, err, rep = sim.perform_step(w["dt"])
+    assert not conv and rep["linear_status"] == 0, rep.get("linear_warning")
+    pg, swg = sim.get_state()
+    # oracle on the relabelled problem (new label of cell c = perm[c]; faces keep their numbers)
+    perm = sim.perm.perm
+    wp = dict(w)
+    wp["N"] = perm[w["N"] - 1]
+    inv = np.empty(n, dtype=np.int64); inv[perm - 1] = np.arange(n)
+    for k in ("pv", "p0", "sw0"):
+        wp[k] = w[k][inv]
+    src = perm[np.asarray(w["src_cells"], dtype=np.int64) - 1]
+    s = oracle_system(O, wp)
+    M0 = O.mass_2ph(wp["pv"], w["params"], wp["p0"], wp["sw0"])
+    nz, r = O.assemble_2ph(s["hf"], s["diag_pos"], s["hf_pos"], w["Tf"], w["gdz"], wp["pv"], w["params"], wp["p0"], wp["sw0"], M0, w["dt"],
+                           s["colidx"].shape[0], src, w["src_vals"])
+    assert np.abs(O.maxabs_rows(r, 2) - err).max() <= 1e-11 * np.abs(err).max()
+    ilu = O.ILU0(n, 2, s["rowptr"], s["colidx"])
+    ilu.factor(nz)
+    assert ilu.set_level_schedule() == 2      # same arithmetic as the sequential sweep, rows of a colour run concurrently
+    x, st, its, hist = O.bicgstab(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, rtol=1e-8, itmax=1000)
+    assert st == 0
+    # eight orders of magnitude of BiCGStab amplify last-bit differences: the oracle itself needs 300-370 iterations here
+    # depending on the summation order of its OpenMP reductions, so the count is compared loosely and the iterate tightly
+    assert abs(rep["linear_iterations"] - its) <= its // 4, (rep["linear_iterations"], its)
+    hg = rep["linear_residuals"]
+    assert np.abs(hg[:6] - hist[:6]).max() <= 1e-6 * hist[0]
+    assert hg[-1] <= 1e-8 * hg[0] + 1e-12
+    p = wp["p0"].copy(); sat = np.stack([wp["sw0"], 1 - wp["sw0"]], axis=1).ravel()
+    dx = -x
+    O.update_scalar(p, dx, dx_stride=2)
+    O.update_fraction_pair(sat, dx[1:], abs_max=0.2, dx_stride=2)
+    p_c, sw_c = p[perm - 1], sat[0::2][perm - 1]          # back to the caller's numbering
+    assert np.abs(pg - p_c).max() <= 1e-8 * np.abs(p_c).max()
+    assert np.abs(swg - sw_c).max() <= 1e-8

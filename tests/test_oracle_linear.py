@@ -352,3 +352,29 @@ def test_schur_complement_reduction(O, J):
     # alpha / beta form of the operator
     v = rng.standard_normal(2 * n); res0 = rng.standard_normal(2 * n)
     assert np.allclose(O.schur_mul(B, C, D, E, v, alpha=2.0, beta=-0.5, res=res0), 2.0 * O.schur_mul(B, C, D, E, v) - 0.5 * res0, rtol=1e-12)
+
+
+def test_level_scheduled_solve_is_bitwise_the_sequential_sweep(J, O):
+    """The checker's optional level schedule of ilu_solve! (rows of a dependency level concurrently) performs, row by row, the
+    operations of the sequential sweep (src/StaticCSR/ilu0.jl:156-187): x must be bitwise identical, for a multicolour
+    numbering (2 levels) and for the mesh's own numbering (many levels)."""
+    w = J.workloads.unstructured_hex(14, 12, 10)
+    n = w["nc"]
+    for relabel in (True, False):
+        wp = dict(w)
+        if relabel:
+            perm, ncol = J.multicolor_ordering(w["N"], n)
+            wp["N"] = perm[w["N"] - 1]
+        s = oracle_system(O, wp)
+        rng = np.random.default_rng(5)
+        nz = rng.standard_normal(s["colidx"].shape[0] * 4).reshape(-1, 4)
+        nz[s["diag_pos"] - 1] += np.array([25.0, 0.0, 0.0, 25.0])
+        ilu = O.ILU0(n, 2, s["rowptr"], s["colidx"])
+        assert ilu.factor(nz.ravel()) == 0
+        b = rng.standard_normal(2 * n)
+        x_seq = ilu.solve(b)
+        nlev = ilu.set_level_schedule(True, max_levels=10000)
+        assert nlev == (2 if relabel else nlev) and nlev >= 2
+        assert np.array_equal(ilu.solve(b), x_seq)
+        assert ilu.set_level_schedule(True, max_levels=1) == 0          # refused: too many levels, sequential sweep stays
+        assert np.array_equal(ilu.solve(b), x_seq)
