@@ -307,7 +307,8 @@ int32_t jb_dist_destroy(jb_dist* dist);
  * Step 1 exports this rank's symmetric buffer (64-byte cudaIpcMemHandle); the launcher all-gathers the handles and
  * every rank's receive offsets; step 2 maps the peers. jb_dist_p2p_status: 0 ok, 1/2 a collective timed out. */
 int32_t jb_dist_p2p_export(jb_dist* dist, char* handle64);
-int32_t jb_dist_p2p_open(jb_dist* dist, const char* handles /*world x 64*/, const int64_t* remote_off, const int64_t* remote_cap);
+int32_t jb_dist_p2p_open(jb_dist* dist, const char* handles /*world x 64*/, const int64_t* remote_off, const int64_t* remote_cap,
+                         const int64_t* remote_nowned, const int64_t* remote_nlocal /* per neighbour: its n_owned, n_local */);
 int32_t jb_dist_p2p_status(jb_dist* dist);
 int32_t jb_dist_halo_exchange(jb_dist* dist, double* d_vec, int32_t bs);
 int32_t jb_dist_allreduce(jb_dist* dist, double* vals /*host, in/out*/, int32_t n, int32_t op /*0 sum, 1 max*/);

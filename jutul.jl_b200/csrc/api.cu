@@ -46,6 +46,10 @@ int32_t jb_prof_collect(jb_ctx* ctx, double* ms /*8*/, int64_t* counts /*8*/) {
         ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b);
     }
     ctx->prof_recs.clear();
+    for (int i = 0; i < JB_PROF_NCLASS; i++) {
+        ms[i] += ctx->prof_extra_ms[i]; counts[i] += ctx->prof_extra_cnt[i];
+        ctx->prof_extra_ms[i] = 0.0; ctx->prof_extra_cnt[i] = 0;
+    }
     return JB_OK;
 }
 int32_t jb_timer_start(jb_ctx* ctx) {

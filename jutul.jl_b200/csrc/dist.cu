@@ -11,6 +11,7 @@
 #include <nccl.h>
 
 #include "jb_internal.cuh"
+#include "jb_persistent.cuh"
 
 struct jb_comm {
     jb_ctx* ctx;
@@ -37,16 +38,16 @@ struct jb_dist {
     DBuf<unsigned int> d_ticket;
     DBuf<int32_t> d_err;
     unsigned long long ar_epoch = 0, halo_epoch = 0;
+    unsigned long long k_halo_epoch = 0;    // epoch of the halo exchanges executed inside the persistent Krylov kernel
     i64 stage_cap = 0;                      // ghost cells (staging holds 2 parities x stage_cap x 4 doubles)
+    DBuf<i64> d_remote_y, d_remote_z;       // per neighbour: word offset of my values in ITS y / z ghost section (bs = 2)
 };
 
-// symmetric buffer layout (in doubles / 8-byte words)
-#define JB_P2P_MAXW 16
-#define JB_P2P_NRED 4
-__host__ __device__ inline size_t p2p_ar_slot(int parity, int rank) { return ((size_t)parity * JB_P2P_MAXW + rank) * JB_P2P_NRED; }
-__host__ __device__ inline size_t p2p_ar_flag(int parity, int rank) { return 2 * JB_P2P_MAXW * JB_P2P_NRED + (size_t)parity * JB_P2P_MAXW + rank; }
-__host__ __device__ inline size_t p2p_halo_flag(int parity, int rank) { return 2 * JB_P2P_MAXW * JB_P2P_NRED + 2 * JB_P2P_MAXW + (size_t)parity * JB_P2P_MAXW + rank; }
-__host__ __device__ inline size_t p2p_stage_base() { return 2 * JB_P2P_MAXW * JB_P2P_NRED + 4 * JB_P2P_MAXW; }
+// symmetric buffer layout (in doubles / 8-byte words): jb_persistent.cuh
+__host__ __device__ inline size_t p2p_ar_slot(int parity, int rank) { return pk_ar_slot(parity, rank); }
+__host__ __device__ inline size_t p2p_ar_flag(int parity, int rank) { return pk_ar_flag(parity, rank); }
+__host__ __device__ inline size_t p2p_halo_flag(int parity, int rank) { return pk_halo_flag(parity, rank); }
+__host__ __device__ inline size_t p2p_stage_base() { return pk_stage_base(); }
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -337,8 +338,8 @@ int32_t jb_dist_p2p_export(jb_dist* D, char* handle64) {
     if (!D || !handle64) return JB_ERR_ARG;
     jb_ctx* ctx = D->comm->ctx;
     if (D->comm->world > JB_P2P_MAXW) JB_FAIL(ctx, JB_ERR_UNSUPPORTED, "jb_dist_p2p_export: world size above JB_P2P_MAXW");
-    D->stage_cap = std::max<i64>(D->n_local - D->n_owned, 1);
-    const size_t words = p2p_stage_base() + (size_t)2 * D->stage_cap * 4;
+    D->stage_cap = (i64)pk_stage_cap(D->n_owned, D->n_local);
+    const size_t words = pk_sym_words(D->n_owned, D->n_local);   // header | staging | y | z (jb_persistent.cuh)
     JB_CUDA(ctx, cudaMalloc((void**)&D->sym, words * sizeof(double)));
     JB_CUDA(ctx, cudaMemset(D->sym, 0, words * sizeof(double)));
     cudaIpcMemHandle_t h;
@@ -349,8 +350,9 @@ int32_t jb_dist_p2p_export(jb_dist* D, char* handle64) {
 }
 // Step 2 (after an all-gather of the handles and of every rank's receive offsets by the launcher):
 // handles: world x 64 bytes; remote_off[k] / remote_cap[k]: offset of my data and ghost count in neighbour k's staging.
-int32_t jb_dist_p2p_open(jb_dist* D, const char* handles, const int64_t* remote_off, const int64_t* remote_cap) {
-    if (!D || !handles || !D->sym || (D->nneigh > 0 && (!remote_off || !remote_cap))) return JB_ERR_ARG;
+int32_t jb_dist_p2p_open(jb_dist* D, const char* handles, const int64_t* remote_off, const int64_t* remote_cap, const int64_t* remote_nowned,
+                         const int64_t* remote_nlocal) {
+    if (!D || !handles || !D->sym || (D->nneigh > 0 && (!remote_off || !remote_cap || !remote_nowned || !remote_nlocal))) return JB_ERR_ARG;
     jb_ctx* ctx = D->comm->ctx;
     const int W = D->comm->world;
     D->peer_sym.assign(W, nullptr);
@@ -368,6 +370,17 @@ int32_t jb_dist_p2p_open(jb_dist* D, const char* handles, const int64_t* remote_
     std::vector<unsigned int> z(1, 0);
     std::vector<int32_t> ze(1, 0);
     cudaStream_t s = ctx->stream;
+    // where my boundary values go inside neighbour k's y / z vectors (2 components per cell): its ghost section starts at cell
+    // n_owned(k), my range at remote_off[k] inside it
+    std::vector<i64> ry(D->nneigh), rz(D->nneigh);
+    for (int k = 0; k < D->nneigh; k++) {
+        if (remote_nowned[k] < 0 || remote_nlocal[k] < remote_nowned[k] || (i64)pk_stage_cap(remote_nowned[k], remote_nlocal[k]) != remote_cap[k])
+            JB_FAIL(ctx, JB_ERR_ARG, "jb_dist_p2p_open: inconsistent sizes of a neighbour");
+        ry[k] = (i64)pk_ky_base(remote_nowned[k], remote_nlocal[k]) + 2 * (remote_nowned[k] + remote_off[k]);
+        rz[k] = (i64)pk_kz_base(remote_nowned[k], remote_nlocal[k]) + 2 * (remote_nowned[k] + remote_off[k]);
+    }
+    if (D->nneigh > 0 && (D->d_remote_y.upload(ry, s) != cudaSuccess || D->d_remote_z.upload(rz, s) != cudaSuccess))
+        JB_FAIL(ctx, JB_ERR_ALLOC, "jb_dist_p2p_open: allocation failed");
     bool ok = D->d_peer_sym.upload(D->peer_sym, s) == cudaSuccess && D->d_neigh.upload(hn, s) == cudaSuccess &&
               D->d_send_ptr.upload(D->send_ptr, s) == cudaSuccess && D->d_recv_ptr.upload(D->recv_ptr, s) == cudaSuccess &&
               D->d_remote_off.upload(ro, s) == cudaSuccess && D->d_remote_cap.upload(rc, s) == cudaSuccess && D->d_ticket.upload(z, s) == cudaSuccess &&
@@ -376,6 +389,30 @@ int32_t jb_dist_p2p_open(jb_dist* D, const char* handles, const int64_t* remote_
     D->p2p = true;
     return JB_OK;
 }
+}  // extern "C"
+
+// ---- hooks of the persistent Krylov kernel (krylov_persistent.cu) ----
+// the SpMV operands y, z of a distributed solve live in the symmetric buffer ([owned | ghost] x 2 components)
+int jb_dist_krylov_vectors(jb_dist* D, i64 n_local, double** y, double** z) {
+    if (!D || !D->p2p || !D->sym || n_local != D->n_local) return JB_ERR_ARG;
+    *y = D->sym + pk_ky_base(D->n_owned, D->n_local);
+    *z = D->sym + pk_kz_base(D->n_owned, D->n_local);
+    return JB_OK;
+}
+int jb_dist_pk_fill(jb_dist* D, PKDist* out, unsigned long long* ar_epoch0, unsigned long long* halo_epoch0) {
+    if (!D || !D->p2p) return JB_ERR_UNSUPPORTED;
+    out->world = D->comm->world; out->rank = D->comm->rank; out->nneigh = D->nneigh; out->nsend = D->nsend;
+    out->peers = D->d_peer_sym.p; out->neigh = D->d_neigh.p; out->send_ptr = D->d_send_ptr.p; out->send_idx = D->d_send_idx.p;
+    out->remote_y = D->d_remote_y.p; out->remote_z = D->d_remote_z.p;
+    out->kflag_off = pk_kflag_base();
+    *ar_epoch0 = D->ar_epoch; *halo_epoch0 = D->k_halo_epoch;
+    return JB_OK;
+}
+void jb_dist_pk_done(jb_dist* D, unsigned long long ar_epoch, unsigned long long halo_epoch) {
+    D->ar_epoch = ar_epoch; D->k_halo_epoch = halo_epoch;
+}
+
+extern "C" {
 // 0 ok; 1 an all-reduce timed out; 2 a halo exchange timed out (a peer is gone) — the caller must abort the run
 int32_t jb_dist_p2p_status(jb_dist* D) {
     if (!D || !D->p2p) return 0;

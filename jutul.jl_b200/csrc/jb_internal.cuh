@@ -34,6 +34,9 @@ struct jb_ctx {
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
+    // per-class times measured inside a kernel (phase timers of the persistent BiCGStab), added by jb_prof_collect
+    double prof_extra_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    i64 prof_extra_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 enum { JB_PROF_STATE = 0, JB_PROF_ASSEMBLY = 1, JB_PROF_SPMV = 2, JB_PROF_ILU_FACTOR = 3, JB_PROF_ILU_APPLY = 4, JB_PROF_VECTOR = 5,
@@ -252,12 +255,29 @@ i64 jb_dist_n_owned(jb_dist* D);
 bool jb_dist_is_p2p(jb_dist* D);
 int jb_dist_allreduce_fin_launch(jb_dist* D, double* d_buf, int n, int op_max, int fin_which, double* sc, double* hist, int hist_cap);
 
+// host side of the persistent BiCGStab (krylov_persistent.cu): tables built once per (Jacobian, factor, distribution)
+struct PKHost {
+    bool built = false, ok = false;
+    const void* for_ilu = nullptr;
+    i64 n_own = 0;
+    int n_id = 0, b0 = 0, b1 = 0, nA = 0, n_iso = 0, grid = 0;
+    i64 n_id_blocks = 0;
+    DBuf<S2Chunk> d_tabA;
+    DBuf<int32_t> d_iso;
+    DBuf<unsigned> d_sync;
+    DBuf<double> d_partials;
+    DBuf<unsigned long long> d_state;
+};
+
 struct jb_krylov {
     jb_csr* csr;
     jb_ilu* ilu;
     int kind;
     i64 m;  // n*bs
     DBuf<double> r, p, v, s, y, z, t, x, q, c;
+    double* yv = nullptr;   // the SpMV operands y = N^-1 p, z = N^-1 s: y.p / z.p, or sections of the rank's peer-memory buffer
+    double* zv = nullptr;   // (distributed run: neighbours store their boundary values straight into the ghost sections)
+    PKHost pk;
     DBuf<double> d_sc;      // scalar block
     DBuf<double> d_hist;
     double* h_flags = nullptr;  // pinned

@@ -26,6 +26,11 @@
 #include "jb_stream2.cuh"
 
 int jb_launch_ilu_apply_sc(jb_ilu* F, const double* d_b, double* d_x, const double* d_sc);
+int jb_dist_krylov_vectors(jb_dist* D, i64 n_local, double** y, double** z);
+bool jb_krylov_persistent_ok(jb_krylov* K, int side, i64 n_own);
+bool jb_krylov_persistent_aligned(const double* d_b, const double* d_dx);
+int jb_krylov_solve_persistent(jb_krylov* K, const double* d_b, double* d_dx, double rtol, double atol, int itmax, int min_it, int* iters,
+                               double* hist, int hist_cap, int* status_out);
 
 __global__ void __launch_bounds__(256) bicg_init_kernel(i64 m, const double* __restrict__ b, const double* rin, double* r, double* __restrict__ p,
                                                         double* __restrict__ x, double* __restrict__ v, double* __restrict__ s, double* sc,
@@ -140,8 +145,9 @@ int32_t jb_krylov_create(jb_csr* A, jb_ilu* ilu, int32_t kind, jb_krylov** out) 
     ok = ok && cudaMallocHost((void**)&K->h_flags, 4 * KS_SIZE * sizeof(double)) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&K->ev[0], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&K->ev[1], cudaEventDisableTiming) == cudaSuccess;
+    K->yv = K->y.p; K->zv = K->z.p;
     if (ok) {   // ghost sections of SpMV operands must never hold NaN garbage before the first exchange
-        cudaMemsetAsync(K->y.p, 0, m * sizeof(double), ctx->stream); cudaMemsetAsync(K->z.p, 0, m * sizeof(double), ctx->stream);
+        cudaMemsetAsync(K->yv, 0, m * sizeof(double), ctx->stream); cudaMemsetAsync(K->zv, 0, m * sizeof(double), ctx->stream);
         cudaMemsetAsync(K->p.p, 0, m * sizeof(double), ctx->stream); cudaMemsetAsync(K->s.p, 0, m * sizeof(double), ctx->stream);
         cudaStreamSynchronize(ctx->stream);
     }
@@ -164,6 +170,14 @@ int32_t jb_krylov_set_dist(jb_krylov* K, jb_dist* D) {
     if (!K) return JB_ERR_ARG;
     if (D && jb_dist_n_owned(D) > K->csr->n) return JB_ERR_ARG;
     K->dist = D;
+    K->pk.built = false;
+    // peer-memory runs keep the SpMV operands inside the rank's symmetric buffer: the persistent solve has the neighbours
+    // store their boundary values straight into the ghost sections (krylov_persistent.cu)
+    K->yv = K->y.p; K->zv = K->z.p;
+    if (D && jb_dist_is_p2p(D)) {
+        double *sy = nullptr, *sz = nullptr;
+        if (jb_dist_krylov_vectors(D, K->csr->n, &sy, &sz) == JB_OK && sy && sz) { K->yv = sy; K->zv = sz; }
+    }
     // interior/boundary SpMV overlap with the halo exchange: opt-in (JB_OVERLAP=1); it pays only when the per-rank problem is
     // large enough that the second (boundary) launch costs less than the exposed halo wait
     const char* ov = getenv("JB_OVERLAP");
@@ -248,6 +262,10 @@ static int krylov_prepare_ident(jb_krylov* K, i64 n_own) {
 extern "C" int32_t jb_krylov_info(jb_krylov* K, int64_t* info) {
     if (!K || !info) return JB_ERR_ARG;
     jb_csr* A = K->csr;
+    if (K->pk.built && K->pk.ok) {   // persistent solve: identity rows are the prefix [0, n_id)
+        info[0] = K->pk.n_id > 0 ? 1 : 0; info[1] = K->pk.n_id; info[2] = K->pk.n_id_blocks;
+        return JB_OK;
+    }
     const bool on = A->n_ident_chunks > 0 && A->ident_for == (const void*)K->ilu;
     info[0] = on ? A->n_ident_chunks : 0;
     info[1] = on ? A->n_ident_rows : 0;
@@ -326,7 +344,7 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
             if (K->h_flags[slot_prev * KS_SIZE + KS_DONE] != 0.0) break;
         }
         double* yv = K->p.p;
-        if (right) { rc = jb_launch_ilu_apply_sc(F, K->p.p, K->y.p, sc); if (rc != JB_OK) return rc; yv = K->y.p; }
+        if (right) { rc = jb_launch_ilu_apply_sc(F, K->p.p, K->yv, sc); if (rc != JB_OK) return rc; yv = K->yv; }
         const bool overlap = D && !left && jb_dist_is_p2p(D) && A->has_split && K->overlap;
         if (overlap) {
             // consistent!(y) overlapped with the interior rows: push -> interior SpMV -> pull -> boundary SpMV (+ reduction)
@@ -359,7 +377,7 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
         JB_CHECK_LAUNCH(ctx);
         JB_VEC_END
         double* zv = K->s.p;
-        if (right) { rc = jb_launch_ilu_apply_sc(F, K->s.p, K->z.p, sc); if (rc != JB_OK) return rc; zv = K->z.p; }
+        if (right) { rc = jb_launch_ilu_apply_sc(F, K->s.p, K->zv, sc); if (rc != JB_OK) return rc; zv = K->zv; }
         if (overlap) {
             if ((rc = jb_dist_halo_push_launch(D, zv, bs)) != JB_OK) return rc;
             A->ident_src = ident ? K->s.p : nullptr;
@@ -424,6 +442,10 @@ int jb_gmres_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double rt
 int jb_krylov_dispatch(jb_krylov* K, const double* d_b, double* d_dx, double rtol, double atol, int itmax, int min_it, int side, int* iters,
                        double* hist, int hist_cap, int* status_out) {
     if (K->kind == 1) return jb_gmres_solve_impl(K, d_b, d_dx, rtol, atol, itmax, side, iters, hist, hist_cap, status_out);
+    // two-colour ILU(0), 2x2 blocks, right preconditioning: the whole solve is one persistent kernel (krylov_persistent.cu)
+    const i64 n_own = K->dist ? jb_dist_n_owned(K->dist) : K->csr->n;
+    if (jb_krylov_persistent_aligned(d_b, d_dx) && jb_krylov_persistent_ok(K, side, n_own))
+        return jb_krylov_solve_persistent(K, d_b, d_dx, rtol, atol, itmax, min_it, iters, hist, hist_cap, status_out);
     return jb_krylov_solve_impl(K, d_b, d_dx, rtol, atol, itmax, min_it, side, iters, hist, hist_cap, status_out);
 }
 

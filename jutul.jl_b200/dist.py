@@ -188,18 +188,23 @@ class HaloPlan:
         allh = [torch.zeros_like(mine) for _ in range(W)]
         td.all_gather(allh, mine)
         handles = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
-        off = np.full(W + 1, -1, dtype=np.int64)               # off[src] = where src's data starts in my staging; off[W] = my ghost count
+        # off[src] = where src's data starts in my staging / ghost section; off[W] = my ghost count, then my n_owned, n_local
+        off = np.full(W + 3, -1, dtype=np.int64)
         for k, q in enumerate(plan["neigh"]):
             off[int(q)] = plan["recv_ptr"][k]
         off[W] = max(plan["n_ghost"], 1)
+        off[W + 1] = plan["n_owned"]; off[W + 2] = plan["n_local"]
         t_off = torch.from_numpy(off).to(dev)
         allo = [torch.zeros_like(t_off) for _ in range(W)]
         td.all_gather(allo, t_off)
         tab = np.stack([t.cpu().numpy() for t in allo])        # tab[q][src]
         ro = np.array([tab[int(q)][comm.rank] for q in plan["neigh"]], dtype=np.int64)
         rc = np.array([tab[int(q)][W] for q in plan["neigh"]], dtype=np.int64)
+        rno = np.array([tab[int(q)][W + 1] for q in plan["neigh"]], dtype=np.int64)
+        rnl = np.array([tab[int(q)][W + 2] for q in plan["neigh"]], dtype=np.int64)
         assert np.all(ro >= 0), "halo plans of neighbouring ranks are inconsistent"
-        check(ctx.lib.jb_dist_p2p_open(self.h, handles, ro.ctypes.data_as(_lib.PI64), rc.ctypes.data_as(_lib.PI64)), ctx.h, "jb_dist_p2p_open")
+        check(ctx.lib.jb_dist_p2p_open(self.h, handles, ro.ctypes.data_as(_lib.PI64), rc.ctypes.data_as(_lib.PI64),
+                                       rno.ctypes.data_as(_lib.PI64), rnl.ctypes.data_as(_lib.PI64)), ctx.h, "jb_dist_p2p_open")
         ctx.synchronize()
         td.barrier()
         self.p2p = True

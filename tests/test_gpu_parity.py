@@ -751,15 +751,23 @@ def test_config3_one_million_cells_newton_iterate(J, O, ctx):
     x, st, its, hist = O.bicgstab(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, rtol=1e-8, itmax=1000)
     assert st == 0
     # eight orders of magnitude of BiCGStab amplify last-bit differences: the oracle itself needs 300-370 iterations here
-    # depending on the summation order of its OpenMP reductions, so the count is compared loosely and the iterate tightly
+    # depending on the summation order of its OpenMP reductions, so the count is compared loosely
     assert abs(rep["linear_iterations"] - its) <= its // 4, (rep["linear_iterations"], its)
     hg = rep["linear_residuals"]
     assert np.abs(hg[:6] - hist[:6]).max() <= 1e-6 * hist[0]
     assert hg[-1] <= 1e-8 * hg[0] + 1e-12
+    # Both solves stop at |r_k| <= 1e-8 |r_0|, so the two increments differ by a vector d with |J d| <= 2e-8 |r| — the bound that
+    # does not depend on the conditioning of J (which is why 1e-8 on the iterate itself, met at 540 cells in
+    # test_newton_step_matches_oracle, cannot hold for ANY two differently rounded solves at 1M cells: cond(J N^-1) ~ 1e2).
+    dx_g = sim.dx.get()                                   # device numbering = numbering of the oracle's relabelled problem
+    d = dx_g - (-x)
+    Jd = O.spmv(n, 2, s["rowptr"], s["colidx"], nz, d)
+    assert np.linalg.norm(Jd) <= 3e-8 * np.linalg.norm(r), np.linalg.norm(Jd) / np.linalg.norm(r)
     p = wp["p0"].copy(); sat = np.stack([wp["sw0"], 1 - wp["sw0"]], axis=1).ravel()
     dx = -x
     O.update_scalar(p, dx, dx_stride=2)
     O.update_fraction_pair(sat, dx[1:], abs_max=0.2, dx_stride=2)
     p_c, sw_c = p[perm - 1], sat[0::2][perm - 1]          # back to the caller's numbering
-    assert np.abs(pg - p_c).max() <= 1e-8 * np.abs(p_c).max()
-    assert np.abs(swg - sw_c).max() <= 1e-8
+    # Newton iterate: the increments agree to (error amplification) x rtol; measured 3e-7 of |p|, bound 2e-6
+    assert np.abs(pg - p_c).max() <= 2e-6 * np.abs(p_c).max()
+    assert np.abs(swg - sw_c).max() <= 2e-6
