@@ -74,7 +74,7 @@ void* jb_stream(jb_ctx* ctx);
 int32_t jb_timer_start(jb_ctx* ctx);
 int32_t jb_timer_stop(jb_ctx* ctx, double* ms);
 int32_t jb_prof_enable(jb_ctx* ctx, int32_t on);
-int32_t jb_prof_collect(jb_ctx* ctx, double* ms /*8*/, int64_t* counts /*8*/);
+int32_t jb_prof_collect(jb_ctx* ctx, double* ms /*9*/, int64_t* counts /*9*/);
 
 /* ---- device memory: transfer(context, x) (src/context.jl:11-60) ----------- */
 int32_t jb_malloc(jb_ctx* ctx, int64_t bytes, void** d_out);
@@ -242,8 +242,15 @@ int32_t jb_krylov_solve(jb_krylov* ks, const double* d_r, double* d_dx, double r
 int32_t jb_krylov_set_gmres(jb_krylov* ks, int32_t memory, int32_t restart, int32_t flexible);
 /* info[0..2] = stream chunks / rows / blocks of the Jacobian whose product in the right-preconditioned operator
  * A N^{-1} w is read off w (first-colour rows of a two-colour ILU(0), see krylov.cu; 0 when not applicable or
- * switched off with JB_RB_IDENTITY=0). Valid after the first solve; used for the byte accounting of bench.py. */
-int32_t jb_krylov_info(jb_krylov* ks, int64_t* info);
+ * switched off with JB_RB_IDENTITY=0). info[3] = 1 when the fused iteration kernel (csrc/krylov_persistent.cu) is the
+ * active path, then info[4..7] = rows of the second colour (b1 - b0), rows entering updates and inner products (owned),
+ * CTAs of the cooperative grid, rows with neither L nor U entries. Valid after the first solve; used for the byte
+ * accounting of bench.py. */
+int32_t jb_krylov_info(jb_krylov* ks, int64_t* info /*8*/);
+/* profiling (jb_prof_enable): per-phase device time in ms of the fused BiCGStab iteration kernel (csrc/krylov_persistent.cu),
+ * measured with %globaltimer between the grid barriers: out[0..11] = init, A1, A2, A3, V1, A4, A5, A6, V2, V3, halo pushes,
+ * final; out[12] = iterations, out[13] = solves covered. Clears the accumulators. */
+int32_t jb_krylov_phase_times(jb_krylov* ks, double* out /*14*/);
 
 /* ---- apply_scaling_to_linearized_system! (src/linsolve/default.jl:325-385):
  *      kind 0 none, 1 diagonal (block rows scaled by inv(D_ii)), 2 dt (J, r *= dt). */

@@ -392,6 +392,10 @@ class _DiagonalPreconditioner(ILUZeroPreconditioner):
         return dict(D=D)
 
 
+PHASE_NAMES = ("init", "A1_sweep_L_y", "A2_sweep_U_y", "A3_spmv_v", "V1_s", "A4_sweep_L_z", "A5_sweep_U_z", "A6_spmv_t", "V2_x_r", "V3_p",
+               "halo_push", "final")
+
+
 class JacobiPreconditioner(_DiagonalPreconditioner):
     """JacobiPreconditioner(w = 2/3) (src/linsolve/precond/jacobi.jl)."""
     _kind = 1
@@ -426,12 +430,31 @@ class GenericKrylov(_Handle):
         if kind == 1:
             check(self.ctx.lib.jb_krylov_set_gmres(h, int(memory), int(bool(restart)), int(solver == "fgmres")), self.ctx.h, "jb_krylov_set_gmres")
 
+    def phase_times(self):
+        """Per-phase device times (ms per iteration) of the fused iteration kernel since the last call (profiling enabled)."""
+        out = (C.c_double * 14)()
+        check(self.ctx.lib.jb_krylov_phase_times(self.h, out), self.ctx.h, "jb_krylov_phase_times")
+        its = max(out[12], 1.0)
+        d = {n: out[i] / (its if n not in ("init", "final") else max(out[13], 1.0)) for i, n in enumerate(PHASE_NAMES)}
+        d["iterations"] = int(out[12]); d["solves"] = int(out[13])
+        return d
+
     def identity_info(self):
         """(chunks, rows, blocks) of the Jacobian whose product in A*N^-1*w is read off w (two-colour ILU(0),
         right preconditioning; see csrc/krylov.cu). Valid after the first solve."""
-        info = (C.c_int64 * 3)()
+        info = (C.c_int64 * 8)()
         check(self.ctx.lib.jb_krylov_info(self.h, info), self.ctx.h, "jb_krylov_info")
         return int(info[0]), int(info[1]), int(info[2])
+
+    def fused_info(self):
+        """None, or the structure of the fused iteration kernel's problem (after the first solve): identity rows and their
+        blocks, rows of the second colour, owned rows, CTAs of the cooperative grid, isolated rows."""
+        info = (C.c_int64 * 8)()
+        check(self.ctx.lib.jb_krylov_info(self.h, info), self.ctx.h, "jb_krylov_info")
+        if not info[3]:
+            return None
+        return dict(identity_rows=int(info[1]), identity_blocks=int(info[2]), second_colour_rows=int(info[4]), owned_rows=int(info[5]),
+                    grid=int(info[6]), isolated_rows=int(info[7]))
 
 
 def linear_solve(krylov, r, dx, rtol=None, atol=None, update_preconditioner=True, status_reduce=None):
@@ -586,7 +609,7 @@ class CellPermutation(_Handle):
 class DeviceProfile:
     """Per-kernel-class device times (CUDA events on the context's stream)."""
 
-    CLASSES = ("state", "assembly", "spmv", "ilu_factor", "ilu_apply", "vector", "newton", "other")
+    CLASSES = ("state", "assembly", "spmv", "ilu_factor", "ilu_apply", "vector", "newton", "other", "fused_solve")
 
     def __init__(self, ctx):
         self.ctx = ctx
@@ -599,7 +622,7 @@ class DeviceProfile:
         self.ctx.lib.jb_prof_enable(self.ctx.h, 0)
 
     def collect(self):
-        ms = np.zeros(8); cnt = np.zeros(8, dtype=i64)
+        ms = np.zeros(9); cnt = np.zeros(9, dtype=i64)
         check(self.ctx.lib.jb_prof_collect(self.ctx.h, _pd(ms), _pi(cnt)), self.ctx.h, "jb_prof_collect")
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.CLASSES)}
 

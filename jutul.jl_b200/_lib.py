@@ -83,6 +83,7 @@ PROTOTYPES = {
     "jb_krylov_destroy": (I32, [P]),
     "jb_krylov_solve": (I32, [P, P, P, F64, F64, I32, I32, I32, PI32, PF64, I32]),
     "jb_krylov_info": (I32, [P, PI64]),
+    "jb_krylov_phase_times": (I32, [P, PF64]),
     "jb_krylov_set_gmres": (I32, [P, I32, I32, I32]),
     "jb_scale_system": (I32, [P, P, I32, F64]),
     "jb_update_scalar": (I32, [P, P, P, I64, I64, F64, F64, F64, F64, F64, F64]),

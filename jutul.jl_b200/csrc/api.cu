@@ -36,7 +36,7 @@ int32_t jb_prof_enable(jb_ctx* ctx, int32_t on) {
     return JB_OK;
 }
 // Sums the recorded per-class kernel times (ms) and launch-group counts since the last call, then clears them.
-int32_t jb_prof_collect(jb_ctx* ctx, double* ms /*8*/, int64_t* counts /*8*/) {
+int32_t jb_prof_collect(jb_ctx* ctx, double* ms /*9*/, int64_t* counts /*9*/) {
     if (!ctx || !ms || !counts) return JB_ERR_ARG;
     JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < JB_PROF_NCLASS; i++) { ms[i] = 0.0; counts[i] = 0; }

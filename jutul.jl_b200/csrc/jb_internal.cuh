@@ -35,12 +35,13 @@ struct jb_ctx {
     std::vector<cudaEvent_t> prof_pool;
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     // per-class times measured inside a kernel (phase timers of the persistent BiCGStab), added by jb_prof_collect
-    double prof_extra_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    i64 prof_extra_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double prof_extra_ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    i64 prof_extra_cnt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 enum { JB_PROF_STATE = 0, JB_PROF_ASSEMBLY = 1, JB_PROF_SPMV = 2, JB_PROF_ILU_FACTOR = 3, JB_PROF_ILU_APPLY = 4, JB_PROF_VECTOR = 5,
-       JB_PROF_NEWTON = 6, JB_PROF_OTHER = 7, JB_PROF_NCLASS = 8 };
+       JB_PROF_NEWTON = 6, JB_PROF_OTHER = 7,
+       JB_PROF_FUSED_SOLVE = 8 /* all launches of one fused-kernel BiCGStab solve, event-timed */, JB_PROF_NCLASS = 9 };
 
 void jb_prof_begin(jb_ctx* ctx, int cls);
 void jb_prof_end(jb_ctx* ctx);
@@ -267,6 +268,8 @@ struct PKHost {
     DBuf<unsigned> d_sync;
     DBuf<double> d_partials;
     DBuf<unsigned long long> d_state;
+    double phase_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // profiling: per-phase device time of the fused kernel
+    i64 phase_iters = 0, phase_solves = 0;
 };
 
 struct jb_krylov {

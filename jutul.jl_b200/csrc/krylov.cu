@@ -262,8 +262,10 @@ static int krylov_prepare_ident(jb_krylov* K, i64 n_own) {
 extern "C" int32_t jb_krylov_info(jb_krylov* K, int64_t* info) {
     if (!K || !info) return JB_ERR_ARG;
     jb_csr* A = K->csr;
-    if (K->pk.built && K->pk.ok) {   // persistent solve: identity rows are the prefix [0, n_id)
+    for (int q = 3; q < 8; q++) info[q] = 0;
+    if (K->pk.built && K->pk.ok) {   // fused iteration kernel: identity rows are the prefix [0, n_id)
         info[0] = K->pk.n_id > 0 ? 1 : 0; info[1] = K->pk.n_id; info[2] = K->pk.n_id_blocks;
+        info[3] = 1; info[4] = K->pk.b1 - K->pk.b0; info[5] = K->pk.n_own; info[6] = K->pk.grid; info[7] = K->pk.n_iso;
         return JB_OK;
     }
     const bool on = A->n_ident_chunks > 0 && A->ident_for == (const void*)K->ilu;

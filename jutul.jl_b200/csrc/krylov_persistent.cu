@@ -653,6 +653,15 @@ bool jb_krylov_persistent_ok(jb_krylov* K, int side, i64 n_own) {
     if (K->dist && !jb_dist_is_p2p(K->dist)) return false;
     return pk_prepare(K, n_own);
 }
+// per-phase device times (ms) of the fused iteration kernel accumulated while profiling is enabled:
+// out[0..11] = init, A1, A2, A3, V1, A4, A5, A6, V2, V3, halo pushes, final; out[12] = iterations, out[13] = solves. Clears.
+extern "C" int32_t jb_krylov_phase_times(jb_krylov* K, double* out) {
+    if (!K || !out) return JB_ERR_ARG;
+    for (int q = 0; q < 12; q++) { out[q] = K->pk.phase_ms[q]; K->pk.phase_ms[q] = 0.0; }
+    out[12] = (double)K->pk.phase_iters; out[13] = (double)K->pk.phase_solves;
+    K->pk.phase_iters = 0; K->pk.phase_solves = 0;
+    return JB_OK;
+}
 bool jb_krylov_persistent_aligned(const double* d_b, const double* d_dx) {
     return (((uintptr_t)d_b | (uintptr_t)d_dx) & 15) == 0;   // vectors are streamed as double2
 }
@@ -709,6 +718,7 @@ int jb_krylov_solve_persistent(jb_krylov* K, const double* d_b, double* d_dx, do
     // iteration it-2 (same pinned slot this iteration reuses); a launch that finds the solve finished returns at once.
     int kflags = 1;
     void* kargs[] = {(void*)&a, (void*)&kflags};
+    if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_FUSED_SOLVE);
     for (int it = 1; it <= std::max(itmax, 1); it++) {
         if (it >= 3) {     // (it = 2: no flags of this solve exist in that slot yet)
             const int slot_prev = it & 1;
@@ -722,6 +732,7 @@ int jb_krylov_solve_persistent(jb_krylov* K, const double* d_b, double* d_dx, do
         JB_CUDA(ctx, cudaMemcpyAsync(K->h_flags + slot * KS_SIZE, K->d_sc.p, KS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
         JB_CUDA(ctx, cudaEventRecord(K->ev[slot], st));
     }
+    if (ctx->prof_on) jb_prof_end(ctx);
     JB_CUDA(ctx, cudaMemcpyAsync(K->h_flags + 3 * KS_SIZE, K->d_sc.p, KS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
     unsigned long long h_state[PH_COUNT + 4];
     unsigned h_sync[8];
@@ -746,6 +757,8 @@ int jb_krylov_solve_persistent(jb_krylov* K, const double* d_b, double* d_dx, do
     if (ctx->prof_on) {
         const unsigned long long* ns = h_state + 4;
         const double ms = 1e-6;
+        for (int q = 0; q < PH_COUNT; q++) H.phase_ms[q] += ms * (double)ns[q];
+        H.phase_iters += niter; H.phase_solves += 1;
         ctx->prof_extra_ms[JB_PROF_ILU_APPLY] += ms * (double)(ns[PH_A1] + ns[PH_A2] + ns[PH_A4] + ns[PH_A5]);
         ctx->prof_extra_cnt[JB_PROF_ILU_APPLY] += 2 * niter;
         ctx->prof_extra_ms[JB_PROF_SPMV] += ms * (double)(ns[PH_A3] + ns[PH_A6]);

@@ -338,19 +338,41 @@ def run_bench(args, J):
     dt = w["dt"]
     p_init, s_init = ctx.transfer(sim.p.get()), ctx.transfer(sim.s.get())
 
+    unconverged = [0]
+
     def step(solve=True):
         conv, e, rep = sim.perform_step(dt, solve=solve)
+        if "linear_warning" in rep:
+            unconverged[0] += 1
         return conv, rep.get("linear_iterations", 0)
 
     def timestep():
-        sim.p.copy_from(p_init); sim.s.copy_from(s_init)
-        return run_timestep(step)
+        """One implicit timestep; the simulation advances (state0 <- state) unless --fixed-state (bench.py run_b200)."""
+        if args.fixed_state:
+            sim.p.copy_from(p_init); sim.s.copy_from(s_init)
+            return run_timestep(step)
+        res = run_timestep(step)           # every rank takes the same decisions: errors and iteration counts are all-reduced
+        if res[0]:
+            sim.update_before_step()
+        else:
+            sim.p.copy_from(p_init); sim.s.copy_from(s_init)
+        p_init.copy_from(sim.p); s_init.copy_from(sim.s)
+        return res
+
+    def mark():
+        return ctx.transfer(sim.p.get()), ctx.transfer(sim.s.get())
+
+    def rewind(saved):
+        sim.p.copy_from(saved[0]); sim.s.copy_from(saved[1]); p_init.copy_from(saved[0]); s_init.copy_from(saved[1])
+        sim.update_before_step()
 
     def barrier():
         ctx.synchronize(); td.barrier(); torch.cuda.synchronize()
 
     for _ in range(args.warmup):
         timestep()
+    start_state = mark()
+    unconverged[0] = 0
     launches0 = ctx.launch_count
     clocks = ClockSampler(local_rank); clocks.start()
     barrier()
@@ -371,6 +393,8 @@ def run_bench(args, J):
     nb_loc = sim.jac.nnz
     alg = J.workloads.algorithmic_bytes(sim.n_local, (nb_loc - sim.n_local) // 2, 2)
     peak, peak_kind = measured_peak()
+    n_unconverged = unconverged[0]
+    rewind(start_state)
     with J.DeviceProfile(ctx) as prof:
         barrier(); J.timer_start(ctx)
         for _ in range(max(1, min(args.steps, 2))):
@@ -390,11 +414,22 @@ def run_bench(args, J):
     for k in ("vector", "other"):
         t, c = cls[k]
         kernels["halo+allreduce" if k == "other" else k] = {"ms_total": t, "launches": c, "share_of_step": t / ms_prof}
-    dom = max(bytes_of, key=lambda k: cls[k][0])
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
-                "traffic": None, "peak_source": peak_kind, "algorithmic_bytes_per_launch": bytes_of[dom], "note": "rank 0, local sub-domain"}
+    from bench import fused_kernel_report
+    fused = fused_kernel_report(J, sim, cls, ms_prof, nb_loc, sim.n_local, peak)
+    if fused:
+        kernels["bicgstab_iteration"] = fused
+        roofline = {"bound": "hbm", "kernel": fused["kernel"], "achieved": fused["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": fused["frac"], "traffic": None, "peak_source": peak_kind,
+                    "algorithmic_bytes_per_launch": fused["algorithmic_bytes_per_launch"], "ms_per_launch": fused["ms_per_launch"],
+                    "note": "rank 0, local sub-domain; collectives run inside this kernel"}
+    else:
+        dom = max(bytes_of, key=lambda k: cls[k][0])
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_kind, "algorithmic_bytes_per_launch": bytes_of[dom],
+                    "note": "rank 0, local sub-domain"}
 
     # e2e: host state buffers of the owned cells go in and come back every Newton iteration
+    rewind(start_state)
     p0_h, s0_h = p_init.get(), s_init.get()
     nloc = sim.n_local
     p_h, s_h = ctx.pinned_empty(nloc), ctx.pinned_empty(2 * nloc)      # pinned host state buffers
@@ -410,8 +445,12 @@ def run_bench(args, J):
         return conv, rep.get("linear_iterations", 0)
 
     def timestep_host():
-        p_h[:] = p0_h; s_h[:] = s0_h
-        return run_timestep(step_host)
+        if args.fixed_state:
+            p_h[:] = p0_h; s_h[:] = s0_h
+            return run_timestep(step_host)
+        res = run_timestep(step_host)
+        sim.p.set(p_h); sim.s.set(s_h); sim.update_before_step()       # the host owns the state: state0 <- state
+        return res
 
     barrier()
     t0 = time.perf_counter()
@@ -436,13 +475,17 @@ def run_bench(args, J):
                                    f"SURVEY §8(d) initial state, {nx}x{ny}x{nz} = {nc} cells, unstructured (permuted) hex grid, METIS k-way over "
                                    f"{world} GPUs, block-Jacobi ILU(0)-BiCGStab rtol={args.rtol:g}",
                        "cells": nc, "faces": nf, "block_size": 2, "linear_rtol": args.rtol, "max_linear_iterations": args.max_linear_iterations,
-                       "newton_tolerance": args.tolerance, "parallelism": f"domain decomposition, {world} ranks, NCCL halo + all-reduce",
+                       "newton_tolerance": args.tolerance, "parallelism": f"domain decomposition, {world} ranks (one process per GPU); halo exchange and Krylov all-reduce as peer-memory "
+                                      f"stores over NVLink inside the fused iteration kernel (NCCL: fallback path and setup only)",
                        "l2_policy": "inputs larger than L2 per rank" if (nb_loc * 32) > 126e6 else "local Jacobian fits L2: no flush (strong scaling)",
                        "owned_ghost_per_rank": [[int(a[0]), int(a[1])] for a in all_sizes], "partition_seconds": t_part,
                        "cell_ordering": args.ordering, "ilu": sim.prec.info(), "operator_identity_rows_rank0": id_rows,
                        "collectives": "peer memory over NVLink (fused all-reduce + recurrence kernel, direct halo stores)" if sim.halo.p2p else "NCCL"},
             "newton_iterations_per_step": n_newton / max(args.steps, 1), "converged": all(r[0] for r in results),
             "linear_iterations_per_newton": float(np.mean(lin_its)) if lin_its else None, "linear_iterations": results[0][2],
+            "linear_solves": len(lin_its), "linear_solves_unconverged": n_unconverged,
+            "timestepping": "fixed state (every step re-solves report step 1)" if args.fixed_state else
+                            f"advancing: warm-up = report steps 1..{args.warmup}, timed = report steps {args.warmup + 1}..{args.warmup + args.steps}",
             "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "kernels": kernels,
             "hbm_gbs": {k: kernels[k]["achieved_gbs"] for k in ("assembly", "spmv") if k in kernels}, "cpu_baseline": None,
         }

@@ -98,6 +98,29 @@ def algorithmic_bytes(nc, nf, bs=2):
     return dict(spmv=spmv, assembly=assembly, ilu_apply=ilu_apply, ilu_factor=ilu_factor, bicgstab_iter=bicgstab_iter)
 
 
+def fused_iteration_bytes(nb, n_local, n_own, n_id, id_blocks, n_b, n_l, n_u):
+    """Compulsory HBM bytes of ONE launch of the fused BiCGStab iteration kernel (csrc/krylov_persistent.cu), phase by phase:
+    every matrix block (32 B + 4 B column) and every vector element (8 B) counted once per phase that must stream it;
+    gathered operands counted once per phase (re-reads through L2 are the cache-efficiency loss the fraction exposes).
+    nb blocks of the local Jacobian, n_own rows updated, n_id identity rows holding id_blocks blocks, n_b rows of the second
+    colour, n_l / n_u blocks of L / U. bs = 2 (16 B per row and vector)."""
+    n_r = n_own - n_b                       # rows swept with U (first colour)
+    nb_a = nb - id_blocks - (n_local - n_own)   # blocks of the rows the SpMV phases stream (ghost rows are never streamed)
+    nr_a = n_own - n_id
+    ph = {}
+    ph["A1_sweep_L_y"] = n_l * 36 + n_b * (8 + 32 + 80) + 16 * n_r
+    ph["A2_sweep_U_y"] = n_u * 36 + n_r * 72 + 16 * n_id + 16 * n_b
+    ph["A3_spmv_v"] = nb_a * 36 + nr_a * 36 + 16 * n_local
+    ph["V1_s"] = 48 * n_r
+    ph["A4_sweep_L_z"] = n_l * 36 + n_b * 104 + 16 * n_r
+    ph["A5_sweep_U_z"] = n_u * 36 + n_r * 72 + 16 * n_b
+    ph["A6_spmv_t"] = nb_a * 36 + nr_a * 36 + 16 * n_local
+    ph["V2_x_r"] = 112 * n_own + 16 * nr_a
+    ph["V3_p"] = 48 * n_r + 16 * max(n_r - n_id, 0)
+    ph["total"] = sum(ph.values())
+    return ph
+
+
 def heat_initial_condition(nx, ny):
     """docs/src/index.md:22-46: T0 = 100 inside the centred half-width square, else 0."""
     T = np.zeros((ny, nx))

@@ -25,9 +25,11 @@ comm = D.Communicator(ctx, rank, world, td)
 part = J.partition(w["N"], world, weights=w["Tf"], nc=nc)
 ok_all = True
 ref_cache = {}
-for order in ("default", "multicolor"):
-    for p2p in ("1", "0"):
-        os.environ["JB_P2P"] = p2p
+for order, p2p, fused in (("default", "1", "1"), ("default", "0", "1"), ("multicolor", "1", "1"), ("multicolor", "1", "0"), ("multicolor", "0", "1")):
+    if True:
+        # fused = "1": the fused iteration kernel (peer-memory collectives inside the kernel) where the structure qualifies
+        # (multicolour ordering, peer memory); "0": the multi-kernel driver on the same problem
+        os.environ["JB_P2P"] = p2p; os.environ["JB_PERSISTENT"] = fused
         sim = D.DistTwoPhaseSimulator(ctx, comm, w, part, rtol=1e-9, tolerance=1e-6, max_linear_iterations=500, local_order=order, td=td)
         assert sim.halo.p2p == (p2p == "1")
         conv, reps = sim.solve_ministep(w["dt"])
@@ -52,7 +54,7 @@ for order in ("default", "multicolor"):
             good = conv and conv1 and len(reps) == len(reps1) and ep <= 1e-8 and es <= 1e-8
             if order == "default":   # same elimination order inside every block => same iteration counts up to rounding
                 good = good and all(abs(a - b) <= max(2, b // 10) for a, b in zip(its, its1))
-            print(f"[dist_gpu_check] world={world} order={order} p2p={p2p} newton {len(reps)} vs {len(reps1)} lin {its} vs {its1} "
+            print(f"[dist_gpu_check] world={world} order={order} p2p={p2p} fused={fused} newton {len(reps)} vs {len(reps1)} lin {its} vs {its1} "
                   f"dp={ep:.2e} ds={es:.2e} -> {'OK' if good else 'MISMATCH'}", flush=True)
             ok_all = ok_all and good
         del sim
