@@ -54,6 +54,9 @@ typedef struct jb_perm jb_perm;
 typedef struct jb_comm jb_comm;
 typedef struct jb_dist jb_dist;
 typedef struct jb_nfvm jb_nfvm;
+typedef struct jb_schur jb_schur;
+typedef struct jb_table jb_table;
+typedef struct jb_varprog jb_varprog;
 
 /* ---- lifecycle: JutulContext (src/core_types/contexts/*.jl, src/context.jl:65-78:
  *      initialize_context!, synchronize) ------------------------------------ */
@@ -116,6 +119,16 @@ double* jb_csr_values_ptr(jb_csr* csr); /* device pointer to nonzeros(jac) */
  * a preconditioner factored from the current values (identity rows of A*N^-1, csrc/krylov.cu) only when the generations
  * match; a lagged preconditioner (apply!/linear_solve! without update_preconditioner!) takes the full SpMV. */
 int32_t jb_csr_values_modified(jb_csr* csr);
+
+/* ---- adjoint systems: context' / matrix_layout(ctx).as_adjoint = true (src/core_types/core_types.jl:140-165). The
+ *      reference assembles J^T in place — transposed pattern (src/models.jl:662-664), cache entry (row, col, eq, partial)
+ *      aligned to block (col, row) at in-block index N (eq - 1) + partial (src/equations.jl:101-108,152-161) — and runs the
+ *      unchanged linear_solve! on it for the Lagrange multipliers (src/ad/gradients.jl:519-590); sens_add_mult!
+ *      (rhs += op * lambda, :592-603) is jb_spmv(T, 1, lambda, 1, rhs). jb_csr_create_transpose builds the pattern of J^T
+ *      and the block map once; jb_csr_transpose_update refreshes its values from the current values of J (one gather
+ *      pass, blocks transposed). The result is an ordinary jb_csr: jb_ilu0_create / jb_krylov_create / jb_spmv apply. */
+int32_t jb_csr_create_transpose(jb_csr* csr, jb_csr** out);
+int32_t jb_csr_transpose_update(jb_csr* csr_t);
 
 /* ---- alignment: align_to_jacobian! / half_face_flux_cells_alignment! /
  *      diagonal_alignment! (src/conservation/conservation.jl:143-216,
@@ -194,6 +207,57 @@ int32_t jb_nfvm_create(jb_ctx* ctx, int64_t nf, int64_t nc, int32_t scheme, cons
                        jb_nfvm** out);
 int32_t jb_nfvm_destroy(jb_nfvm* d);
 int32_t jb_nfvm_evaluate_flux(jb_nfvm* d, const double* d_p, int64_t nph, int64_t ph, double* d_q);
+/* Conservation law on the NFVM flux with the face-based assembly, PotentialFlow{:fvm}:
+ *      ConservationLawFiniteVolumeStorage (src/conservation/fvm_assembly.jl:1-53). The partials of evaluate_flux with respect
+ *      to every stencil cell (the reference evaluates the AD-generic flux once per stencil cell, :194-208) are formed in
+ *      closed form inside the face kernel.
+ *      jb_nfvm_stencil: discretization_stencil of every face (src/NFVM/decomposition.jl:131-141, types.jl:38-42) as
+ *      vpos[nf+1] / vars (1-based), the layout of face_cache.vpos / .variables; n_out = total slots.
+ *      jb_nfvm_pattern: declare_pattern (:55-89) -> scalar CSR Jacobian (diagonal; (l,c), (r,c), (c,l), (c,r) per slot).
+ *      jb_nfvm_align: align_to_jacobian! (:98-165); jb_nfvm_positions dumps left_facepos / right_facepos (1-based nz index).
+ *      jb_nfvm_assemble: update_equation! + update_linearized_system_equation! / fvm_face_assembly! (:216-283):
+ *      r = d_acc (or 0), J[c,c] = d_dacc (or 0), then r[l] += q, r[r] -= q, J[l,c] += dq/dp_c, J[r,c] -= dq/dp_c
+ *      (warp-aggregated FP64 atomics). d_q (nf) optionally receives the face fluxes. */
+int32_t jb_nfvm_stencil(jb_nfvm* d, int64_t* vpos, int64_t* vars, int64_t cap, int64_t* n_out);
+int32_t jb_nfvm_pattern(jb_nfvm* d, jb_csr** out);
+int32_t jb_nfvm_align(jb_nfvm* d, jb_csr* csr);
+int32_t jb_nfvm_positions(jb_nfvm* d, int64_t* left_pos, int64_t* right_pos);
+int32_t jb_nfvm_assemble(jb_nfvm* d, const double* d_p, int64_t nph, int64_t ph, const double* d_acc, const double* d_dacc,
+                         double* d_r, double* d_q);
+
+/* ---- secondary variables: update_secondary_variables! (src/variable_evaluation.jl:87-148) over the graph ordered by
+ *      sort_secondary_variables! / sort_symbols (:260-350), tables of src/interpolation.jl. One kernel evaluates the whole
+ *      dependency graph per cell with forward-mode partials with respect to the cell's primary variables.
+ *      jb_table_*: LinearInterpolant (interpolation.jl:69-99; first_lower :3-20, linear_interp :29-40) and
+ *      BilinearInterpolant (:156-222); constant_dx: -1 = `missing` (detected as interpolation_constant_lookup :50-67
+ *      does), 0 / 1 = forced. X / F are the interpolant's own arrays (get_1d_interpolator's end-point capping,
+ *      :118-154, is the caller's). jb_table_eval: interpolate(I, x[, y]) with d/dx (, d/dy) on device arrays.
+ *      jb_var_spec: kind, dep[3] (1-based indices into the spec array, packed from the left, 0 = unused), table (1-based),
+ *      output flag, constants c[4]:
+ *        PRIMARY / PARAMETER  input array (partial 1 with respect to itself / no partials)
+ *        CONST      c0
+ *        AFFINE     c0 + c1 a + c2 b + c3 c            (1 - Sw, sums of phases, ...)
+ *        PRODUCT    c0 a b c                          (rho S phi V, kr / mu via QUOTIENT, ...)
+ *        QUOTIENT   c0 a / b
+ *        EXP        c0 exp(c1 (a - c2))               (density with constant compressibility)
+ *        POWER      c0 clamp((a - c2) / c3, 0, 1)^c1  (Brooks-Corey relative permeability)
+ *        TABLE1D    c0 I(a),  TABLE2D  c0 I(a, b)
+ *      The evaluation order is sort_symbols' (depth-first post-order, dependencies in ascending node order); a cycle or a
+ *      dangling dependency is an error. Outputs: per flagged variable (1 + np) planes of nc doubles (value, d/d primary q). */
+enum { JB_VAR_PRIMARY = 0, JB_VAR_PARAMETER = 1, JB_VAR_CONST = 2, JB_VAR_AFFINE = 3, JB_VAR_PRODUCT = 4, JB_VAR_QUOTIENT = 5,
+       JB_VAR_EXP = 6, JB_VAR_POWER = 7, JB_VAR_TABLE1D = 8, JB_VAR_TABLE2D = 9 };
+typedef struct { int32_t kind; int32_t dep[3]; int32_t table; int32_t output; double c[4]; } jb_var_spec;
+int32_t jb_table_create_1d(jb_ctx* ctx, int64_t n, const double* X, const double* F, int32_t constant_dx, jb_table** out);
+int32_t jb_table_create_2d(jb_ctx* ctx, int64_t nx, int64_t ny, const double* X, const double* Y, const double* F /*nx x ny, column-major*/,
+                           int32_t constant_dx, int32_t constant_dy, jb_table** out);
+int32_t jb_table_destroy(jb_table* t);
+int32_t jb_table_info(jb_table* t, int64_t* info /*5: dim, nx, ny, lookup_x, lookup_y*/);
+int32_t jb_table_eval(jb_table* t, int64_t n, const double* d_x, const double* d_y, double* d_f, double* d_dfdx, double* d_dfdy);
+int32_t jb_varprog_create(jb_ctx* ctx, int64_t nc, int32_t nvars, const jb_var_spec* specs, int32_t ntables, jb_table* const* tables,
+                          jb_varprog** out);
+int32_t jb_varprog_destroy(jb_varprog* p);
+int32_t jb_varprog_order(jb_varprog* p, int64_t* order /*nvars, 1-based*/, int64_t* counts /*4: primaries, inputs, outputs, secondaries*/);
+int32_t jb_varprog_evaluate(jb_varprog* p, const double* const* d_inputs, double* const* d_outputs);
 
 /* ---- post_update_linearized_system! for ghost rows: unit_diagonalize!
  *      (ext/JutulPartitionedArraysExt/linalg.jl:1-35): rows >= n_owned become -I, r = 0. */
@@ -251,6 +315,30 @@ int32_t jb_krylov_info(jb_krylov* ks, int64_t* info /*8*/);
  * measured with %globaltimer between the grid barriers: out[0..11] = init, A1, A2, A3, V1, A4, A5, A6, V2, V3, halo pushes,
  * final; out[12] = iterations, out[13] = solves covered. Clears the accumulators. */
 int32_t jb_krylov_phase_times(jb_krylov* ks, double* out /*14*/);
+
+/* ---- MultiModel with reduction = :schur_apply (src/linsolve/multimodel.jl:17-160; block system of
+ *      setup_linearized_system!(::MultiModel), src/multimodel/model.jl:534-601): [B C; D E][x; y] = [a; b] with B the device
+ *      Jacobian (jb_csr) and ngroups eliminated groups (wells, facility). C_i is (n bs) x m_i, D_i is m_i x (n bs), E_i is
+ *      m_i x m_i, all scalar sparse matrices given as COO triplets (1-based, duplicates are summed as sparse() does), the
+ *      groups concatenated with *_ptr[ngroups+1] (1-based offsets into the I / J / V arrays). m_i <= 2048.
+ *      jb_schur_update: new values (same COO order) and lu!(E_i) (get_schur_blocks!(update = true), :36-54) — host
+ *      factorisation with partial pivoting, explicit inverse uploaded; JB_BAD_PIVOT for a singular E_i.
+ *      jb_schur_prepare: prepare_linear_solve! (:17-33), d_a -= C (E \ b); b (host, sum m_i) stays resident.
+ *      jb_schur_mul: schur_mul! (:139-160), res <- beta res + alpha (B x - C (E \ (D x))).
+ *      jb_krylov_set_schur: linear_operator(sys) (:70-91) — the Krylov solve then runs on S = B - C E^-1 D while the
+ *      preconditioner keeps acting on B (jacobian(sys), :162-169). NULL restores the plain operator.
+ *      jb_schur_dx_update: update_dx_from_vector! / schur_dx_update! (:97-137) with d_dx as jb_krylov_solve left it
+ *      (dx = -x): y_i = E_i \ (D_i x - b_i), written to the host array y (sum m_i). */
+int32_t jb_schur_create(jb_csr* B, int32_t ngroups, const int64_t* msize, const int64_t* C_ptr, const int64_t* C_I, const int64_t* C_J,
+                        const int64_t* D_ptr, const int64_t* D_I, const int64_t* D_J, const int64_t* E_ptr, const int64_t* E_I,
+                        const int64_t* E_J, jb_schur** out);
+int32_t jb_schur_destroy(jb_schur* s);
+int64_t jb_schur_size(jb_schur* s);
+int32_t jb_schur_update(jb_schur* s, const double* C_V, const double* D_V, const double* E_V);
+int32_t jb_schur_prepare(jb_schur* s, double* d_a, const double* b);
+int32_t jb_schur_mul(jb_schur* s, double alpha, const double* d_x, double beta, double* d_res);
+int32_t jb_krylov_set_schur(jb_krylov* ks, jb_schur* s);
+int32_t jb_schur_dx_update(jb_schur* s, const double* d_dx, double* y);
 
 /* ---- apply_scaling_to_linearized_system! (src/linsolve/default.jl:325-385):
  *      kind 0 none, 1 diagonal (block rows scaled by inv(D_ii)), 2 dt (J, r *= dt). */

@@ -231,6 +231,19 @@ class StaticSparsityMatrixCSR(_Handle):
         check(self.ctx.lib.jb_spmv(self.h, alpha, _dp(x), beta, _dp(y)), self.ctx.h, "jb_spmv")
         return y
 
+    def adjoint(self):
+        """Jacobian of the adjoint system: context' gives matrix_layout.as_adjoint = true (src/core_types/core_types.jl:140-165)
+        and the reference assembles J^T in place; here J^T is a second resident matrix refreshed from J by `update_adjoint`."""
+        h = C.c_void_p()
+        check(self.ctx.lib.jb_csr_create_transpose(self.h, C.byref(h)), self.ctx.h, "jb_csr_create_transpose")
+        T = StaticSparsityMatrixCSR(self.ctx, h, self.bs)
+        T._source = self
+        return T
+
+    def update_adjoint(self):
+        """Refresh the values of an `adjoint()` matrix from its source (adjoint_reassemble!, src/ad/gradients.jl:603-621)."""
+        check(self.ctx.lib.jb_csr_transpose_update(self.h), self.ctx.h, "jb_csr_transpose_update")
+
     def unit_diagonalize_ghosts(self, r, n_owned):
         check(self.ctx.lib.jb_unit_diagonalize_ghosts(self.h, _dp(r), n_owned), self.ctx.h, "jb_unit_diagonalize_ghosts")
 
@@ -556,6 +569,34 @@ class NFVMDiscretization(_Handle):
         check(self.ctx.lib.jb_nfvm_evaluate_flux(self.h, _dp(p), nph, ph, _dp(q)), self.ctx.h, "jb_nfvm_evaluate_flux")
         return q
 
+    # ---- conservation law on this flux with the face-based (:fvm) assembly, src/conservation/fvm_assembly.jl
+    def stencil(self):
+        """(vpos, variables) of the face cache: discretization_stencil of every face, 1-based."""
+        n = C.c_int64(0)
+        check(self.ctx.lib.jb_nfvm_stencil(self.h, None, None, 0, C.byref(n)), self.ctx.h, "jb_nfvm_stencil")
+        vpos = np.zeros(self.nf + 1, dtype=i64); vars_ = np.zeros(n.value, dtype=i64)
+        check(self.ctx.lib.jb_nfvm_stencil(self.h, _pi(vpos), _pi(vars_), n.value, C.byref(n)), self.ctx.h, "jb_nfvm_stencil")
+        return vpos, vars_
+
+    def declare_pattern(self):
+        """declare_pattern (:55-89) + build_jacobian: scalar CSR Jacobian of the law."""
+        h = C.c_void_p()
+        check(self.ctx.lib.jb_nfvm_pattern(self.h, C.byref(h)), self.ctx.h, "jb_nfvm_pattern")
+        return StaticSparsityMatrixCSR(self.ctx, h, 1)
+
+    def align_to_jacobian(self, jac):
+        check(self.ctx.lib.jb_nfvm_align(self.h, jac.h), self.ctx.h, "jb_nfvm_align")
+        self.jac = jac
+        n = self.stencil()[1].shape[0]
+        lp = np.zeros(n, dtype=i64); rp = np.zeros(n, dtype=i64)
+        check(self.ctx.lib.jb_nfvm_positions(self.h, _pi(lp), _pi(rp)), self.ctx.h, "jb_nfvm_positions")
+        return lp, rp
+
+    def update_equation_and_linearized_system(self, p, r, acc=None, dacc=None, q=None, nph=1, ph=1):
+        """update_equation! + update_linearized_system_equation! (fvm_face_assembly!, :216-283)."""
+        check(self.ctx.lib.jb_nfvm_assemble(self.h, _dp(p), nph, ph, _dp(acc), _dp(dacc), _dp(r), _dp(q)), self.ctx.h, "jb_nfvm_assemble")
+        return r
+
 
 def process_partition(N, nc, part, weights=None):
     """process_partition(neighbors, partition; weights) (src/partitioning.jl:128-160)."""
@@ -639,5 +680,8 @@ def timer_stop(ctx):
 
 from .simulator import HeatSimulator, PoissonSimulator, TwoPhaseSimulator  # noqa: E402
 from . import workloads  # noqa: E402,F401
+from .multimodel import MultiLinearizedSystemSchur  # noqa: E402
+from .variables import (BilinearInterpolant, LinearInterpolant, SecondaryVariables, get_1d_interpolator,  # noqa: E402
+                        get_2d_interpolator)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

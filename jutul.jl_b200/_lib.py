@@ -50,6 +50,8 @@ PROTOTYPES = {
     "jb_csr_values_set": (I32, [P, PF64]),
     "jb_csr_values_ptr": (P, [P]),
     "jb_csr_values_modified": (I32, [P]),
+    "jb_csr_create_transpose": (I32, [P, PP]),
+    "jb_csr_transpose_update": (I32, [P]),
     "jb_tpfa_create": (I32, [P, P, PP]),
     "jb_tpfa_destroy": (I32, [P]),
     "jb_tpfa_positions": (I32, [P, PI64, PI64]),
@@ -70,6 +72,28 @@ PROTOTYPES = {
     "jb_nfvm_create": (I32, [P, I64, I64, I32, PI64, PI64, PF64, PF64, PI64, PI64, PF64, PF64, PF64, PI64, PI64, PF64, PP]),
     "jb_nfvm_destroy": (I32, [P]),
     "jb_nfvm_evaluate_flux": (I32, [P, P, I64, I64, P]),
+    "jb_nfvm_stencil": (I32, [P, PI64, PI64, I64, PI64]),
+    "jb_nfvm_pattern": (I32, [P, PP]),
+    "jb_nfvm_align": (I32, [P, P]),
+    "jb_nfvm_positions": (I32, [P, PI64, PI64]),
+    "jb_nfvm_assemble": (I32, [P, P, I64, I64, P, P, P, P]),
+    "jb_table_create_1d": (I32, [P, I64, PF64, PF64, I32, PP]),
+    "jb_table_create_2d": (I32, [P, I64, I64, PF64, PF64, PF64, I32, I32, PP]),
+    "jb_table_destroy": (I32, [P]),
+    "jb_table_info": (I32, [P, PI64]),
+    "jb_table_eval": (I32, [P, I64, P, P, P, P, P]),
+    "jb_varprog_create": (I32, [P, I64, I32, P, I32, PP, PP]),
+    "jb_varprog_destroy": (I32, [P]),
+    "jb_varprog_order": (I32, [P, PI64, PI64]),
+    "jb_varprog_evaluate": (I32, [P, PP, PP]),
+    "jb_schur_create": (I32, [P, I32, PI64, PI64, PI64, PI64, PI64, PI64, PI64, PI64, PI64, PI64, PP]),
+    "jb_schur_destroy": (I32, [P]),
+    "jb_schur_size": (I64, [P]),
+    "jb_schur_update": (I32, [P, PF64, PF64, PF64]),
+    "jb_schur_prepare": (I32, [P, P, PF64]),
+    "jb_schur_mul": (I32, [P, F64, P, F64, P]),
+    "jb_krylov_set_schur": (I32, [P, P]),
+    "jb_schur_dx_update": (I32, [P, P, PF64]),
     "jb_unit_diagonalize_ghosts": (I32, [P, P, I64]),
     "jb_spmv": (I32, [P, F64, P, F64, P]),
     "jb_ilu0_create": (I32, [P, PI64, PP]),

@@ -24,8 +24,8 @@
 //   twophase_faces_kernel   — variant B of the reference (fvm_face_assembly!,
 //                             src/conservation/fvm_assembly.jl:253-283): one lane
 //                             per face, off-diagonal blocks written directly,
-//                             r and diagonal blocks scattered with FP64 atomics
-//                             (kept for comparison; order-dependent rounding).
+//                             r and diagonal blocks scattered with warp-aggregated
+//                             FP64 atomics (jb_reduce.cuh; order-dependent rounding).
 //
 // Physics: builder-defined two-phase immiscible plug-in for the face_flux! slot
 // (src/conservation/conservation.jl:642-649), see SURVEY.md §8(d) / DESIGN.md.
@@ -656,11 +656,11 @@ __global__ void __launch_bounds__(256) twophase_faces_kernel(i64 nf, TPParams P,
             double Fl, dl_dp, dl_ds, Fr, dr_dp, dr_ds;
             flux_phase(P, L, R, a, T, g, Fl, dl_dp, dl_ds);     // out of left  (sign +1)
             flux_phase(P, R, L, a, T, -g, Fr, dr_dp, dr_ds);    // out of right (sign -1)
-            atomicAdd(r + 2 * (size_t)l + a, Fl);
-            atomicAdd(r + 2 * (size_t)rr + a, Fr);
+            warp_agg_atomic_add(r + 2 * (size_t)l + a, Fl);
+            warp_agg_atomic_add(r + 2 * (size_t)rr + a, Fr);
             const size_t dl = (size_t)__ldg(diag_pos + l) * 4, dr = (size_t)__ldg(diag_pos + rr) * 4;
-            atomicAdd(nz + dl + a, dl_dp); atomicAdd(nz + dl + 2 + a, dl_ds);
-            atomicAdd(nz + dr + a, dr_dp); atomicAdd(nz + dr + 2 + a, dr_ds);
+            warp_agg_atomic_add(nz + dl + a, dl_dp); warp_agg_atomic_add(nz + dl + 2 + a, dl_ds);
+            warp_agg_atomic_add(nz + dr + a, dr_dp); warp_agg_atomic_add(nz + dr + 2 + a, dr_ds);
             bl[a] = -dr_dp; bl[2 + a] = -dr_ds;   // J[l, r] = -dF_{r->l}/dx_r
             br[a] = -dl_dp; br[2 + a] = -dl_ds;   // J[r, l] = -dF_{l->r}/dx_l
         }

@@ -240,9 +240,12 @@ int jb_gmres_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double rt
                 rc = jb_launch_ilu_apply_sc(F, K->gm_V[j - 1], dst, sc); if (rc != JB_OK) return rc;
                 pv = dst;
             }
-            if (!left) { rc = jb_launch_spmv_dots(A, pv, q, JB_DOT_NONE, nullptr, nullptr); if (rc != JB_OK) return rc; }
-            else {
+            if (!left) {
+                rc = jb_launch_spmv_dots(A, pv, q, JB_DOT_NONE, nullptr, nullptr); if (rc != JB_OK) return rc;
+                if (K->schur && (rc = jb_schur_correct_launch(K->schur, pv, q, 1.0)) != JB_OK) return rc;   // q = S pv (multimodel.jl:139-160)
+            } else {
                 rc = jb_launch_spmv_dots(A, pv, K->t.p, JB_DOT_NONE, nullptr, nullptr); if (rc != JB_OK) return rc;
+                if (K->schur && (rc = jb_schur_correct_launch(K->schur, pv, K->t.p, 1.0)) != JB_OK) return rc;
                 rc = jb_launch_ilu_apply_sc(F, K->t.p, q, sc); if (rc != JB_OK) return rc;
             }
             GM_BEGIN
@@ -278,6 +281,7 @@ int jb_gmres_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double rt
         if (!restart || f[KS_DONE] != 0.0 || base >= itmax) break;
         // restart: r0 = M^{-1}(b - A x), beta = |r0|, v_1 = r0 / beta
         rc = jb_launch_spmv_dots(A, K->x.p, q, JB_DOT_NONE, nullptr, nullptr); if (rc != JB_OK) return rc;
+        if (K->schur && (rc = jb_schur_correct_launch(K->schur, K->x.p, q, 1.0)) != JB_OK) return rc;
         GM_BEGIN
         gm_residual_kernel<<<g, 256, 0, st>>>(m, d_b, q, K->r.p); JB_CHECK_LAUNCH(ctx);
         GM_END

@@ -156,6 +156,72 @@ int32_t jb_csr_create_tpfa(jb_mesh* m, int32_t bs, jb_csr** out) {
 int32_t jb_csr_destroy(jb_csr* A) { delete A; return JB_OK; }
 }  // extern "C"
 
+// ---------------------------------------------------------------- adjoint (transposed) system
+// The reference solves adjoint problems by assembling J^T in place: with context = adjoint(ctx) the layout carries
+// as_adjoint = true (src/core_types/core_types.jl:140-165), the pattern is transposed (src/models.jl:662-664), every cache
+// entry (row, col, eq, partial) is aligned to block (col, row) at in-block index N (eq - 1) + partial
+// (src/equations.jl:101-108, find_sparse_position(A, row, col, is_adjoint) :152-161), and the unchanged linear_solve! runs on
+// it (src/ad/gradients.jl:519-590). Here the forward assembly kernels keep their layout and J^T is produced from the
+// resident J by one gather pass: block k of T reads block tmap[k] of A and swaps its in-block indices.
+template <int BS>
+__global__ void __launch_bounds__(256) csr_transpose_kernel(i64 nnzb, const int32_t* __restrict__ tmap, const double* __restrict__ src,
+                                                            double* __restrict__ dst) {
+    constexpr int B2 = BS * BS;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < nnzb; k += (i64)gridDim.x * blockDim.x) {
+        const double* a = src + (size_t)__ldg(tmap + k) * B2;
+        double v[B2];
+#pragma unroll
+        for (int q = 0; q < B2; q++) v[q] = __ldg(a + q);
+#pragma unroll
+        for (int i = 0; i < BS; i++)
+#pragma unroll
+            for (int j = 0; j < BS; j++) dst[(size_t)k * B2 + j * BS + i] = v[i * BS + j];
+    }
+}
+
+extern "C" {
+int32_t jb_csr_create_transpose(jb_csr* A, jb_csr** out) {
+    if (!A || !out) return JB_ERR_ARG;
+    jb_ctx* ctx = A->ctx;
+    jb_csr* T = new jb_csr();
+    T->ctx = ctx; T->n = A->n; T->bs = A->bs; T->nnzb = A->nnzb; T->tr_src = A;
+    T->h_rowptr.assign(A->n + 1, 0);
+    for (i64 k = 0; k < A->nnzb; k++) T->h_rowptr[A->h_colidx[k] + 1]++;
+    for (i64 r = 0; r < A->n; r++) T->h_rowptr[r + 1] += T->h_rowptr[r];
+    T->h_colidx.assign(A->nnzb, 0);
+    std::vector<int32_t> tmap(A->nnzb), cur(T->h_rowptr.begin(), T->h_rowptr.end() - 1);
+    for (i64 r = 0; r < A->n; r++)               // rows ascending: the columns of every row of T come out sorted
+        for (int32_t k = A->h_rowptr[r]; k < A->h_rowptr[r + 1]; k++) {
+            const int32_t slot = cur[A->h_colidx[k]]++;
+            T->h_colidx[slot] = (int32_t)r; tmap[slot] = k;
+        }
+    int rc = csr_finish(ctx, T);
+    if (rc == JB_OK && T->d_tmap.upload(tmap, ctx->stream) != cudaSuccess) rc = JB_ERR_ALLOC;
+    if (rc != JB_OK) { delete T; JB_FAIL(ctx, rc, "jb_csr_create_transpose: device allocation failed"); }
+    *out = T;
+    return JB_OK;
+}
+int32_t jb_csr_transpose_update(jb_csr* T) {
+    if (!T || !T->tr_src) return JB_ERR_ARG;
+    jb_ctx* ctx = T->ctx;
+    const int g = (int)std::max<i64>(1, std::min<i64>((T->nnzb + 255) / 256, (i64)ctx->sm_count * 16));
+    {
+        ProfScope _ps(ctx, JB_PROF_OTHER);
+        switch (T->bs) {
+            case 1: csr_transpose_kernel<1><<<g, 256, 0, ctx->stream>>>(T->nnzb, T->d_tmap.p, T->tr_src->d_val.p, T->d_val.p); break;
+            case 2: csr_transpose_kernel<2><<<g, 256, 0, ctx->stream>>>(T->nnzb, T->d_tmap.p, T->tr_src->d_val.p, T->d_val.p); break;
+            case 3: csr_transpose_kernel<3><<<g, 256, 0, ctx->stream>>>(T->nnzb, T->d_tmap.p, T->tr_src->d_val.p, T->d_val.p); break;
+            case 4: csr_transpose_kernel<4><<<g, 256, 0, ctx->stream>>>(T->nnzb, T->d_tmap.p, T->tr_src->d_val.p, T->d_val.p); break;
+            default: return JB_ERR_UNSUPPORTED;
+        }
+        JB_CHECK_LAUNCH(ctx);
+    }
+    jb_csr_touch(T);
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+}  // extern "C"
+
 // Classify the stream chunks of a rank-local matrix ([owned | ghost] numbering): interior = every row and every column of
 // the chunk is owned; boundary = some owned row reads a ghost column (or the chunk straddles n_owned). Chunks of ghost rows
 // only are dropped (those rows are -I and never needed by the distributed SpMV).

@@ -151,6 +151,9 @@ struct jb_csr {
     // values_set, unit_diagonalize). jb_ilu records the generation it was factored from; shortcuts that are exact only for a
     // preconditioner built from the CURRENT values (identity rows of A N^-1, krylov.cu) are taken only when the two match.
     uint64_t val_gen = 1;
+    // adjoint system (jb_csr_create_transpose): the matrix this one is the transpose of, and per block the source block
+    jb_csr* tr_src = nullptr;
+    DBuf<int32_t> d_tmap;
 };
 inline void jb_csr_touch(jb_csr* A) { if (A) A->val_gen++; }
 int jb_csr_split_owned(jb_csr* A, i64 n_owned);
@@ -287,6 +290,7 @@ struct jb_krylov {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int hist_cap = 0;
     bool overlap = false;      // interior SpMV overlapped with the halo exchange (JB_OVERLAP=1)
+    struct jb_schur* schur = nullptr;   // MultiModel Schur operator S = B - C E^-1 D applied after every SpMV (schur.cu)
     jb_dist* dist = nullptr;   // distributed solve: dots over owned rows + all-reduce, halo exchange before each SpMV
     // gmres: Arnoldi basis (grows on demand), packed Hessenberg/R columns, Givens c/s, z, y
     std::vector<double*> gm_V, gm_Z;  // Z_j = N^{-1} v_j (fgmres only)
@@ -296,6 +300,10 @@ struct jb_krylov {
     bool gm_flexible = false;         // fgmres!
     DBuf<double> gm_R, gm_cs;
 };
+
+struct jb_schur;
+int jb_schur_correct_launch(jb_schur* S, const double* d_x, double* d_res, double alpha);   // res -= alpha C (E \ (D x))
+i64 jb_schur_nrows(jb_schur* S);
 
 // ---- launchers implemented in the kernel translation units (all enqueue on ctx->stream) ----
 enum { JB_DOT_NONE = 0, JB_DOT_CV = 1, JB_DOT_TS_TT = 2 };

@@ -10,6 +10,17 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// Warp-aggregated FP64 atomic add for the face-parallel scatters (fvm_face_assembly!, src/conservation/fvm_assembly.jl:253-283):
+// lanes of the calling warp that target the same address (faces listed by cell: neighbouring lanes share a cell) are found
+// with match.any, their values are added in lane order by every member and ONE lane issues the atomic. Correct for any
+// subset of converged lanes; cuts the atomic traffic of a face sweep by the number of faces a cell owns.
+__device__ __forceinline__ void warp_agg_atomic_add(double* addr, double v) {
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, (unsigned long long)addr);
+    double sum = 0.0;
+    for (unsigned rem = peers; rem; rem &= rem - 1) sum += __shfl_sync(peers, v, __ffs(rem) - 1);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(addr, sum);
+}
 // NaN-propagating max: a non-finite residual must reach the host (fmax would drop the NaN)
 __device__ __forceinline__ double nan_max(double a, double b) { return (a != a) ? a : ((b != b) ? b : fmax(a, b)); }
 __device__ __forceinline__ double warp_max(double v) {

@@ -166,6 +166,14 @@ int32_t jb_krylov_destroy(jb_krylov* K) {
     delete K;
     return JB_OK;
 }
+// MultiModel: the operator of the solve becomes S = B - C E^-1 D (linear_operator(::MultiLinearizedSystem), multimodel.jl:70-91);
+// the preconditioner keeps acting on B = jacobian(sys) (multimodel.jl:162-169). NULL restores the plain Jacobian.
+int32_t jb_krylov_set_schur(jb_krylov* K, jb_schur* S) {
+    if (!K) return JB_ERR_ARG;
+    if (S && jb_schur_nrows(S) != K->m) return JB_ERR_ARG;
+    K->schur = S;
+    return JB_OK;
+}
 int32_t jb_krylov_set_dist(jb_krylov* K, jb_dist* D) {
     if (!K) return JB_ERR_ARG;
     if (D && jb_dist_n_owned(D) > K->csr->n) return JB_ERR_ARG;
@@ -283,6 +291,8 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
     jb_ctx* ctx = A->ctx;
     cudaStream_t st = ctx->stream;
     jb_dist* D = K->dist;
+    jb_schur* SC = K->schur;
+    if (SC && D) JB_FAIL(ctx, JB_ERR_UNSUPPORTED, "bicgstab: the Schur-reduced operator is not available in the distributed solve");
     const int bs = A->bs;
     const i64 n_own = D ? jb_dist_n_owned(D) : A->n;     // rows that enter updates and inner products
     const i64 m = n_own * bs;
@@ -360,6 +370,14 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
             if (rc != JB_OK) return rc;
         } else if (D && (rc = jb_dist_halo_launch(D, yv, bs)) != JB_OK) return rc;    // consistent!(y)
         if (overlap) {
+        } else if (!left && SC) {
+            // v = S y = B y - C E^-1 D y: the inner product cannot ride on the SpMV, it follows the correction
+            rc = jb_launch_spmv_dots(A, yv, K->v.p, JB_DOT_NONE, nullptr, nullptr); if (rc != JB_OK) return rc;
+            rc = jb_schur_correct_launch(SC, yv, K->v.p, 1.0); if (rc != JB_OK) return rc;
+            JB_VEC_BEGIN
+            bicg_dot_kernel<JB_DOT_CV><<<g, 256, 0, st>>>(m, sc, K->v.p, d_b, ctx->d_partials, ctx->d_counters);
+            JB_CHECK_LAUNCH(ctx);
+            JB_VEC_END
         } else if (!left) {
             A->ident_src = ident ? K->p.p : nullptr;
             rc = jb_launch_spmv_dots(A, yv, K->v.p, JB_DOT_CV, d_b, sc, n_own);       // v = A y, alpha = rho/<c,v>
@@ -367,6 +385,7 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
             if (rc != JB_OK) return rc;
         } else {
             rc = jb_launch_spmv_dots(A, yv, K->q.p, JB_DOT_NONE, nullptr, nullptr); if (rc != JB_OK) return rc;
+            if (SC && (rc = jb_schur_correct_launch(SC, yv, K->q.p, 1.0)) != JB_OK) return rc;
             rc = jb_launch_ilu_apply_sc(F, K->q.p, K->v.p, sc); if (rc != JB_OK) return rc;
             JB_VEC_BEGIN
             bicg_dot_kernel<JB_DOT_CV><<<g, 256, 0, st>>>(m, sc, K->v.p, d_b, ctx->d_partials, ctx->d_counters);
@@ -391,6 +410,13 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
             if (rc != JB_OK) return rc;
         } else if (D && (rc = jb_dist_halo_launch(D, zv, bs)) != JB_OK) return rc;    // consistent!(z)
         if (overlap) {
+        } else if (!left && SC) {
+            rc = jb_launch_spmv_dots(A, zv, K->t.p, JB_DOT_NONE, nullptr, nullptr); if (rc != JB_OK) return rc;
+            rc = jb_schur_correct_launch(SC, zv, K->t.p, 1.0); if (rc != JB_OK) return rc;
+            JB_VEC_BEGIN
+            bicg_dot_kernel<JB_DOT_TS_TT><<<g, 256, 0, st>>>(m, sc, K->t.p, K->s.p, ctx->d_partials, ctx->d_counters);
+            JB_CHECK_LAUNCH(ctx);
+            JB_VEC_END
         } else if (!left) {
             A->ident_src = ident ? K->s.p : nullptr;
             rc = jb_launch_spmv_dots(A, zv, K->t.p, JB_DOT_TS_TT, K->s.p, sc, n_own);  // t = A z, omega = <t,s>/<t,t>
@@ -398,6 +424,7 @@ int jb_krylov_solve_impl(jb_krylov* K, const double* d_b, double* d_dx, double r
             if (rc != JB_OK) return rc;
         } else {
             rc = jb_launch_spmv_dots(A, zv, K->q.p, JB_DOT_NONE, nullptr, nullptr); if (rc != JB_OK) return rc;
+            if (SC && (rc = jb_schur_correct_launch(SC, zv, K->q.p, 1.0)) != JB_OK) return rc;
             rc = jb_launch_ilu_apply_sc(F, K->q.p, K->t.p, sc); if (rc != JB_OK) return rc;
             JB_VEC_BEGIN
             bicg_dot_kernel<JB_DOT_TS_TT><<<g, 256, 0, st>>>(m, sc, K->t.p, K->s.p, ctx->d_partials, ctx->d_counters);

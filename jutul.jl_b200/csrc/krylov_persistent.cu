@@ -647,7 +647,7 @@ static bool pk_prepare(jb_krylov* K, i64 n_own) {
 }
 
 bool jb_krylov_persistent_ok(jb_krylov* K, int side, i64 n_own) {
-    if (!pk_enabled() || K->kind != 0 || side != 0 || !K->ilu) return false;
+    if (!pk_enabled() || K->kind != 0 || side != 0 || !K->ilu || K->schur) return false;
     jb_csr* A = K->csr;
     if (K->ilu->factored_gen != A->val_gen) return false;   // the identity rows need factors of the current values
     if (K->dist && !jb_dist_is_p2p(K->dist)) return false;

@@ -491,6 +491,16 @@ struct jb_nfvm {
     int scheme;   // 0 linear, 1 :ntpfa, 2 :nmpfa
     DBuf<int32_t> left, right, L_ptr, L_cell, R_ptr, R_cell;
     DBuf<double> L_Tl, L_Tr, L_T, R_Tl, R_Tr, R_T;
+    // conservation law on this flux with the :fvm assembly (below): host copies of the discretisation, the stencil of every
+    // face (discretization_stencil), per stencil slot the coefficient of p[cell] in (q_l, r_l, q_R, r_R) and the aligned
+    // Jacobian positions of (left, cell) / (right, cell)
+    i64 nc = 0;
+    std::vector<int32_t> h_left, h_right, h_Lptr, h_Lcell, h_Rptr, h_Rcell;
+    std::vector<double> h_LTl, h_LTr, h_LT, h_RTl, h_RTr, h_RT;
+    std::vector<int32_t> h_vpos, h_vars, h_lpos, h_rpos;
+    DBuf<int32_t> d_vpos, d_vars, d_lpos, d_rpos;
+    DBuf<double4> d_coef;
+    jb_csr* csr = nullptr;
 };
 
 __device__ __forceinline__ double nfvm_compute_r(const int32_t* __restrict__ ptr, const int32_t* __restrict__ cell, const double* __restrict__ T,
@@ -526,13 +536,14 @@ __global__ void __launch_bounds__(256) nfvm_flux_kernel(i64 nf, int scheme, cons
 extern "C" {
 
 static int nfvm_half(jb_ctx* ctx, i64 nf, i64 nc, const double* Tl, const double* Tr, const int64_t* ptr, const int64_t* cell, const double* T,
-                     DBuf<double>& dTl, DBuf<double>& dTr, DBuf<int32_t>& dptr, DBuf<int32_t>& dcell, DBuf<double>& dT) {
-    std::vector<int32_t> hp(nf + 1);
+                     DBuf<double>& dTl, DBuf<double>& dTr, DBuf<int32_t>& dptr, DBuf<int32_t>& dcell, DBuf<double>& dT,
+                     std::vector<int32_t>& hp, std::vector<int32_t>& hc, std::vector<double>& a, std::vector<double>& b, std::vector<double>& c) {
+    hp.assign(nf + 1, 0);
     for (i64 f = 0; f <= nf; f++) { if (ptr[f] < 1) return JB_ERR_ARG; hp[f] = (int32_t)(ptr[f] - 1); }
     const i64 nnz = hp[nf];
-    std::vector<int32_t> hc(nnz);
+    hc.assign(nnz, 0);
     for (i64 k = 0; k < nnz; k++) { if (cell[k] < 1 || cell[k] > nc) return JB_ERR_ARG; hc[k] = (int32_t)(cell[k] - 1); }
-    std::vector<double> a(Tl, Tl + nf), b(Tr, Tr + nf), c(T, T + nnz);
+    a.assign(Tl, Tl + nf); b.assign(Tr, Tr + nf); c.assign(T, T + nnz);
     cudaStream_t s = ctx->stream;
     bool ok = dTl.upload(a, s) == cudaSuccess && dTr.upload(b, s) == cudaSuccess && dptr.upload(hp, s) == cudaSuccess &&
               dcell.upload(hc, s) == cudaSuccess && dT.upload(c, s) == cudaSuccess;
@@ -545,15 +556,18 @@ int32_t jb_nfvm_create(jb_ctx* ctx, int64_t nf, int64_t nc, int32_t scheme, cons
     if (!ctx || !out || nf < 1 || scheme < 0 || scheme > 2 || !left || !right || !L_Tl || !L_Tr || !L_ptr) return JB_ERR_ARG;
     if (scheme > 0 && (!R_Tl || !R_Tr || !R_ptr)) return JB_ERR_ARG;
     jb_nfvm* d = new jb_nfvm();
-    d->ctx = ctx; d->nf = nf; d->scheme = scheme;
-    std::vector<int32_t> hl(nf), hr(nf);
+    d->ctx = ctx; d->nf = nf; d->scheme = scheme; d->nc = nc;
+    std::vector<int32_t>&hl = d->h_left, &hr = d->h_right;
+    hl.assign(nf, 0); hr.assign(nf, 0);
     for (i64 f = 0; f < nf; f++) {
         if (left[f] < 1 || left[f] > nc || right[f] < 1 || right[f] > nc) { delete d; JB_FAIL(ctx, JB_ERR_ARG, "jb_nfvm_create: cell out of range"); }
         hl[f] = (int32_t)(left[f] - 1); hr[f] = (int32_t)(right[f] - 1);
     }
     int rc = (d->left.upload(hl, ctx->stream) == cudaSuccess && d->right.upload(hr, ctx->stream) == cudaSuccess) ? JB_OK : JB_ERR_ALLOC;
-    if (rc == JB_OK) rc = nfvm_half(ctx, nf, nc, L_Tl, L_Tr, L_ptr, L_cell, L_T, d->L_Tl, d->L_Tr, d->L_ptr, d->L_cell, d->L_T);
-    if (rc == JB_OK && scheme > 0) rc = nfvm_half(ctx, nf, nc, R_Tl, R_Tr, R_ptr, R_cell, R_T, d->R_Tl, d->R_Tr, d->R_ptr, d->R_cell, d->R_T);
+    if (rc == JB_OK) rc = nfvm_half(ctx, nf, nc, L_Tl, L_Tr, L_ptr, L_cell, L_T, d->L_Tl, d->L_Tr, d->L_ptr, d->L_cell, d->L_T,
+                                    d->h_Lptr, d->h_Lcell, d->h_LTl, d->h_LTr, d->h_LT);
+    if (rc == JB_OK && scheme > 0) rc = nfvm_half(ctx, nf, nc, R_Tl, R_Tr, R_ptr, R_cell, R_T, d->R_Tl, d->R_Tr, d->R_ptr, d->R_cell, d->R_T,
+                                                  d->h_Rptr, d->h_Rcell, d->h_RTl, d->h_RTr, d->h_RT);
     if (rc != JB_OK) { delete d; JB_FAIL(ctx, rc, "jb_nfvm_create: bad stencil arrays or allocation failure"); }
     *out = d;
     return JB_OK;
@@ -566,6 +580,185 @@ int32_t jb_nfvm_evaluate_flux(jb_nfvm* d, const double* d_p, int64_t nph, int64_
     nfvm_flux_kernel<<<sgrid(ctx, d->nf), 256, 0, ctx->stream>>>(d->nf, d->scheme, d->left.p, d->right.p, d->L_Tl.p, d->L_Tr.p, d->L_ptr.p, d->L_cell.p,
                                                                 d->L_T.p, d->R_Tl.p, d->R_Tr.p, d->R_ptr.p, d->R_cell.p, d->R_T.p, d_p, nph, ph - 1, d_q);
     JB_CHECK_LAUNCH(ctx);
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+
+}  // extern "C"
+
+// ---- conservation law on the NFVM flux with the face-based assembly (PotentialFlow{:fvm}) -------------------------------
+// Reference: ConservationLawFiniteVolumeStorage (src/conservation/fvm_assembly.jl:1-53), declare_pattern (:55-89),
+// align_to_jacobian! (:98-165), fvm_update_face_fluxes_inner! (:194-208: the face flux is evaluated once per stencil cell with
+// that cell carrying the partial), update_linearized_system_equation! / fvm_face_assembly! (:216-283): zero, r = accumulation,
+// J[c,c] = d(accumulation), then per face r[l] += q, r[r] -= q, J[l,cell] += dq/dp_cell, J[r,cell] -= dq/dp_cell.
+//
+// evaluate_flux (src/NFVM/evaluation.jl:1-88) is differentiated in closed form instead of once per stencil cell: with
+// q_l = <cLq, p>, r_l = <cLr, p>, q_R = <cRq, p>, r_R = <cRr, p> (q_r = -q_R, r_r = -r_R) and q = mu_l q_l - mu_r q_r,
+//   dq/dp_s = mu_l cLq_s + mu_r cRq_s + (q_l + q_r) dmu_l/dp_s,   dmu_l = (r_lw d r_rw - r_rw d r_lw) / r_total^2,
+// d r_lw = sigma_l cLr_s, d r_rw = -sigma_r cRr_s (sigma = 1 for :ntpfa, the sign ForwardDiff gives abs for :nmpfa), and
+// dmu = 0 inside the |r_total| < 1e-10 guard. One lane per face, one pass over the face's stencil slots; the scatter uses the
+// warp-aggregated atomics of jb_reduce.cuh (faces of one cell sit in neighbouring lanes).
+__device__ __forceinline__ double4 ld_coef(const double4* __restrict__ p) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+__global__ void __launch_bounds__(256) nfvm_law_init_kernel(i64 nc, i64 nnz, const int32_t* __restrict__ diag, const double* __restrict__ acc,
+                                                            const double* __restrict__ dacc, double* __restrict__ nz, double* __restrict__ r) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (i64)gridDim.x * blockDim.x) nz[i] = 0.0;
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (i64)gridDim.x * blockDim.x) r[c] = acc ? __ldg(acc + c) : 0.0;
+    (void)diag; (void)dacc;
+}
+__global__ void __launch_bounds__(256) nfvm_law_diag_kernel(i64 nc, const int32_t* __restrict__ diag, const double* __restrict__ dacc, double* __restrict__ nz) {
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (i64)gridDim.x * blockDim.x) nz[__ldg(diag + c)] = __ldg(dacc + c);
+}
+__global__ void __launch_bounds__(256) nfvm_law_faces_kernel(i64 nf, int scheme, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                                                             const int32_t* __restrict__ vpos, const int32_t* __restrict__ vars,
+                                                             const double4* __restrict__ coef, const int32_t* __restrict__ lpos,
+                                                             const int32_t* __restrict__ rpos, const double* __restrict__ p, i64 nph, i64 ph0,
+                                                             double* __restrict__ nz, double* __restrict__ r, double* __restrict__ qout) {
+    for (i64 f = (i64)blockIdx.x * blockDim.x + threadIdx.x; f < nf; f += (i64)gridDim.x * blockDim.x) {
+        const int32_t s0 = __ldg(vpos + f), s1 = __ldg(vpos + f + 1);
+        double q_l = 0.0, r_l = 0.0, q_R = 0.0, r_R = 0.0;
+        for (int32_t s = s0; s < s1; s++) {
+            const double ps = __ldg(p + (size_t)__ldg(vars + s) * nph + ph0);
+            const double4 c = ld_coef(coef + s);
+            q_l = fma(c.x, ps, q_l); r_l = fma(c.y, ps, r_l); q_R = fma(c.z, ps, q_R); r_R = fma(c.w, ps, r_R);
+        }
+        double a = 1.0, cc = 0.0, b = 0.0, d = 0.0, q = q_l;
+        if (scheme != 0) {
+            const double q_r = -q_R, r_r = -r_R;
+            double r_lw = r_l, r_rw = r_r, sg_l = 1.0, sg_r = 1.0;
+            if (scheme == 2) { r_lw = fabs(r_l); r_rw = fabs(r_r); sg_l = signbit(r_l) ? -1.0 : 1.0; sg_r = signbit(r_r) ? -1.0 : 1.0; }
+            const double r_total = r_lw + r_rw;
+            double mu_l = 0.5, mu_r = 0.5;
+            if (!(fabs(r_total) < 1e-10)) {
+                mu_l = r_rw / r_total; mu_r = r_lw / r_total;
+                const double w = (q_l + q_r) / (r_total * r_total);
+                b = -w * r_rw * sg_l;      // multiplies cLr_s
+                d = -w * r_lw * sg_r;      // multiplies cRr_s
+            }
+            a = mu_l; cc = mu_r;
+            q = mu_l * q_l - mu_r * q_r;
+        }
+        if (qout) qout[f] = q;
+        const int32_t l = __ldg(left + f), rr = __ldg(right + f);
+        warp_agg_atomic_add(r + l, q);
+        warp_agg_atomic_add(r + rr, -q);
+        for (int32_t s = s0; s < s1; s++) {
+            const double4 c = ld_coef(coef + s);
+            const double dq = a * c.x + b * c.y + cc * c.z + d * c.w;
+            atomicAdd(nz + __ldg(lpos + s), dq);
+            atomicAdd(nz + __ldg(rpos + s), -dq);
+        }
+    }
+}
+
+// discretization_stencil of every face: unique!([left, right, mpfa cells of ft_left..., (left, right,) mpfa cells of ft_right...])
+static void nfvm_build_stencil(jb_nfvm* d) {
+    if (!d->h_vpos.empty()) return;
+    const i64 nf = d->nf;
+    d->h_vpos.assign(nf + 1, 0);
+    std::vector<double4> coef;
+    std::vector<int32_t> cells;
+    auto slot_of = [&](int32_t first, int32_t c) -> int32_t {
+        for (int32_t s = first; s < (int32_t)d->h_vars.size(); s++) if (d->h_vars[s] == c) return s;
+        d->h_vars.push_back(c); coef.push_back(make_double4(0.0, 0.0, 0.0, 0.0));
+        return (int32_t)d->h_vars.size() - 1;
+    };
+    for (i64 f = 0; f < nf; f++) {
+        const int32_t first = (int32_t)d->h_vars.size();
+        const int32_t sl = slot_of(first, d->h_left[f]), sr = slot_of(first, d->h_right[f]);
+        coef[sl].x += d->h_LTl[f]; coef[sr].x += d->h_LTr[f];
+        for (int32_t k = d->h_Lptr[f]; k < d->h_Lptr[f + 1]; k++) { const int32_t s = slot_of(first, d->h_Lcell[k]); coef[s].x += d->h_LT[k]; coef[s].y += d->h_LT[k]; }
+        if (d->scheme > 0) {
+            coef[sl].z += d->h_RTl[f]; coef[sr].z += d->h_RTr[f];
+            for (int32_t k = d->h_Rptr[f]; k < d->h_Rptr[f + 1]; k++) { const int32_t s = slot_of(first, d->h_Rcell[k]); coef[s].z += d->h_RT[k]; coef[s].w += d->h_RT[k]; }
+        }
+        d->h_vpos[f + 1] = (int32_t)d->h_vars.size();
+    }
+    d->d_coef.upload(coef, d->ctx->stream);
+    d->d_vpos.upload(d->h_vpos, d->ctx->stream);
+    d->d_vars.upload(d->h_vars, d->ctx->stream);
+}
+
+extern "C" {
+
+// parity dump of the face stencils (face_cache.vpos / .variables): vpos[nf+1] and vars[vpos[nf]-1], 1-based
+int32_t jb_nfvm_stencil(jb_nfvm* d, int64_t* vpos, int64_t* vars, int64_t cap, int64_t* n_out) {
+    if (!d) return JB_ERR_ARG;
+    nfvm_build_stencil(d);
+    if (n_out) *n_out = (int64_t)d->h_vars.size();
+    if (vpos) for (i64 f = 0; f <= d->nf; f++) vpos[f] = d->h_vpos[f] + 1;
+    if (vars) {
+        if (cap < (int64_t)d->h_vars.size()) return JB_ERR_ARG;
+        for (size_t s = 0; s < d->h_vars.size(); s++) vars[s] = d->h_vars[s] + 1;
+    }
+    return JB_OK;
+}
+// declare_pattern (fvm_assembly.jl:55-89): diagonal, and for every face and stencil cell c: (l,c), (r,c), (c,l), (c,r)
+int32_t jb_nfvm_pattern(jb_nfvm* d, jb_csr** out) {
+    if (!d || !out) return JB_ERR_ARG;
+    nfvm_build_stencil(d);
+    std::vector<int64_t> I, J;
+    I.reserve(d->nc + 4 * d->h_vars.size()); J.reserve(d->nc + 4 * d->h_vars.size());
+    for (i64 c = 1; c <= d->nc; c++) { I.push_back(c); J.push_back(c); }
+    for (i64 f = 0; f < d->nf; f++) {
+        const int64_t l = d->h_left[f] + 1, r = d->h_right[f] + 1;
+        for (int32_t s = d->h_vpos[f]; s < d->h_vpos[f + 1]; s++) {
+            const int64_t c = d->h_vars[s] + 1;
+            I.push_back(l); J.push_back(c); I.push_back(r); J.push_back(c);
+            I.push_back(c); J.push_back(l); I.push_back(c); J.push_back(r);
+        }
+    }
+    return jb_csr_create_from_coo(d->ctx, I.data(), J.data(), (int64_t)I.size(), d->nc, 1, out);
+}
+// align_to_jacobian! (fvm_assembly.jl:98-165): left / right positions of every stencil slot
+int32_t jb_nfvm_align(jb_nfvm* d, jb_csr* A) {
+    if (!d || !A || A->bs != 1 || A->n != d->nc) return JB_ERR_ARG;
+    nfvm_build_stencil(d);
+    jb_ctx* ctx = d->ctx;
+    auto find = [&](int32_t row, int32_t col) -> int32_t {
+        const int32_t* b = A->h_colidx.data() + A->h_rowptr[row];
+        const int32_t* e = A->h_colidx.data() + A->h_rowptr[row + 1];
+        const int32_t* it = std::lower_bound(b, e, col);
+        return (it != e && *it == col) ? (int32_t)(it - A->h_colidx.data()) : -1;
+    };
+    d->h_lpos.assign(d->h_vars.size(), -1); d->h_rpos.assign(d->h_vars.size(), -1);
+    for (i64 f = 0; f < d->nf; f++)
+        for (int32_t s = d->h_vpos[f]; s < d->h_vpos[f + 1]; s++) {
+            d->h_lpos[s] = find(d->h_left[f], d->h_vars[s]); d->h_rpos[s] = find(d->h_right[f], d->h_vars[s]);
+            if (d->h_lpos[s] < 0 || d->h_rpos[s] < 0) JB_FAIL(ctx, JB_ERR_ARG, "jb_nfvm_align: Jacobian alignment failed (entry not allocated)");
+        }
+    for (i64 c = 0; c < d->nc; c++) if (A->h_diag[c] < 0) JB_FAIL(ctx, JB_ERR_ARG, "jb_nfvm_align: diagonal entry not allocated");
+    if (d->d_lpos.upload(d->h_lpos, ctx->stream) != cudaSuccess || d->d_rpos.upload(d->h_rpos, ctx->stream) != cudaSuccess)
+        JB_FAIL(ctx, JB_ERR_ALLOC, "jb_nfvm_align: allocation failed");
+    d->csr = A;
+    return JB_OK;
+}
+int32_t jb_nfvm_positions(jb_nfvm* d, int64_t* left_pos, int64_t* right_pos) {
+    if (!d || !d->csr) return JB_ERR_ARG;
+    for (size_t s = 0; s < d->h_vars.size(); s++) { if (left_pos) left_pos[s] = d->h_lpos[s] + 1; if (right_pos) right_pos[s] = d->h_rpos[s] + 1; }
+    return JB_OK;
+}
+// update_equation! + update_linearized_system_equation! for the law  acc_c + sum_faces (+/-) q_f(p) = 0:
+// d_acc / d_dacc (nc, may be NULL = 0): value and d/dp of the accumulation term; writes nonzeros(jac), d_r (nc) and,
+// if d_q != NULL, the face fluxes.
+int32_t jb_nfvm_assemble(jb_nfvm* d, const double* d_p, int64_t nph, int64_t ph, const double* d_acc, const double* d_dacc, double* d_r,
+                         double* d_q) {
+    if (!d || !d->csr || !d_p || !d_r || nph < 1 || ph < 1 || ph > nph) return JB_ERR_ARG;
+    jb_ctx* ctx = d->ctx;
+    jb_csr* A = d->csr;
+    {
+        ProfScope _ps(ctx, JB_PROF_ASSEMBLY);
+        nfvm_law_init_kernel<<<sgrid(ctx, std::max(A->nnzb, d->nc)), 256, 0, ctx->stream>>>(d->nc, A->nnzb, A->d_diag.p, d_acc, d_dacc, A->d_val.p, d_r);
+        JB_CHECK_LAUNCH(ctx);
+        if (d_dacc) { nfvm_law_diag_kernel<<<sgrid(ctx, d->nc), 256, 0, ctx->stream>>>(d->nc, A->d_diag.p, d_dacc, A->d_val.p); JB_CHECK_LAUNCH(ctx); }
+        nfvm_law_faces_kernel<<<sgrid(ctx, d->nf), 256, 0, ctx->stream>>>(d->nf, d->scheme, d->left.p, d->right.p, d->d_vpos.p, d->d_vars.p, d->d_coef.p,
+                                                                         d->d_lpos.p, d->d_rpos.p, d_p, nph, ph - 1, A->d_val.p, d_r, d_q);
+        JB_CHECK_LAUNCH(ctx);
+    }
+    jb_csr_touch(A);
     JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return JB_OK;
 }
