@@ -1,0 +1,334 @@
+"""GPU parity of the rows SURVEY §8 marks "next", through the C ABI: MultiModel Schur complement (f3), adjoint /
+transposed systems (f4), the NFVM conservation law with Jacobian (a21), secondary variables and tables (f1)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from conftest import to_scipy
+from oracle import widen as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _coo(M):
+    M = sp.coo_matrix(M)
+    return (M.row + 1).astype(np.int64), (M.col + 1).astype(np.int64), M.data.astype(np.float64), M.shape
+
+
+def _schur_setup(J, O, ctx, sizes=(3, 5), dims=(6, 5, 4)):
+    from test_gpu_parity import _jacobian_on_gpu
+    w, s, sim, nz, r = _jacobian_on_gpu(J, O, ctx, dims=dims)
+    n = w["nc"]
+    nz = sim.jac.nonzeros(); r = sim.r.get()
+    B = to_scipy(n, 2, s["rowptr"], s["colidx"], nz).tocsr()
+    rng = np.random.default_rng(12)
+    sc = abs(B).max()
+    Cm = [sp.csr_matrix(sc * 1e-2 * rng.standard_normal((2 * n, m)) * (rng.random((2 * n, m)) < 0.05)) for m in sizes]
+    Dm = [sp.csr_matrix(sc * 1e-2 * rng.standard_normal((m, 2 * n)) * (rng.random((m, 2 * n)) < 0.05)) for m in sizes]
+    Em = [sc * (np.eye(m) + 0.1 * rng.standard_normal((m, m))) for m in sizes]
+    b = [sc * rng.standard_normal(m) for m in sizes]
+    cs, ds, es = [_coo(c) for c in Cm], [_coo(d) for d in Dm], [_coo(e) for e in Em]
+    S = J.MultiLinearizedSystemSchur(sim.jac, [(c[0], c[1], c[3]) for c in cs], [(d[0], d[1], d[3]) for d in ds],
+                                     [(e[0], e[1], e[3][0]) for e in es])
+    assert S.update([c[2] for c in cs], [d[2] for d in ds], [e[2] for e in es]) == 0
+    return w, s, sim, B, Cm, Dm, Em, b, r, S
+
+
+def test_schur_operator_and_reduction_match_oracle(J, O, ctx):
+    """schur_mul!, prepare_linear_solve!, schur_dx_update! (src/linsolve/multimodel.jl:17-160) vs the oracle restatement."""
+    w, s, sim, B, Cm, Dm, Em, b, r, S = _schur_setup(J, O, ctx)
+    n2 = 2 * w["nc"]
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(n2); res0 = rng.standard_normal(n2)
+    C_ = [c.toarray() for c in Cm]; D_ = [d.toarray() for d in Dm]
+    for alpha, beta in [(1.0, 0.0), (2.0, -0.5)]:
+        dres = ctx.transfer(res0)
+        S.mul(dres, ctx.transfer(x), alpha, beta)
+        ref = O.schur_mul(B, C_, D_, Em, x, alpha=alpha, beta=beta, res=res0)
+        assert np.abs(dres.get() - ref).max() <= 1e-12 * np.abs(ref).max()
+    da = ctx.transfer(r)
+    S.prepare_linear_solve(da, b)
+    a_ref = O.schur_prepare(r.copy(), C_, Em, b)
+    assert np.abs(da.get() - a_ref).max() <= 1e-12 * np.abs(a_ref).max()
+    dxs = rng.standard_normal(n2)
+    y = S.update_dx_from_vector(ctx.transfer(-dxs))
+    x_ref, y_ref = O.schur_dx_update(D_, Em, b, dxs)
+    for yi, yr in zip(y, y_ref):
+        assert np.abs(yi - yr).max() <= 1e-11 * max(np.abs(yr).max(), 1e-300)
+
+
+@pytest.mark.parametrize("solver,side", [("gmres", "right"), ("bicgstab", "right"), ("bicgstab", "left"), ("gmres", "left")])
+def test_schur_krylov_solve_equals_full_block_solve(J, O, ctx, solver, side):
+    """The device Krylov solve on S = B - C E^-1 D (ILU(0) of B as preconditioner) followed by the recovery of the eliminated
+    unknowns equals the direct solve of the full block system, with Jutul's sign convention dx = -(J \\ r)."""
+    w, s, sim, B, Cm, Dm, Em, b, r, S = _schur_setup(J, O, ctx)
+    n2 = 2 * w["nc"]
+    full = sp.bmat([[B, Cm[0], Cm[1]], [Dm[0], sp.csr_matrix(Em[0]), None], [Dm[1], None, sp.csr_matrix(Em[1])]]).tocsc()
+    z = spla.spsolve(full, np.concatenate([r] + b))
+    kry = J.GenericKrylov(sim.jac, solver, sim.prec, relative_tolerance=1e-12, max_iterations=300, precond_side=side)
+    S.attach(kry)
+    da = ctx.transfer(r)
+    S.prepare_linear_solve(da, b)
+    dx = ctx.zeros(n2)
+    ok, its, hist, st = J.linear_solve(kry, da, dx)
+    assert ok, (st, its, hist[-1] / hist[0])
+    y = S.update_dx_from_vector(dx)
+    assert np.linalg.norm(dx.get() + z[:n2]) <= 1e-8 * np.linalg.norm(z[:n2])
+    off = n2
+    for yi in y:
+        assert np.linalg.norm(yi + z[off: off + yi.shape[0]]) <= 1e-8 * max(np.linalg.norm(z[off: off + yi.shape[0]]), 1e-30)
+        off += yi.shape[0]
+    # detaching restores the plain operator: the same handle now solves B x = r
+    S.detach(kry)
+    ok, its, hist, st = J.linear_solve(kry, ctx.transfer(r), dx)
+    xb = spla.spsolve(B.tocsc(), r)
+    assert ok and np.linalg.norm(dx.get() + xb) <= 1e-8 * np.linalg.norm(xb)
+
+
+def test_schur_multimodel_known_answer(J, ctx):
+    """test/test_systems/multimodel.jl:4-37 through the device: two ScalarTestSystems with forces +1 / -1 and the
+    skew-symmetric cross term, groups = [1, 2] with the Schur reduction: XA = 1/3, XB = -1/3 (default GMRES)."""
+    dt = 1.0
+    A = J.build_sparse_matrix(ctx, [1], [1], 1, 1)
+    A.set_nonzeros(np.array([1.0 / dt + 1.0]))
+    S = J.MultiLinearizedSystemSchur(A, [([1], [1], (1, 1))], [([1], [1], (1, 1))], [([1], [1], 1)])
+    assert S.update([[-1.0]], [[-1.0]], [[1.0 / dt + 1.0]]) == 0
+    rA, rB = -1.0, 1.0
+    da = ctx.transfer(np.array([rA]))
+    S.prepare_linear_solve(da, [np.array([rB])])
+    kry = J.GenericKrylov(A, "gmres", None, relative_tolerance=1e-14)
+    S.attach(kry)
+    dx = ctx.zeros(1)
+    ok, its, hist, st = J.linear_solve(kry, da, dx)
+    y = S.update_dx_from_vector(dx)
+    assert np.isclose(0.0 + dx.get()[0], 1.0 / 3.0, rtol=1e-14) and np.isclose(0.0 + y[0][0], -1.0 / 3.0, rtol=1e-14)
+
+
+def test_schur_errors(J, ctx):
+    A = J.build_sparse_matrix(ctx, [1, 2], [1, 2], 2, 1)
+    with pytest.raises(J.JutulB200Error):
+        J.MultiLinearizedSystemSchur(A, [([3], [1], (2, 1))], [([1], [1], (1, 2))], [([1], [1], 1)])     # C row outside B
+    S = J.MultiLinearizedSystemSchur(A, [([1], [1], (2, 1))], [([1], [2], (1, 2))], [([1], [1], 1)])
+    assert S.update([[1.0]], [[1.0]], [[0.0]]) == J.JB_BAD_PIVOT                                           # singular E
+    with pytest.raises(J.JutulB200Error):
+        S.mul(ctx.zeros(2), ctx.zeros(2))                                                                # no factorised values
+
+
+# ------------------------------------------------------------------ f4: adjoint systems
+def test_adjoint_jacobian_and_solve(J, O, ctx):
+    """J^T as the reference's as_adjoint layout holds it (src/equations.jl:101-108): pattern and values equal the oracle's
+    adjoint alignment; the Lagrange-multiplier solve J^T lambda = rhs (src/ad/gradients.jl:519-590) with ILU(0)-BiCGStab on the
+    device equals the direct solve; sens_add_mult! (rhs += J^T lambda) is the device SpMV."""
+    from test_gpu_parity import _jacobian_on_gpu
+    w, s, sim, nz, r = _jacobian_on_gpu(J, O, ctx, dims=(7, 6, 5))
+    n = w["nc"]
+    nz = sim.jac.nonzeros()
+    JT = sim.jac.adjoint()
+    JT.update_adjoint()
+    rpT, ciT = JT.pattern()
+    rp_o, ci_o = O.csr_from_coo(*[a for a in _pattern_transposed(s)], n)
+    assert np.array_equal(rpT, rp_o) and np.array_equal(ciT, ci_o)
+    # values: every entry (row, col, eq, partial) sits at the adjoint position of the transposed pattern
+    nzT_o = np.zeros_like(nz)
+    rowptr, colidx = s["rowptr"], s["colidx"]
+    for row in range(1, n + 1):
+        for k in range(rowptr[row - 1] - 1, rowptr[row] - 1):
+            for eq in (1, 2):
+                for d in (1, 2):
+                    src = O.block_nz_index(k + 1, 2, eq, d) - 1
+                    nzT_o[W.find_jac_position_block(rpT, ciT, row, int(colidx[k]), eq, d, 2, adjoint=True) - 1] = nz[src]
+    assert np.array_equal(JT.nonzeros(), nzT_o)
+    A = to_scipy(n, 2, rowptr, colidx, nz)
+    AT = to_scipy(n, 2, rpT, ciT, JT.nonzeros())
+    assert abs(AT - A.T).max() == 0.0
+    rng = np.random.default_rng(8)
+    rhs = rng.standard_normal(2 * n) * np.abs(r).max()
+    prec = J.ILUZeroPreconditioner(JT)
+    kry = J.GenericKrylov(JT, "bicgstab", prec, relative_tolerance=1e-11, max_iterations=300)
+    dlam = ctx.zeros(2 * n)
+    ok, its, hist, st = J.linear_solve(kry, ctx.transfer(rhs), dlam)
+    lam = spla.spsolve(A.T.tocsc(), rhs)
+    assert ok and np.linalg.norm(dlam.get() + lam) <= 1e-8 * np.linalg.norm(lam)
+    # sens_add_mult!: rhs += op * lambda
+    acc = ctx.transfer(rhs)
+    JT.mul(acc, ctx.transfer(lam), 1.0, 1.0)
+    ref = rhs + A.T @ lam
+    assert np.abs(acc.get() - ref).max() <= 1e-13 * (abs(A.T) @ np.abs(lam)).max()      # 1e-13 of |A^T||lambda|, as for the SpMV
+    # the transposed copy follows the source: new values, new transpose
+    sim.jac.set_nonzeros(2.0 * nz)
+    JT.update_adjoint()
+    assert np.array_equal(JT.nonzeros(), 2.0 * nzT_o)
+
+
+def _pattern_transposed(s):
+    rowptr, colidx = s["rowptr"], s["colidx"]
+    rows = np.repeat(np.arange(1, len(rowptr)), np.diff(rowptr))
+    return colidx.astype(np.int64), rows.astype(np.int64)
+
+
+# ------------------------------------------------------------------ a21: NFVM law with Jacobian
+@pytest.mark.parametrize("scheme", ["linear", "ntpfa", "nmpfa"])
+def test_nfvm_law_assembly_matches_oracle(J, O, ctx, scheme):
+    """Stencils, pattern and alignment bit-exact; residual, Jacobian and face fluxes of the :fvm assembly within 1e-12 of the
+    oracle, whose partials come from Dual arithmetic on evaluate_flux (one evaluation per stencil cell)."""
+    from test_oracle_widen import _random_nfvm
+    rng = np.random.default_rng(21)
+    nc, nf = 300, 900
+    left, right, L, R = _random_nfvm(rng, nc, nf, nm=4)
+    Rn = None if scheme == "linear" else R
+    disc = J.NFVMDiscretization(ctx, left, right, nc, L, Rn, scheme=scheme)
+    vpos, vars_ = disc.stencil()
+    vpos_o, vars_o = W.nfvm_discretization_stencil(left, right, L, Rn)
+    assert np.array_equal(vpos, vpos_o) and np.array_equal(vars_, vars_o)
+    jac = disc.declare_pattern()
+    I, Jc = W.fvm_declare_pattern(nc, left, right, vpos_o, vars_o)
+    rp_o, ci_o = O.csr_from_coo(I, Jc, nc)
+    rp, ci = jac.pattern()
+    assert np.array_equal(rp, rp_o) and np.array_equal(ci, ci_o)
+    lp, rpz = disc.align_to_jacobian(jac)
+    lp_o, rp2_o = W.fvm_align(left, right, vpos_o, vars_o, rp_o, ci_o)
+    assert np.array_equal(lp, lp_o) and np.array_equal(rpz, rp2_o)
+    p = rng.uniform(1.0, 2.0, nc)
+    acc = rng.normal(size=nc); dacc = rng.uniform(1.0, 2.0, nc)
+    dpos = np.array([W.find_jac_position_block(rp_o, ci_o, c, c, 1, 1, 1) for c in range(1, nc + 1)])
+    nz_o, r_o, q_o = W.fvm_assemble_nfvm(nc, left, right, L, R, scheme, p, vpos_o, vars_o, lp_o, rp2_o, dpos, len(ci_o), acc, dacc)
+    r = ctx.zeros(nc); q = ctx.zeros(nf)
+    disc.update_equation_and_linearized_system(ctx.transfer(p), r, ctx.transfer(acc), ctx.transfer(dacc), q)
+    assert np.abs(q.get() - q_o).max() <= 1e-13 * np.abs(q_o).max()
+    assert np.abs(r.get() - r_o).max() <= 1e-12 * np.abs(r_o).max()
+    scale = np.abs(nz_o).max()
+    assert np.abs(jac.nonzeros() - nz_o).max() <= 1e-11 * scale
+    # the assembled system is usable by the device solver: one Newton update reduces the residual of the (linear) scheme
+    if scheme == "linear":
+        kry = J.GenericKrylov(jac, "gmres", J.ILUZeroPreconditioner(jac), relative_tolerance=1e-12, max_iterations=300)
+        dx = ctx.zeros(nc)
+        ok, its, hist, st = J.linear_solve(kry, r, dx)
+        assert ok
+        p1 = p + dx.get()
+        # for the linear scheme with d(acc) held fixed the Newton step solves J dp = -r exactly
+        Jm = sp.csr_matrix((nz_o, ci_o - 1, rp_o - 1), shape=(nc, nc))
+        assert np.abs(Jm @ (p1 - p) + r_o).max() <= 1e-8 * np.abs(r_o).max()
+
+
+# ------------------------------------------------------------------ f1: tables and secondary variables
+@pytest.mark.parametrize("constant_dx", [True, False, None])
+def test_tables_match_oracle_and_reference_known_answers(J, ctx, constant_dx):
+    rng = np.random.default_rng(4)
+    x = np.arange(0, 4.0001, 0.1)
+    I = J.get_1d_interpolator(ctx, x, np.sin(x), constant_dx=constant_dx)
+    Io = W.get_1d_interpolator(x, np.sin(x), constant_dx=constant_dx)
+    assert I.info()["lookup_x"] == (Io.lookup is not None)
+    xs = np.concatenate([rng.uniform(-1.0, 5.0, 2000), x, [np.pi / 2]])
+    f = ctx.zeros(xs.shape[0]); df = ctx.zeros(xs.shape[0])
+    I.interpolate(ctx.transfer(xs), f, df)
+    ref = [Io(W.Dual(v, np.array([1.0]))) for v in xs]
+    fv, dfv = f.get(), df.get()
+    assert np.abs(fv - np.array([r.v for r in ref])).max() <= 1e-15
+    assert np.abs(dfv - np.array([r.d[0] for r in ref])).max() <= 1e-13
+    assert abs(fv[-1] - 1.0) <= 1e-2                                        # test/utils.jl:159
+    F = J.get_1d_interpolator(ctx, [0.0, 0.5, 1.0], [0.0, 0.25, 1.0], constant_dx=constant_dx)
+    g = ctx.zeros(4)
+    F.interpolate(ctx.transfer(np.array([0.5, 0.25, -1.0, 1.5])), g)
+    assert np.allclose(g.get(), [0.25, 0.125, 0.0, 1.0], rtol=1e-15)          # test/utils.jl:164-165,175-176 (capped ends)
+    # 2-D (test/utils.jl:180-230)
+    fxy = lambda a, b: np.sin(a) + np.cos(b) + 0.5 * a
+    gx = np.linspace(0.0, 4.0, 10); gy = np.linspace(0.0, 5.0, 8)
+    fs = fxy(gx[:, None], gy[None, :])
+    I2 = J.get_2d_interpolator(ctx, gx, gy, fs, constant_dx=constant_dx, constant_dy=constant_dx)
+    I2o = W.get_2d_interpolator(gx, gy, fs, constant_dx=constant_dx, constant_dy=constant_dx)
+    X, Y = np.meshgrid(gx, gy, indexing="ij")
+    px = np.concatenate([X.ravel(), rng.uniform(-1.0, 5.0, 1500)]); py = np.concatenate([Y.ravel(), rng.uniform(-1.0, 6.0, 1500)])
+    f2 = ctx.zeros(px.shape[0]); dfx = ctx.zeros(px.shape[0]); dfy = ctx.zeros(px.shape[0])
+    I2.interpolate(ctx.transfer(px), ctx.transfer(py), f2, dfx, dfy)
+    ref2 = [I2o(W.Dual(a, np.array([1.0, 0.0])), W.Dual(b, np.array([0.0, 1.0]))) for a, b in zip(px, py)]
+    assert np.abs(f2.get() - np.array([r.v for r in ref2])).max() <= 1e-14
+    assert np.abs(dfx.get() - np.array([r.d[0] for r in ref2])).max() <= 1e-13
+    assert np.abs(dfy.get() - np.array([r.d[1] for r in ref2])).max() <= 1e-13
+    assert np.allclose(f2.get()[: X.size], fxy(X.ravel(), Y.ravel()))          # nodes reproduced
+
+
+def _property_graph(J, W_, ctx, mode):
+    xs = np.linspace(5e4, 4e5, 8)
+    mu = 1e-3 * (1 + 1e-6 * xs) + 1e-5 * np.sin(xs / 3e4)
+    gx = np.linspace(5e4, 4e5, 6); gy = np.linspace(0.0, 1.0, 5)
+    fs = 1.0 + 1e-6 * gx[:, None] * (0.5 + gy[None, :] ** 2)
+    if mode == "gpu":
+        t1 = J.get_1d_interpolator(ctx, xs, mu); t2 = J.get_2d_interpolator(ctx, gx, gy, fs)
+    else:
+        t1 = W_.get_1d_interpolator(xs, mu); t2 = W_.get_2d_interpolator(gx, gy, fs)
+    # declared out of dependency order on purpose: the library has to sort
+    defs = {
+        "Pressure": dict(kind="primary"), "Saturation": dict(kind="primary"), "PoreVolume": dict(kind="parameter"),
+        "Mass": dict(kind="product", deps=["Density", "Saturation", "PoreVolume"], c=[1.0], output=True),
+        "Mobility": dict(kind="quotient", deps=["Kr", "Viscosity"], c=[1.0], output=True),
+        "OilMobility": dict(kind="quotient", deps=["KrO", "ShrinkageVisc"], c=[2.0], output=True),
+        "KrO": dict(kind="power", deps=["So"], c=[0.8, 2.5, 0.15, 0.7]),
+        "So": dict(kind="affine", deps=["Saturation"], c=[1.0, -1.0]),
+        "Kr": dict(kind="power", deps=["Saturation"], c=[0.9, 2.0, 0.1, 0.8]),
+        "Viscosity": dict(kind="table1d", deps=["Pressure"], c=[1.0], table=t1),
+        "ShrinkageVisc": dict(kind="table2d", deps=["Pressure", "So"], c=[1e-3], table=t2),
+        "Density": dict(kind="exp", deps=["Pressure"], c=[1000.0, 4.5e-10, 1e5], output=True),
+        "Half": dict(kind="const", c=[0.5]),
+        "Blend": dict(kind="affine", deps=["Mobility", "OilMobility", "Half"], c=[0.25, 1.0, -2.0, 3.0], output=True),
+    }
+    return defs
+
+
+def test_secondary_variable_graph_matches_oracle(J, ctx):
+    """The fused graph kernel against update_secondary_variables_state! on Duals in sort_secondary_variables! order: same
+    order (bit-exact integer work), values and partials to 1e-13 relative."""
+    rng = np.random.default_rng(17)
+    nc = 5000
+    p = rng.uniform(4e4, 4.2e5, nc); sw = rng.uniform(0.0, 1.0, nc); pv = rng.uniform(1.0, 2.0, nc)
+    defs = _property_graph(J, W, ctx, "gpu")
+    sv = J.SecondaryVariables(ctx, nc, defs)
+    defs_o = _property_graph(J, W, ctx, "cpu")
+    prim = [k for k, v in defs_o.items() if v["kind"] == "primary"]; par = [k for k, v in defs_o.items() if v["kind"] == "parameter"]
+    sec = {k: v.get("deps", []) for k, v in defs_o.items() if v["kind"] not in ("primary", "parameter")}
+    order_o = W.sort_secondary_variables(prim, sec, par)
+    order_g = [n for n in sv.order() if n in sec]
+    assert order_g == order_o
+    state = {"Pressure": ctx.transfer(p), "Saturation": ctx.transfer(sw), "PoreVolume": ctx.transfer(pv)}
+    out = {n: ctx.zeros(3 * nc) for n in sv.outputs}
+    sv.update_secondary_variables(state, out)
+    e = np.eye(2)
+    st = {"Pressure": W.Dual(p, e[:, :1] * np.ones(nc)), "Saturation": W.Dual(sw, e[:, 1:] * np.ones(nc)), "PoreVolume": pv}
+    for k, v in defs_o.items():
+        v.setdefault("c", [0.0])
+    W.update_secondary_variables_state(st, defs_o, order_o)
+    for n in sv.outputs:
+        g = out[n].get().reshape(3, nc)
+        o = st[n]
+        sv_ = max(np.abs(o.v).max(), 1e-300)
+        assert np.abs(g[0] - o.v).max() <= 1e-13 * sv_, n
+        for q in range(2):
+            sd = max(np.abs(o.d[q]).max(), 1e-300)
+            assert np.abs(g[1 + q] - o.d[q]).max() <= 1e-12 * sd, (n, q)
+
+
+def test_secondary_variable_graph_errors(J, ctx):
+    with pytest.raises(J.JutulB200Error):
+        J.SecondaryVariables(ctx, 4, {"P": dict(kind="primary"), "A": dict(kind="exp", deps=["B"]), "B": dict(kind="exp", deps=["A"])})   # cycle
+    with pytest.raises(KeyError):
+        J.SecondaryVariables(ctx, 4, {"P": dict(kind="primary"), "A": dict(kind="exp", deps=["Missing"])})
+    with pytest.raises(J.JutulB200Error):
+        J.SecondaryVariables(ctx, 4, {"A": dict(kind="const", c=[1.0])})                                                                 # no primary
+
+
+def test_faces_variant_warp_aggregated_atomics(J, O, ctx):
+    """Variant B of the two-phase assembly (fvm_face_assembly!) now scatters with warp-aggregated atomics: same result as the
+    row-owner kernel within the reassociation tolerance."""
+    from test_gpu_parity import _setup
+    w, s = _setup(J, O, ctx, (11, 9, 7), True)
+    sim = J.TwoPhaseSimulator(ctx, w["N"], w["nc"], w["Tf"], w["gdz"], w["pv"], w["params"], ordering=None)
+    sim.set_forces(w["src_cells"], w["src_vals"])
+    sim.set_state(w["p0"], w["sw0"])
+    p1 = w["p0"] * (1 + 1e-3 * np.sin(np.arange(w["nc"])))
+    sim.p.set(p1)
+    sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r, variant="cells")
+    nz_a, r_a = sim.jac.nonzeros(), sim.r.get()
+    sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r, variant="faces")
+    nz_b, r_b = sim.jac.nonzeros(), sim.r.get()
+    assert np.abs(nz_a - nz_b).max() <= 1e-11 * np.abs(nz_a).max()
+    assert np.abs(r_a - r_b).max() <= 1e-10 * np.abs(r_a).max()
