@@ -58,7 +58,7 @@ typedef struct jb_schur jb_schur;
 typedef struct jb_table jb_table;
 typedef struct jb_varprog jb_varprog;
 
-/* ---- lifecycle: JutulContext (src/core_types/contexts/*.jl, src/context.jl:65-78:
+/* ---- lifecycle: JutulContext (src/core_types/contexts/, src/context.jl:65-78:
  *      initialize_context!, synchronize) ------------------------------------ */
 int32_t jb_version(void);
 int32_t jb_ctx_create(int32_t device, jb_ctx** out);

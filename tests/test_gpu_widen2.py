@@ -332,3 +332,50 @@ def test_faces_variant_warp_aggregated_atomics(J, O, ctx):
     nz_b, r_b = sim.jac.nonzeros(), sim.r.get()
     assert np.abs(nz_a - nz_b).max() <= 1e-11 * np.abs(nz_a).max()
     assert np.abs(r_a - r_b).max() <= 1e-10 * np.abs(r_a).max()
+
+
+# ------------------------------------------------------------------ b: the boundary driven from plain C (stand-in for ccall)
+def test_newton_iteration_from_plain_c_matches_oracle(J, O, tmp_path):
+    """tests/abi_c_harness.c (dlopen, no Python in that process) runs one Newton iteration in the call order of the Julia glue;
+    residual, Jacobian, increment and updated state are compared with the oracle."""
+    import subprocess
+    from conftest import oracle_system
+    from test_abi import build_c_harness
+    w = J.workloads.unstructured_hex(9, 8, 6)
+    nc = w["nc"]; N = np.ascontiguousarray(w["N"], dtype=np.int64); nf = N.shape[0]
+    p1 = w["p0"] * (1 + 1e-3 * np.sin(np.arange(nc)))
+    s = np.empty((nc, 2)); s[:, 0] = w["sw0"]; s[:, 1] = 1.0 - w["sw0"]
+    M0 = O.mass_2ph(w["pv"], w["params"], w["p0"], w["sw0"])
+    src_cells = np.ascontiguousarray(w["src_cells"], dtype=np.int64); src_vals = np.ascontiguousarray(w["src_vals"], dtype=np.float64)
+    rtol = 1e-10
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(fin, "wb") as f:
+        f.write(np.array([nc, nf, src_cells.shape[0]], dtype=np.int64).tobytes())
+        f.write(np.array([w["dt"], rtol], dtype=np.float64).tobytes())
+        for a in (N, w["Tf"], w["gdz"], w["pv"], w["params"], p1, s, M0):
+            f.write(np.ascontiguousarray(a).tobytes())
+        f.write(src_cells.tobytes()); f.write(src_vals.tobytes())
+    res = subprocess.run([build_c_harness(), J._lib.SO_PATH, "run", str(fin), str(fout)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr + res.stdout
+    raw = open(fout, "rb").read()
+    nnzb, iters, status = np.frombuffer(raw[:24], dtype=np.int64)
+    body = np.frombuffer(raw[24:], dtype=np.float64)
+    errors, body = body[:2], body[2:]
+    r_c, body = body[:2 * nc], body[2 * nc:]
+    nz_c, body = body[:4 * nnzb], body[4 * nnzb:]
+    dx_c, body = body[:2 * nc], body[2 * nc:]
+    p_c, s_c = body[:nc], body[nc:]
+    sy = oracle_system(O, w)
+    assert nnzb == sy["colidx"].shape[0] and status == 0
+    nz, r = O.assemble_2ph(sy["hf"], sy["diag_pos"], sy["hf_pos"], w["Tf"], w["gdz"], w["pv"], w["params"], p1, w["sw0"], M0, w["dt"], nnzb,
+                           w["src_cells"], w["src_vals"])
+    assert np.abs(r_c - r).max() <= 1e-11 * np.abs(r).max() and np.abs(nz_c - nz).max() <= 1e-11 * np.abs(nz).max()
+    assert np.allclose(errors, O.maxabs_rows(r, 2), rtol=1e-11)
+    ilu = O.ILU0(nc, 2, sy["rowptr"], sy["colidx"]); ilu.factor(nz)
+    x, st, its, hist = O.bicgstab(nc, 2, sy["rowptr"], sy["colidx"], nz, r, ilu, rtol=rtol, itmax=1000)
+    assert abs(int(iters) - its) <= max(2, its // 10)
+    assert np.linalg.norm(dx_c + x) <= 1e-7 * np.linalg.norm(x)
+    p_o = p1.copy(); s_o = s.copy().ravel()
+    O.update_scalar(p_o, dx_c, dx_stride=2)
+    O.update_fraction_pair(s_o, dx_c[1:], abs_max=0.2, dx_stride=2)
+    assert np.array_equal(p_c, p_o) and np.array_equal(s_c, s_o)         # the update is bit-exact given the same dx
