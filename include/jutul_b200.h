@@ -428,6 +428,11 @@ int32_t jb_twophase_perform_step_host(jb_twophase* m, jb_ilu* ilu, jb_krylov* ks
                                       double ds_abs_max, double* errors, int32_t* converged,
                                       int32_t* lin_iters);
 
+/* update_after_step! (src/models.jl:983-1011) for that host-buffer stepping: state0 <- state on the device — the conserved
+ * masses of the accepted state are formed from the resident primaries of the last (converged) perform_step_host call, so the
+ * next timestep passes M0 = NULL and nothing crosses the bus between steps. */
+int32_t jb_twophase_update_after_step(jb_twophase* m);
+
 #ifdef __cplusplus
 }
 #endif

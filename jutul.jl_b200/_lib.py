@@ -135,6 +135,7 @@ PROTOTYPES = {
     "jb_dist_allreduce": (I32, [P, PF64, I32, I32]),
     "jb_krylov_set_dist": (I32, [P, P]),
     "jb_twophase_set_owned": (I32, [P, I64]),
+    "jb_twophase_update_after_step": (I32, [P]),
     "jb_twophase_perform_step_host": (I32, [P, P, P, PF64, PF64, PF64, F64, F64, F64, F64, I32, F64, F64, PF64, PI32, PI32]),
 }
 

@@ -168,6 +168,20 @@ int32_t jb_twophase_set_permutation(jb_twophase* m, jb_perm* p) {
 //   -> update_linearized_system! -> check_convergence (max|r| per equation <= tol)
 //   -> [not converged] update_preconditioner! + linear_solve! + update_primary_variables!
 //   -> D2H(p, s).
+// update_after_step! (src/models.jl:983-1011) for the host-buffer stepping below: state0 <- state on the device. The primaries
+// of the last jb_twophase_perform_step_host call are resident (a converged call uploads them and changes nothing), so the
+// conserved masses of the accepted state are formed in place: no transfer. The next step passes M0 = NULL.
+int32_t jb_twophase_update_after_step(jb_twophase* m) {
+    if (!m) return JB_ERR_ARG;
+    jb_ctx* ctx = m->t->mesh->ctx;
+    const i64 nc = m->t->mesh->nc;
+    if (m->d_p.n != (size_t)nc || m->d_M0.n != (size_t)2 * nc) JB_FAIL(ctx, JB_ERR_ARG, "jb_twophase_update_after_step: no resident state (call jb_twophase_perform_step_host first)");
+    int rc = jb_launch_twophase_mass(m, m->d_p.p, m->d_s.p, m->d_M0.p);
+    if (rc != JB_OK) return rc;
+    m->M0_resident = true;
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
 int32_t jb_twophase_perform_step_host(jb_twophase* m, jb_ilu* ilu, jb_krylov* ks, double* p, double* s, const double* M0, double dt, double tol,
                                       double rtol, double atol, int32_t itmax, double dp_abs_max, double ds_abs_max, double* errors,
                                       int32_t* converged, int32_t* lin_iters) {

@@ -82,7 +82,7 @@ static int csr_finish(jb_ctx* ctx, jb_csr* A) {
     if (!A->h_chunks.empty() && A->d_chunks.upload(A->h_chunks, s) != cudaSuccess) return JB_ERR_ALLOC;
     // TMA-staged SpMV (2x2 blocks)
     A->h_s2.clear(); A->s2_ok = false;
-    if (A->bs == 2 && A->n > 0 && jb_s2_cut(A->h_rowptr, 0, (int32_t)A->n, A->h_s2)) {
+    if (A->bs == 2 && A->n > 0 && jb_s2_cut(A->h_rowptr, 0, (int32_t)A->n, A->h_s2, ctx->sm_count * JB_S2_CTAS_PER_SM)) {
         if (A->d_s2.upload(A->h_s2, s) != cudaSuccess) return JB_ERR_ALLOC;
         A->s2_ok = true;
     }
@@ -439,7 +439,7 @@ int jb_ilu_symbolic(jb_ilu* F, const int64_t* partition) {
         tab.clear(); lev_tab.assign(nlev + 1, 0);
         for (int l = 0; l < nlev; l++) {
             lev_tab[l] = (int32_t)tab.size();
-            if (F->s2_ok && !jb_s2_cut(ptrT, lev_ptr[l], lev_ptr[l + 1], tab)) F->s2_ok = false;
+            if (F->s2_ok && !jb_s2_cut(ptrT, lev_ptr[l], lev_ptr[l + 1], tab, F->csr->ctx->sm_count * JB_S2_CTAS_PER_SM)) F->s2_ok = false;
         }
         lev_tab[nlev] = (int32_t)tab.size();
     };

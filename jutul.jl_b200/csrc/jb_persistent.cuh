@@ -23,7 +23,8 @@ inline size_t pk_ky_base(int64_t n_owned, int64_t n_local) { return pk_stage_bas
 inline size_t pk_kz_base(int64_t n_owned, int64_t n_local) { return pk_ky_base(n_owned, n_local) + (size_t)n_local * 4; }
 inline size_t pk_sym_words(int64_t n_owned, int64_t n_local) { return pk_kz_base(n_owned, n_local) + (size_t)n_local * 4; }
 
-struct PKSync { unsigned count, gen, push_count, abort; };
+// bar: grid-barrier word (bit 31 = phase, low bits = arrivals of the barrier in flight); count: arrivals of a reducing barrier
+struct PKSync { unsigned count, bar, push_count, abort; };
 
 struct PKDist {
     int world, rank, nneigh;

@@ -23,6 +23,7 @@
 #define JB_S2_CAP 448
 #define JB_S2_THREADS 128
 #define JB_S2_IDENT_ROWS 512   // rows per identity super-chunk of the SpMV table (krylov.cu)
+#define JB_S2_CTAS_PER_SM 6    // resident CTAs per SM of the s2 kernels (launch bounds): grid of the persistent kernels = SMs x 6
 
 struct __align__(16) S2Stage {
     double val[JB_S2_CAP * 4];        // 32-byte blocks: always aligned, no lead
@@ -125,11 +126,29 @@ __device__ __forceinline__ double s2_row_sum(const S2Stage& S, int lead_col, int
 }
 
 // Host: cut stored rows [r0, r1) (offsets ptr) into chunks; returns false if a row exceeds the stage.
-inline bool jb_s2_cut(const std::vector<int32_t>& ptr, int32_t r0, int32_t r1, std::vector<S2Chunk>& out) {
+// balance_ctas > 0: the persistent kernels deal chunk k to CTA k mod grid, so with n chunks of 64 rows the busiest CTA
+// streams ceil(n / grid) * 64 rows while the average is n * 64 / grid — 8 % more at 11.1 chunks per CTA (1.26M cells per
+// GPU). The rows are therefore cut into a multiple of `balance_ctas` chunks of equal size (<= 64 rows): every CTA gets the
+// same number of rows. Large row sets (>= 64 chunks per CTA, quantisation < 1.6 %) keep full 64-row chunks.
+inline bool jb_s2_cut(const std::vector<int32_t>& ptr, int32_t r0, int32_t r1, std::vector<S2Chunk>& out, int balance_ctas = 0) {
     int32_t start = r0;
+    int64_t target = 0;     // number of chunks aimed at (0: greedy 64-row chunks)
+    const int64_t rows = (int64_t)r1 - r0;
+    if (balance_ctas > 0 && rows > 0) {
+        const int64_t full = (rows + JB_S2_ROWS - 1) / JB_S2_ROWS;
+        const int64_t per_cta = (full + balance_ctas - 1) / balance_ctas;
+        if (per_cta < 64) target = per_cta * balance_ctas;
+    }
+    int64_t made = 0;
     while (start < r1) {
+        int32_t limit = JB_S2_ROWS;
+        if (target > made) {      // spread the remaining rows evenly over the remaining chunks of the target
+            const int64_t left = (int64_t)r1 - start, chunks_left = target - made;
+            limit = (int32_t)std::min<int64_t>(JB_S2_ROWS, std::max<int64_t>(1, (left + chunks_left - 1) / chunks_left));
+        }
         int32_t end = start;
-        while (end < r1 && end - start < JB_S2_ROWS && ptr[end + 1] - ptr[start] <= JB_S2_CAP) end++;
+        while (end < r1 && end - start < limit && ptr[end + 1] - ptr[start] <= JB_S2_CAP) end++;
+        made++;
         if (end == start) return false;
         S2Chunk c;
         c.t0 = start; c.nr = end - start; c.e0 = ptr[start]; c.cnt = ptr[end] - ptr[start]; c.flags = 0; c.pad0 = c.pad1 = c.pad2 = 0;

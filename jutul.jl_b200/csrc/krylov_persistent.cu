@@ -66,10 +66,13 @@ __device__ __forceinline__ unsigned long long pk_globaltimer() {
 }
 // Bounded spins: a lost CTA or peer raises the abort word instead of hanging the GPU.
 #define PK_SPIN_LIMIT_NS 40000000000ULL   // 40 s (a peer may itself be waiting ~30 s for a third rank)
-__device__ __forceinline__ bool pk_spin_gen(const PKSync* S, unsigned gen) {
+// Wait until the phase bit of the barrier word differs from the one in `old` (volatile polls, as cooperative groups does:
+// measured 2.0 us per barrier at 888 CTAs against 3.3 us for an atomic counter + release store + acquire polls,
+// profiles/r02_barrier_microbench.txt).
+__device__ __forceinline__ bool pk_spin_flip(const PKSync* S, unsigned old) {
     const unsigned long long t0 = pk_globaltimer();
     unsigned n = 0;
-    while (pk_ld_acquire_gpu(&S->gen) == gen) {
+    while (((old ^ *reinterpret_cast<const volatile unsigned*>(&S->bar)) & 0x80000000u) == 0u) {
         if ((++n & 1023u) == 0) {
             if (pk_ld_acquire_gpu(&S->abort) != 0) return false;
             if (pk_globaltimer() - t0 > PK_SPIN_LIMIT_NS) { atomicExch(const_cast<unsigned*>(&S->abort), 1u); return false; }
@@ -91,7 +94,6 @@ __device__ __forceinline__ bool pk_spin_peer(const unsigned long long* flag, uns
 }
 
 struct PKState {
-    unsigned gen;                    // generation of the grid barrier this CTA waits for next
     unsigned long long ar_epoch;     // all-reduce epoch (continues jb_dist::ar_epoch)
     unsigned long long halo_epoch;   // epoch of the in-kernel halo exchanges
     unsigned long long t_prev;       // phase timer (CTA 0, thread 0)
@@ -105,24 +107,20 @@ __device__ __forceinline__ void pk_phase_time(const PKArgs& a, PKState& st, int 
     }
 }
 
-// Grid barrier. Returns false when the solve was aborted (timeout).
+// Grid barrier: ONE atomic per CTA on one word. CTA 0 adds 2^31 - (grid - 1), every other CTA adds 1, so the word's phase bit
+// flips exactly when the last CTA arrives and its low bits are back where they were — arrival and release are the same
+// operation (the protocol of cooperative groups' grid.sync()). Returns false when the solve was aborted (timeout).
 __device__ __forceinline__ bool pk_sync(const PKArgs& a, PKState& st, int* flag_s) {
     __syncthreads();
     if (threadIdx.x == 0) {
+        const unsigned nb = blockIdx.x == 0 ? 0x80000000u - (gridDim.x - 1u) : 1u;
         __threadfence();
-        bool ok = true;
-        if (atomicAdd(&a.sync->count, 1u) == gridDim.x - 1) {
-            a.sync->count = 0;
-            __threadfence();
-            pk_st_release_gpu(&a.sync->gen, st.gen + 1);
-        } else {
-            ok = pk_spin_gen(a.sync, st.gen);
-        }
+        const unsigned old = atomicAdd(&a.sync->bar, nb);
+        const bool ok = pk_spin_flip(a.sync, old);
         __threadfence();
         *flag_s = ok ? 1 : 0;
     }
     __syncthreads();
-    st.gen++;
     return *flag_s != 0;
 }
 
@@ -161,9 +159,11 @@ __device__ __forceinline__ bool pk_sync_reduce(const PKArgs& a, PKState& st, dou
     double v[2] = {d0, d1};
     if (a.dist.world > 1) st.ar_epoch++;               // one exchange per reduction, on every rank alike
     block_reduce<2, OpSum>(v, red_s);
+    unsigned old = 0u;       // barrier word before this barrier: it cannot change until this CTA has arrived on `count`
     if (threadIdx.x == 0) {
         a.partials[2 * blockIdx.x] = v[0];
         a.partials[2 * blockIdx.x + 1] = v[1];
+        old = *reinterpret_cast<const volatile unsigned*>(&a.sync->bar);
         __threadfence();
         flag_s[1] = (atomicAdd(&a.sync->count, 1u) == gridDim.x - 1) ? 1 : 0;
     }
@@ -187,17 +187,16 @@ __device__ __forceinline__ bool pk_sync_reduce(const PKArgs& a, PKState& st, dou
                 fin(a.sc, a.hist);
                 a.sync->count = 0;
                 __threadfence();
-                pk_st_release_gpu(&a.sync->gen, st.gen + 1);
+                atomicAdd(&a.sync->bar, 0x80000000u);      // flip the phase bit: the barrier opens
                 flag_s[0] = ok ? 1 : 0;
             }
         }
     } else if (threadIdx.x == 0) {
-        const bool ok = pk_spin_gen(a.sync, st.gen);
+        const bool ok = pk_spin_flip(a.sync, old);
         __threadfence();
         flag_s[0] = ok ? 1 : 0;
     }
     __syncthreads();
-    st.gen++;
     return flag_s[0] != 0;
 }
 
@@ -492,7 +491,6 @@ __global__ void __launch_bounds__(JB_S2_THREADS, PK_MINB) bicgstab_rb_iteration_
     PKPar par = {0u, 0u};
     PKState st;
     PKSums sums = {0.0, 0.0};
-    st.gen = *reinterpret_cast<volatile unsigned*>(&a.sync->gen);
     st.ar_epoch = __ldcg(a.state);
     st.halo_epoch = __ldcg(a.state + 1);
     st.t_prev = a.phase_ns ? pk_globaltimer() : 0ULL;
@@ -611,7 +609,7 @@ static bool pk_prepare(jb_krylov* K, i64 n_own) {
     if (eid && eid[0] == '0') n_id = 0;
     // SpMV table over the rows [n_id, n_own); bit 1 of the flags = the chunk reads a ghost column
     std::vector<S2Chunk> tab;
-    if (n_id < n_own && !jb_s2_cut(A->h_rowptr, n_id, (int32_t)n_own, tab)) return false;
+    if (n_id < n_own && !jb_s2_cut(A->h_rowptr, n_id, (int32_t)n_own, tab, A->ctx->sm_count * JB_S2_CTAS_PER_SM)) return false;
     for (S2Chunk& c : tab) {
         bool ghost = false;
         for (int32_t k = c.e0; !ghost && k < c.e0 + c.cnt; k++) ghost = A->h_colidx[k] >= n_own;

@@ -184,6 +184,11 @@ class TwoPhaseSimulator:
             raise _lib.JutulB200Error(f"perform_step!: {'bad ILU(0) pivot' if st == _lib.JB_BAD_PIVOT else 'Bad linear solve'} (status {st})")
         return st, bool(conv.value), its.value, errors
 
+    def update_after_step_host(self):
+        """update_after_step! for the host-buffer stepping: state0 <- the state the last (converged) perform_step_host call
+        uploaded; its masses are formed on the device, the next step passes M0 = None."""
+        check(self.ctx.lib.jb_twophase_update_after_step(self.law.h), self.ctx.h, "jb_twophase_update_after_step")
+
 
 class HeatSimulator:
     """SimpleHeatSystem on a periodic nx x ny CartesianMesh (config 1)."""
