@@ -379,3 +379,35 @@ def test_newton_iteration_from_plain_c_matches_oracle(J, O, tmp_path):
     O.update_scalar(p_o, dx_c, dx_stride=2)
     O.update_fraction_pair(s_o, dx_c[1:], abs_max=0.2, dx_stride=2)
     assert np.array_equal(p_c, p_o) and np.array_equal(s_c, s_o)         # the update is bit-exact given the same dx
+
+
+# ------------------------------------------------------------------ a15: the fused iteration kernel against the multi-kernel driver and the oracle
+@pytest.mark.parametrize("rtol", [1e-3, 1e-8])
+def test_fused_bicgstab_kernel_matches_multi_kernel_driver_and_oracle(J, O, ctx, monkeypatch, rtol):
+    """bicgstab_rb_iteration_kernel (one cooperative launch per iteration: sweeps, SpMVs, updates, inner products behind grid
+    barriers) runs the arithmetic of the multi-kernel driver and of the oracle's Krylov.jl-order BiCGStab on the renumbered
+    system: same residual history (first iterations to 1e-6), iteration counts within 10 %, same increment."""
+    w = J.workloads.unstructured_hex(26, 22, 18)
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("JB_PERSISTENT", fused)
+        sim = J.TwoPhaseSimulator(ctx, w["N"], w["nc"], w["Tf"], w["gdz"], w["pv"], w["params"], ordering="multicolor", rtol=rtol,
+                                  max_linear_iterations=400)
+        sim.set_forces(w["src_cells"], w["src_vals"])
+        sim.set_state(w["p0"], w["sw0"])
+        conv, err, rep = sim.perform_step(w["dt"])
+        info = sim.krylov.fused_info()
+        assert (info is not None) == (fused == "1")
+        out[fused] = (rep["linear_iterations"], np.asarray(rep["linear_residuals"]), sim.dx.get(), sim.jac.nonzeros(), sim.r.get(), sim.jac.pattern())
+    a, b = out["1"], out["0"]
+    assert abs(a[0] - b[0]) <= max(2, b[0] // 10)
+    assert np.allclose(a[1][:6], b[1][:6], rtol=1e-6)
+    amp = 1e-1 if rtol > 1e-6 else 1e-4      # two solves to rtol differ by (error amplification) * rtol
+    assert np.linalg.norm(a[2] - b[2]) <= amp * np.linalg.norm(b[2])
+    # oracle on the device's own (renumbered) system
+    its_f, hist_f, dx_f, nz, r, (rp, ci) = a
+    ilu = O.ILU0(w["nc"], 2, rp, ci); ilu.factor(nz)
+    x, st, its, hist = O.bicgstab(w["nc"], 2, rp, ci, nz, r, ilu, rtol=rtol, itmax=400)
+    assert abs(its_f - its) <= max(2, its // 10)
+    assert np.allclose(hist_f[:5], hist[:5], rtol=1e-6)
+    assert np.linalg.norm(dx_f + x) <= amp * np.linalg.norm(x)
