@@ -474,6 +474,65 @@ int jb_ilu_symbolic(jb_ilu* F, const int64_t* partition) {
         F->rb_factor = ok;
         if (!ok) F->h_usrc.clear();
     }
+    // single-pass form of the same refactorisation (ilu.cu, ilu_factor_rb2_kernel): everything is read from the Jacobian
+    F->rb2_ok = false;
+    if (F->rb_factor && A->bs == 2) {
+        const i64 nb = A->nnzb;
+        F->h_fdst.assign((size_t)nb, -1);
+        for (i64 r = 0; r < n; r++) F->h_fdst[(size_t)F->h_Dmap[r]] = -2;
+        for (i64 li = 0; li < F->nL; li++) F->h_fdst[(size_t)F->h_Lmap[li]] = (int32_t)li;
+        for (i64 ui = 0; ui < F->nU; ui++) F->h_fdst[(size_t)F->h_Umap[ui]] = (int32_t)(baseU + ui);
+        F->h_rtype.assign((size_t)n, 0);
+        i64 bmin = n, bmax = -1, nB = 0;
+        for (i64 r = 0; r < n; r++)
+            if (F->h_Lend[r] != F->h_Lstart[r]) { F->h_rtype[(size_t)r] = 1; bmin = std::min(bmin, r); bmax = std::max(bmax, r); nB++; }
+        // gather indices (A_kk, A_ki) per Jacobian block of the second-colour rows, indexed by block - first block of that row range,
+        // so that the kernel loads slot and gather indices independently of each other
+        F->rb2_kB0 = nB > 0 ? A->h_rowptr[bmin] : 0;
+        const i64 kB1 = nB > 0 ? A->h_rowptr[bmax + 1] : 0;
+        F->h_gL.assign((size_t)(kB1 - F->rb2_kB0), make_int2(-1, -1));
+        for (i64 li = 0; li < F->nL; li++) {
+            const int32_t us = F->h_usrc[li];
+            F->h_gL[(size_t)(F->h_Lmap[li] - F->rb2_kB0)] = make_int2(F->h_Dmap[F->h_Lcol[li]], us >= 0 ? F->h_Umap[(size_t)(us - baseU)] : -1);
+        }
+        // row chunks of the Jacobian (<= 128 rows, <= 1024 blocks), never across the border of the second colour's range
+        std::vector<int32_t> cuts;
+        bool ok = true;
+        auto cut_range = [&](i64 a, i64 b) {
+            i64 start = a;
+            while (ok && start < b) {
+                i64 end = start;
+                while (end < b && end - start < 128 && A->h_rowptr[end + 1] - A->h_rowptr[start] <= 1024) end++;   // JB_RB2_ROWS / JB_RB2_CAP (ilu.cu)
+                if (end == start) { ok = false; break; }
+                cuts.push_back((int32_t)start); cuts.push_back((int32_t)end);
+                start = end;
+            }
+        };
+        const bool contiguous = nB > 0 && bmax - bmin + 1 == nB;
+        if (contiguous) { cut_range(0, bmin); cut_range(bmin, bmax + 1); cut_range(bmax + 1, n); }
+        else cut_range(0, n);
+        if (ok) {
+            const size_t nch = cuts.size() / 2;
+            std::vector<size_t> order(nch);
+            std::iota(order.begin(), order.end(), (size_t)0);
+            if (contiguous && bmin > 0) {
+                // a second-colour chunk right after the first-colour chunk at the same relative position: its gathers
+                // (A_kk, A_ki of neighbouring first-colour rows) then find those rows in L2
+                auto key = [&](size_t c) {
+                    const double r0 = cuts[2 * c];
+                    if (r0 < bmin) return std::make_pair(r0 / (double)bmin, 0);
+                    if (r0 <= bmax) return std::make_pair((r0 - bmin) / (double)nB, 1);
+                    return std::make_pair(2.0, 2);
+                };
+                std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return key(a) < key(b); });
+            }
+            F->h_rb2_chunks.clear();
+            for (size_t c : order) { F->h_rb2_chunks.push_back(cuts[2 * c]); F->h_rb2_chunks.push_back(cuts[2 * c + 1]); }
+            F->n_rb2_chunks = (int)nch;
+            F->rb2_ok = true;
+        }
+        if (!F->rb2_ok) { F->h_fdst.clear(); F->h_gL.clear(); F->h_rtype.clear(); F->h_rb2_chunks.clear(); }
+    }
     return JB_OK;
 }
 
@@ -496,6 +555,9 @@ int jb_ilu_upload(jb_ilu* F) {
     ok = ok && (F->h_iso.empty() || F->d_iso.upload(F->h_iso, s) == cudaSuccess);
     if (F->s2_ok) ok = ok && (F->h_s2F.empty() || F->d_s2F.upload(F->h_s2F, s) == cudaSuccess) && (F->h_s2B.empty() || F->d_s2B.upload(F->h_s2B, s) == cudaSuccess);
     ok = ok && (!F->rb_factor || F->h_usrc.empty() || F->d_usrc.upload(F->h_usrc, s) == cudaSuccess);
+    if (F->rb2_ok)
+        ok = ok && F->d_fdst.upload(F->h_fdst, s) == cudaSuccess && (F->h_gL.empty() || F->d_gL.upload(F->h_gL, s) == cudaSuccess) &&
+             F->d_rtype.upload(F->h_rtype, s) == cudaSuccess && F->d_rb2_chunks.upload(F->h_rb2_chunks, s) == cudaSuccess;
     ok = ok && F->d_LptrT.upload(F->h_LptrT, s) == cudaSuccess && F->d_UptrT.upload(F->h_UptrT, s) == cudaSuccess &&
          F->d_chunksF.upload(F->h_chunksF, s) == cudaSuccess && F->d_chunksB.upload(F->h_chunksB, s) == cudaSuccess;
     const size_t b2 = (size_t)F->bs * F->bs;

@@ -151,6 +151,105 @@ __global__ void __launch_bounds__(256) ilu_factor_rb_kernel(int c0, int c1, cons
     }
 }
 
+
+// Single-pass two-colour numeric refactorisation (2x2 blocks): ONE sweep over the Jacobian in row chunks produces L, D^-1 and
+// U. Everything a row needs is in the Jacobian itself: first-colour rows k have no L entries, so D_k = A_kk and U_k* = A_k*
+// (copied to their slots); a second-colour row i needs, per L entry, m_ik = A_ik inv(A_kk) and D_i -= m_ik A_ki — A_kk and
+// A_ki are gathered from the Jacobian (rows k are spatial neighbours: the chunk order interleaves the two colours by
+// position so those rows were streamed moments ago and sit in L2). No intermediate copy of D / U, no second pass over L,
+// and no dependency between rows, hence no levels. Arithmetic per entry is that of ilu_factor_level_kernel /
+// ilu_factor_rb_kernel (blk_inv, blk_mul, products subtracted in ascending column order; src/StaticCSR/ilu0.jl:108-144).
+// Thread per block of the chunk; products parked in shared memory; one thread per row finishes D_i.
+#define JB_RB2_ROWS 128
+#define JB_RB2_CAP 1024
+__global__ void __launch_bounds__(256, 4) ilu_factor_rb2_kernel(int nchunks, const int32_t* __restrict__ chunks, const int32_t* __restrict__ rowptr,
+                                                                const int32_t* __restrict__ diag, const int32_t* __restrict__ fdst,
+                                                                const int2* __restrict__ gL, int32_t kB0, int32_t kB1, const unsigned char* __restrict__ rtype, i64 nL,
+                                                                const double* __restrict__ A, double* __restrict__ fv, double* __restrict__ dinv,
+                                                                int32_t* status) {
+    __shared__ int32_t s_rp[JB_RB2_ROWS + 1];
+    __shared__ __align__(16) double s_prod[JB_RB2_CAP * 4];   // 4 doubles per block of the chunk
+    constexpr int UF = 2;     // blocks in flight per thread: slot, gather indices and the block itself are loaded independently, then A_kk / A_ki;
+                              // all loads of both blocks are issued before any arithmetic
+    for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const int r0 = __ldg(chunks + 2 * c), nr = __ldg(chunks + 2 * c + 1) - r0;
+        for (int j = threadIdx.x; j <= nr; j += blockDim.x) s_rp[j] = __ldg(rowptr + r0 + j);
+        __syncthreads();
+        const int base = s_rp[0], cnt = s_rp[nr] - base;
+        for (int eb = threadIdx.x; eb < cnt; eb += blockDim.x * UF) {
+            int32_t dst[UF];
+            double2 a0[UF], a1[UF], k0[UF], k1[UF], u0[UF], u1[UF];
+            int2 g[UF];
+#pragma unroll
+            for (int u = 0; u < UF; u++) {
+                const int e = eb + u * blockDim.x;
+                dst[u] = -1;
+                g[u] = make_int2(-1, -1);
+                if (e < cnt) {
+                    const size_t kA = (size_t)base + e;
+                    dst[u] = __ldg(fdst + kA);
+                    if ((int32_t)kA >= kB0 && (int32_t)kA < kB1) g[u] = __ldg(gL + (kA - (size_t)kB0));
+                    const double2* ap = reinterpret_cast<const double2*>(A + kA * 4);
+                    a0[u] = ap[0]; a1[u] = ap[1];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UF; u++) {
+                k0[u] = k1[u] = u0[u] = u1[u] = make_double2(0.0, 0.0);
+                if (g[u].x >= 0) { const double2* kp = reinterpret_cast<const double2*>(A + (size_t)g[u].x * 4); k0[u] = kp[0]; k1[u] = kp[1]; }
+                if (g[u].y >= 0) { const double2* up = reinterpret_cast<const double2*>(A + (size_t)g[u].y * 4); u0[u] = up[0]; u1[u] = up[1]; }
+            }
+#pragma unroll
+            for (int u = 0; u < UF; u++) {
+                const int e = eb + u * blockDim.x;
+                if (e >= cnt) continue;
+                double prod[4] = {0.0, 0.0, 0.0, 0.0};
+                if (dst[u] == -2) { prod[0] = a0[u].x; prod[1] = a0[u].y; prod[2] = a1[u].x; prod[3] = a1[u].y; }   // diagonal block: parked for the row thread
+                else if (dst[u] >= 0) {
+                    double2* out = reinterpret_cast<double2*>(fv + (size_t)dst[u] * 4);
+                    if ((i64)dst[u] >= nL) { __stcs(out, a0[u]); __stcs(out + 1, a1[u]); }            // U entry of a first-colour row: copy
+                    else {                                                                             // L entry of a second-colour row
+                        const double Lik[4] = {a0[u].x, a0[u].y, a1[u].x, a1[u].y}, Akk[4] = {k0[u].x, k0[u].y, k1[u].x, k1[u].y};
+                        const double Uki[4] = {u0[u].x, u0[u].y, u1[u].x, u1[u].y};
+                        double Dk[4], m[4];
+                        blk_inv<2>(Akk, Dk);
+                        blk_mul<2>(Lik, Dk, m);
+                        __stcs(out, make_double2(m[0], m[1])); __stcs(out + 1, make_double2(m[2], m[3]));
+                        if (g[u].y >= 0) blk_mul<2>(m, Uki, prod);
+                    }
+                }
+                double2* sp = reinterpret_cast<double2*>(s_prod + (size_t)e * 4);
+                sp[0] = make_double2(prod[0], prod[1]); sp[1] = make_double2(prod[2], prod[3]);
+            }
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < nr) {
+            const size_t i = (size_t)r0 + threadIdx.x;
+            const int ed = __ldg(diag + i) - base;
+            double D[4], Di[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) D[q] = s_prod[(size_t)ed * 4 + q];
+            if (__ldg(rtype + i)) {
+                for (int e = s_rp[threadIdx.x] - base; e < s_rp[threadIdx.x + 1] - base; e++) {
+                    if (e == ed) continue;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) D[q] -= s_prod[(size_t)e * 4 + q];
+                }
+            }
+            blk_inv<2>(D, Di);
+            bool bad = false;
+            double2* fd = reinterpret_cast<double2*>(fv + ((size_t)nL + i) * 4);
+            double2* dd = reinterpret_cast<double2*>(dinv + i * 4);
+            fd[0] = make_double2(D[0], D[1]); fd[1] = make_double2(D[2], D[3]);
+            dd[0] = make_double2(Di[0], Di[1]); dd[1] = make_double2(Di[2], Di[3]);
+#pragma unroll
+            for (int q = 0; q < 4; q++) bad |= !isfinite(Di[q]);
+            if (bad) *status = JB_BAD_PIVOT;
+        }
+        __syncthreads();
+    }
+}
+
 // forward sweep: x_i = b_i - sum_j L_ij x_j  (unit diagonal), rows of one level
 template <int BS>
 __global__ void __launch_bounds__(256) ilu_forward_level_kernel(int32_t t0, int32_t t1, const int32_t* __restrict__ forder,
@@ -461,6 +560,17 @@ static int ilu_factor_t(jb_ilu* F) {
     JB_CUDA(ctx, cudaMemsetAsync(F->d_status.p, 0, sizeof(int32_t), s));
     const i64 total = (F->nL + F->n + F->nU) * BS * BS;
     int grid = (int)std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 16);
+    if (BS == 2 && F->rb2_ok && F->two_colour && !getenv("JB_ILU_FACTOR_GENERIC") && !getenv("JB_ILU_FACTOR_RB1")) {
+        // single pass over the Jacobian (ilu_factor_rb2_kernel)
+        static int per_sm2 = 0;
+        if (per_sm2 == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, ilu_factor_rb2_kernel, 256, 0) != cudaSuccess || per_sm2 < 1)) per_sm2 = 1;
+        ilu_factor_rb2_kernel<<<std::max(1, std::min(F->n_rb2_chunks, ctx->sm_count * per_sm2)), 256, 0, s>>>(
+            F->n_rb2_chunks, F->d_rb2_chunks.p, F->csr->d_rowptr.p, F->csr->d_diag.p, F->d_fdst.p, F->d_gL.p, F->rb2_kB0, F->rb2_kB0 + (int32_t)F->d_gL.n,
+            F->d_rtype.p, F->nL, F->csr->d_val.p,
+            F->d_fv.p, F->d_dinv.p, F->d_status.p);
+        JB_CHECK_LAUNCH(ctx);
+        return JB_OK;
+    }
     if (BS <= 2 && F->rb_factor && F->two_colour && F->stream_ok && !getenv("JB_ILU_FACTOR_GENERIC")) {
         // two-colour stream factorisation: D and U from the Jacobian, first colour inverted, second colour in one stream pass
         constexpr int BSS = BS <= 2 ? BS : 1;

@@ -238,6 +238,18 @@ struct jb_ilu {
     std::vector<int32_t> h_usrc;
     DBuf<int32_t> d_usrc;
     DBuf<int32_t> d_LptrT, d_UptrT, d_chunksF, d_chunksB;
+    // single-pass two-colour refactorisation (ilu_factor_rb2_kernel): per Jacobian block its slot in the factor buffer
+    // (-1 dropped coupling, -2 diagonal), per L slot the Jacobian blocks A_kk and A_ki it needs, row type (1 = has L entries),
+    // and the row chunks in processing order (first / second colour interleaved by position for L2 reuse)
+    bool rb2_ok = false;
+    std::vector<int32_t> h_fdst, h_rb2_chunks;
+    std::vector<int2> h_gL;
+    std::vector<unsigned char> h_rtype;
+    DBuf<int32_t> d_fdst, d_rb2_chunks;
+    DBuf<int2> d_gL;
+    DBuf<unsigned char> d_rtype;
+    int n_rb2_chunks = 0;
+    int32_t rb2_kB0 = 0;              // first Jacobian block of the second-colour row range (d_gL is indexed relative to it)
     // device
     DBuf<int32_t> d_forder, d_border, d_Lstart, d_Lend, d_Ustart, d_Uend, d_Lcol, d_Ucol, d_Lmap, d_Umap, d_Dmap;
     DBuf<int32_t> d_upd_ptr, d_upd_tgt, d_upd_src;
