@@ -387,43 +387,70 @@ __device__ __forceinline__ PKPar pk_phase_A(S2Smem* smp, PKPar pp, const S2Chunk
     return qq;
 }
 
-// rows outside [b0, b1): V1 s = r - alpha v, V3 p = r + beta (p - omega v); v_i = p_i on the identity rows
+// rows outside [b0, b1): V1 s = r - alpha v, V3 p = r + beta (p - omega v); v_i = p_i on the identity rows. Two rows per
+// thread and trip, loads first.
 template <int WHICH>
 __device__ __forceinline__ void pk_phase_VR(int n_own, int n_id, int b0, int b1, const double* r, double* p, const double* v, double* s, double alpha,
                                          double beta, double omega) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
     const int nb = b1 - b0, n_R = n_own - nb;
-    for (long long q = tid; q < n_R; q += nth) {
-        const long long i = q < b0 ? q : q + nb;
-        const double2 ri = reinterpret_cast<const double2*>(r)[i];
-        const double2 pi = reinterpret_cast<const double2*>(p)[i];
-        const double2 vi = i < n_id ? pi : reinterpret_cast<const double2*>(v)[i];
-        if (WHICH == 0) reinterpret_cast<double2*>(s)[i] = make_double2(fma(-alpha, vi.x, ri.x), fma(-alpha, vi.y, ri.y));
-        else {
-            const double pax = fma(-omega, vi.x, pi.x), pay = fma(-omega, vi.y, pi.y);
-            reinterpret_cast<double2*>(p)[i] = make_double2(fma(beta, pax, ri.x), fma(beta, pay, ri.y));
+    for (long long q0 = tid; q0 < n_R; q0 += 2 * nth) {
+        const long long q1 = q0 + nth;
+        const bool two = q1 < n_R;
+        const long long ia = q0 < b0 ? q0 : q0 + nb;
+        const long long ib = two ? (q1 < b0 ? q1 : q1 + nb) : ia;
+        const double2 ra = reinterpret_cast<const double2*>(r)[ia], rb = reinterpret_cast<const double2*>(r)[ib];
+        const double2 pa = reinterpret_cast<const double2*>(p)[ia], pb = reinterpret_cast<const double2*>(p)[ib];
+        const double2 va = ia < n_id ? pa : reinterpret_cast<const double2*>(v)[ia];
+        const double2 vb = ib < n_id ? pb : reinterpret_cast<const double2*>(v)[ib];
+        if (WHICH == 0) {
+            reinterpret_cast<double2*>(s)[ia] = make_double2(fma(-alpha, va.x, ra.x), fma(-alpha, va.y, ra.y));
+            if (two) reinterpret_cast<double2*>(s)[ib] = make_double2(fma(-alpha, vb.x, rb.x), fma(-alpha, vb.y, rb.y));
+        } else {
+            const double pax = fma(-omega, va.x, pa.x), pay = fma(-omega, va.y, pa.y);
+            reinterpret_cast<double2*>(p)[ia] = make_double2(fma(beta, pax, ra.x), fma(beta, pay, ra.y));
+            if (two) {
+                const double pbx = fma(-omega, vb.x, pb.x), pby = fma(-omega, vb.y, pb.y);
+                reinterpret_cast<double2*>(p)[ib] = make_double2(fma(beta, pbx, rb.x), fma(beta, pby, rb.y));
+            }
         }
     }
 }
 
 // all owned rows: x += alpha y + omega z; r = s - omega t (t_i = s_i on the identity rows); <c,r>, <r,r>
+// Two rows per thread and trip: the 14 loads of both rows are issued before the first fma (the phase has no TMA pipeline;
+// its memory-level parallelism is what the threads themselves keep in flight).
 __device__ __forceinline__ void pk_phase_V2(int n_own, int n_id, const double* y, const double* z, const double* s, const double* t,
                                          const double* __restrict__ c, double* x, double* r, double alpha, double omega, PKSums* sums) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
     double d0 = 0.0, d1 = 0.0;
-    for (long long i = tid; i < n_own; i += nth) {
-        const double2 yi = reinterpret_cast<const double2*>(y)[i], zi = reinterpret_cast<const double2*>(z)[i];
-        const double2 si = reinterpret_cast<const double2*>(s)[i];
-        const double2 ti = i < n_id ? si : reinterpret_cast<const double2*>(t)[i];
-        const double2 ci = __ldg(reinterpret_cast<const double2*>(c) + i);
-        double2 xi = reinterpret_cast<const double2*>(x)[i];
-        xi.x = fma(omega, zi.x, fma(alpha, yi.x, xi.x));
-        xi.y = fma(omega, zi.y, fma(alpha, yi.y, xi.y));
-        reinterpret_cast<double2*>(x)[i] = xi;
-        const double rx = fma(-omega, ti.x, si.x), ry = fma(-omega, ti.y, si.y);
-        reinterpret_cast<double2*>(r)[i] = make_double2(rx, ry);
-        d0 = fma(ci.x, rx, d0); d0 = fma(ci.y, ry, d0);
-        d1 = fma(rx, rx, d1); d1 = fma(ry, ry, d1);
+    for (long long i0 = tid; i0 < n_own; i0 += 2 * nth) {
+        const long long i1 = i0 + nth;
+        const bool two = i1 < n_own;
+        const long long j1 = two ? i1 : i0;
+        const double2 ya = reinterpret_cast<const double2*>(y)[i0], yb = reinterpret_cast<const double2*>(y)[j1];
+        const double2 za = reinterpret_cast<const double2*>(z)[i0], zb = reinterpret_cast<const double2*>(z)[j1];
+        const double2 sa = reinterpret_cast<const double2*>(s)[i0], sb = reinterpret_cast<const double2*>(s)[j1];
+        const double2 ta = i0 < n_id ? sa : reinterpret_cast<const double2*>(t)[i0];
+        const double2 tb = j1 < n_id ? sb : reinterpret_cast<const double2*>(t)[j1];
+        const double2 ca = __ldg(reinterpret_cast<const double2*>(c) + i0), cb = __ldg(reinterpret_cast<const double2*>(c) + j1);
+        double2 xa = reinterpret_cast<const double2*>(x)[i0], xb = reinterpret_cast<const double2*>(x)[j1];
+        xa.x = fma(omega, za.x, fma(alpha, ya.x, xa.x));
+        xa.y = fma(omega, za.y, fma(alpha, ya.y, xa.y));
+        reinterpret_cast<double2*>(x)[i0] = xa;
+        const double rax = fma(-omega, ta.x, sa.x), ray = fma(-omega, ta.y, sa.y);
+        reinterpret_cast<double2*>(r)[i0] = make_double2(rax, ray);
+        d0 = fma(ca.x, rax, d0); d0 = fma(ca.y, ray, d0);
+        d1 = fma(rax, rax, d1); d1 = fma(ray, ray, d1);
+        if (two) {
+            xb.x = fma(omega, zb.x, fma(alpha, yb.x, xb.x));
+            xb.y = fma(omega, zb.y, fma(alpha, yb.y, xb.y));
+            reinterpret_cast<double2*>(x)[i1] = xb;
+            const double rbx = fma(-omega, tb.x, sb.x), rby = fma(-omega, tb.y, sb.y);
+            reinterpret_cast<double2*>(r)[i1] = make_double2(rbx, rby);
+            d0 = fma(cb.x, rbx, d0); d0 = fma(cb.y, rby, d0);
+            d1 = fma(rbx, rbx, d1); d1 = fma(rby, rby, d1);
+        }
     }
     sums->d0 = d0; sums->d1 = d1;
 }
