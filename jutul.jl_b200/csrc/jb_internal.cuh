@@ -299,6 +299,8 @@ struct jb_krylov {
     DBuf<double> d_sc;      // scalar block
     DBuf<double> d_hist;
     double* h_flags = nullptr;  // pinned
+    unsigned long long* h_prog = nullptr;    // pinned + mapped: progress word written by the fused kernel (krylov_persistent.cu)
+    unsigned long long* d_prog = nullptr;    // its device address
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int hist_cap = 0;
     bool overlap = false;      // interior SpMV overlapped with the halo exchange (JB_OVERLAP=1)

@@ -58,5 +58,6 @@ struct PKArgs {
     unsigned long long* state;       // [0] all-reduce epoch, [1] halo epoch after the solve
     unsigned long long* phase_ns;    // per-phase time accumulators (profiling) or nullptr
     unsigned long long ar_epoch0, halo_epoch0;
+    unsigned long long* host_prog;   // pinned host word the kernel reports to: (launch index << 1) | done, or nullptr
     PKDist dist;
 };

@@ -143,6 +143,10 @@ int32_t jb_krylov_create(jb_csr* A, jb_ilu* ilu, int32_t kind, jb_krylov** out) 
     K->hist_cap = 1026;
     ok = ok && K->d_hist.alloc(K->hist_cap) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&K->h_flags, 4 * KS_SIZE * sizeof(double)) == cudaSuccess;
+    if (ok && cudaHostAlloc((void**)&K->h_prog, 64, cudaHostAllocMapped) == cudaSuccess) {
+        if (cudaHostGetDevicePointer((void**)&K->d_prog, K->h_prog, 0) != cudaSuccess) { cudaFreeHost(K->h_prog); K->h_prog = nullptr; K->d_prog = nullptr; }
+        else K->h_prog[0] = 0ULL;
+    } else { K->h_prog = nullptr; cudaGetLastError(); }
     ok = ok && cudaEventCreateWithFlags(&K->ev[0], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&K->ev[1], cudaEventDisableTiming) == cudaSuccess;
     K->yv = K->y.p; K->zv = K->z.p;
@@ -158,6 +162,7 @@ int32_t jb_krylov_create(jb_csr* A, jb_ilu* ilu, int32_t kind, jb_krylov** out) 
 int32_t jb_krylov_destroy(jb_krylov* K) {
     if (K) {
         if (K->h_flags) cudaFreeHost(K->h_flags);
+        if (K->h_prog) cudaFreeHost(K->h_prog);
         if (K->ev[0]) cudaEventDestroy(K->ev[0]);
         if (K->ev[1]) cudaEventDestroy(K->ev[1]);
         for (double* p : K->gm_V) cudaFree(p);

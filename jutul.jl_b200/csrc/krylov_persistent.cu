@@ -31,7 +31,9 @@
 //   V2  all rows         : x += alpha y + omega z; r = s - omega t; <c,r>, <r,r>                       barrier+reduce -> beta, stop?
 //   V3  R rows           : p_R = r_R + beta (p_R - omega v_R)                                          barrier
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
+#include <thread>
 
 #include "jb_internal.cuh"
 #include "jb_krylov_scalars.cuh"
@@ -508,6 +510,15 @@ __device__ __forceinline__ void pk_halo(const PKArgs& a, PKState& st, int which,
 // gather registers of every phase — 1.8 KB of spill code in the hot loops, measured 2x slower — while the loop-free body
 // compiles to 80 registers without a single local-memory access.)
 // flags: bit 0 = first launch of a solve (initialisation phase, then iteration 1).
+// The termination test of launch `it` reaches the host through a pinned word the kernel writes itself ((it << 1) | done): no
+// copy sits on the stream between two launches (a D2H copy + event there cost ~15 us per iteration: profiles/README.md).
+__device__ __forceinline__ void pk_report(const PKArgs& a, int flags) {
+    if (a.host_prog && blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long done = __ldcg(a.sc + KS_DONE) != 0.0 ? 1ULL : 0ULL;
+        *reinterpret_cast<volatile unsigned long long*>(a.host_prog) = ((unsigned long long)(flags >> 1) << 1) | done;
+        __threadfence_system();
+    }
+}
 __global__ void __launch_bounds__(JB_S2_THREADS, PK_MINB) bicgstab_rb_iteration_kernel(const __grid_constant__ PKArgs a, const int flags) {
     extern __shared__ __align__(128) unsigned char s2_raw[];
     S2Smem* sm = reinterpret_cast<S2Smem*>(s2_raw);
@@ -538,6 +549,7 @@ __global__ void __launch_bounds__(JB_S2_THREADS, PK_MINB) bicgstab_rb_iteration_
         pk_phase_init(a.n_own, a.b, a.r, a.p, a.x, &sums);
         if (!pk_barrier_reduce(a, st, &sums, red_s, flag_s, 0, PH_INIT)) return;
         if (__ldcg(a.sc + KS_DONE) != 0.0) {            // x = 0 solves the system (or breakdown): dx = -x = 0
+            pk_report(a, flags);
             pk_phase_final(a.n_own, a.x, a.dx);
             PK_EXIT()
         }
@@ -580,6 +592,7 @@ __global__ void __launch_bounds__(JB_S2_THREADS, PK_MINB) bicgstab_rb_iteration_
     const double omega = __ldcg(a.sc + KS_OMEGA);
     pk_phase_V2(a.n_own, a.n_id, a.y, a.z, a.s, a.t, a.b, a.x, a.r, alpha, omega, &sums);
     if (!pk_barrier_reduce(a, st, &sums, red_s, flag_s, 3, PH_V2)) return;
+    pk_report(a, flags);
     if (__ldcg(a.sc + KS_DONE) != 0.0) {
         pk_phase_final(a.n_own, a.x, a.dx);
         pk_phase_time(a, st, PH_FINAL);
@@ -743,19 +756,40 @@ int jb_krylov_solve_persistent(jb_krylov* K, const double* d_b, double* d_dx, do
     // iteration it-2 (same pinned slot this iteration reuses); a launch that finds the solve finished returns at once.
     int kflags = 1;
     void* kargs[] = {(void*)&a, (void*)&kflags};
+    const char* ehp = getenv("JB_PK_HOST_FLAGS");
+    const bool mapped = K->h_prog != nullptr && !(ehp && ehp[0] == '0');
+    a.host_prog = mapped ? K->d_prog : nullptr;
+    volatile unsigned long long* prog = K->h_prog;
+    if (mapped) *prog = 0ULL;      // the stream is idle here: the previous solve ended with a synchronisation
     if (ctx->prof_on) jb_prof_begin(ctx, JB_PROF_FUSED_SOLVE);
     for (int it = 1; it <= std::max(itmax, 1); it++) {
-        if (it >= 3) {     // (it = 2: no flags of this solve exist in that slot yet)
-            const int slot_prev = it & 1;
-            JB_CUDA(ctx, cudaEventSynchronize(K->ev[slot_prev]));
-            if (K->h_flags[slot_prev * KS_SIZE + KS_DONE] != 0.0) break;
+        if (it >= 3) {     // stay two launches ahead of the device: wait for the termination test of launch it - 2
+            if (mapped) {
+                const auto t0 = std::chrono::steady_clock::now();
+                unsigned long long w;
+                unsigned spins = 0;
+                while ((((w = *prog) >> 1) < (unsigned long long)(it - 2)) && !(w & 1ULL)) {
+                    if ((++spins & 0xfffu) == 0) {
+                        if (cudaStreamQuery(st) != cudaErrorNotReady) break;                 // everything enqueued has finished (abort / error path)
+                        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(90)) break;
+                        std::this_thread::yield();
+                    }
+                }
+                if (*prog & 1ULL) break;
+            } else {
+                const int slot_prev = it & 1;
+                JB_CUDA(ctx, cudaEventSynchronize(K->ev[slot_prev]));
+                if (K->h_flags[slot_prev * KS_SIZE + KS_DONE] != 0.0) break;
+            }
         }
-        kflags = it == 1 ? 1 : 0;
+        kflags = (it << 1) | (it == 1 ? 1 : 0);
         JB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)bicgstab_rb_iteration_kernel, dim3(H.grid), dim3(JB_S2_THREADS), kargs, sizeof(S2Smem), st));
         ctx->launches++;
-        const int slot = it & 1;
-        JB_CUDA(ctx, cudaMemcpyAsync(K->h_flags + slot * KS_SIZE, K->d_sc.p, KS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
-        JB_CUDA(ctx, cudaEventRecord(K->ev[slot], st));
+        if (!mapped) {
+            const int slot = it & 1;
+            JB_CUDA(ctx, cudaMemcpyAsync(K->h_flags + slot * KS_SIZE, K->d_sc.p, KS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
+            JB_CUDA(ctx, cudaEventRecord(K->ev[slot], st));
+        }
     }
     if (ctx->prof_on) jb_prof_end(ctx);
     JB_CUDA(ctx, cudaMemcpyAsync(K->h_flags + 3 * KS_SIZE, K->d_sc.p, KS_SIZE * sizeof(double), cudaMemcpyDeviceToHost, st));
