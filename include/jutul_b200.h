@@ -316,6 +316,15 @@ int32_t jb_krylov_info(jb_krylov* ks, int64_t* info /*8*/);
  * final; out[12] = iterations, out[13] = solves covered. Clears the accumulators. */
 int32_t jb_krylov_phase_times(jb_krylov* ks, double* out /*14*/);
 
+/* ---- two-phase law with properties from the secondary-variable graph: update_secondary_variables! -> update_equation! ->
+ *      update_linearized_system_equation! for models whose densities / mobilities / masses are property objects (tables,
+ *      power laws, ...) rather than the closed forms of jb_twophase_assemble. d_props: HOST array of 6 device pointers, each
+ *      3 * nc doubles as jb_varprog_evaluate writes them (value plane, d/dp plane, d/dSw plane): conserved mass of water / oil,
+ *      mass density of water / oil (gravity term), mobility rho k_r / mu of water / oil. Same law, same outputs, same
+ *      summation order as jb_twophase_assemble (row-owner form, no atomics); sources from jb_twophase_set_sources. */
+int32_t jb_twophase_assemble_props(jb_twophase* m, const double* d_p, const double* const* d_props, const double* d_M0, double dt,
+                                   double* d_r);
+
 /* ---- MultiModel with reduction = :schur_apply (src/linsolve/multimodel.jl:17-160; block system of
  *      setup_linearized_system!(::MultiModel), src/multimodel/model.jl:534-601): [B C; D E][x; y] = [a; b] with B the device
  *      Jacobian (jb_csr) and ngroups eliminated groups (wells, facility). C_i is (n bs) x m_i, D_i is m_i x (n bs), E_i is

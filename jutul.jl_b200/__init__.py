@@ -322,6 +322,17 @@ class TwoPhaseConservationLaw(_Handle):
         return r
 
 
+def assemble_with_properties(law, p, props, M0, dt, r):
+    """update_equation! + update_linearized_system_equation! of the two-phase law with property values from a
+    SecondaryVariables graph. props: dict with DeviceArrays (3 nc each: value, d/dp, d/dSw planes) under the keys
+    MassW, MassO, DensityW, DensityO, MobilityW, MobilityO."""
+    keys = ("MassW", "MassO", "DensityW", "DensityO", "MobilityW", "MobilityO")
+    ptrs = (C.c_void_p * 6)(*[props[k].ptr for k in keys])
+    check(law.ctx.lib.jb_twophase_assemble_props(law.h, _dp(p), C.cast(ptrs, _lib.PP), _dp(M0), float(dt), _dp(r)), law.ctx.h,
+          "jb_twophase_assemble_props")
+    return r
+
+
 class GenericAutoDiffCacheFill(_Handle):
     """fill_equation_entries!(nz, r, model, cache::GenericAutoDiffCache) (src/ad/generic.jl:53-96) for equations that the
     host evaluates: the cache's vpos / diagonal_positions / jacobian_positions are uploaded once, every fill ships the

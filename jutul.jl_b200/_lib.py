@@ -86,6 +86,7 @@ PROTOTYPES = {
     "jb_varprog_destroy": (I32, [P]),
     "jb_varprog_order": (I32, [P, PI64, PI64]),
     "jb_varprog_evaluate": (I32, [P, PP, PP]),
+    "jb_twophase_assemble_props": (I32, [P, P, PP, P, F64, P]),
     "jb_schur_create": (I32, [P, I32, PI64, PI64, PI64, PI64, PI64, PI64, PI64, PI64, PI64, PI64, PP]),
     "jb_schur_destroy": (I32, [P]),
     "jb_schur_size": (I64, [P]),

@@ -433,3 +433,47 @@ def find_jac_position_block(rowptr, colidx, row, col, eq, partial, N, adjoint=Fa
             base = (pos - 1) * N * N
             return base + (N * (eq - 1) + partial if adjoint else N * (partial - 1) + eq)
     raise RuntimeError("Jacobian alignment failed. Giving up.")
+
+
+# ------------------------------------------------------------------ two-phase law on property Duals
+def assemble_2ph_props(hf, diag_pos, hf_pos, Tf, gdz, p, props, M0, dt, nnzb, src_cells=None, src_vals=None):
+    """update_accumulation! + update_half_face_flux_tpfa! + fill_conservation_eq! (src/conservation/conservation.jl:558-626,
+    373-430) for the two-phase law whose properties are secondary variables held as Duals in the state: props[name] is a
+    (3, nc) array — value, d/dp, d/dSw of the cell's own primaries — for MassW, MassO, DensityW, DensityO, MobilityW, MobilityO.
+    Local-perspective AD (src/ad/local_ad.jl:54-79): inside the loop of cell c only the entries of c carry partials, the
+    neighbour's are plain values. The flux follows two_point_potential_drop / upw_flux (src/conservation/flux.jl:335-435).
+    Same summation order as the reference: accumulation first, then the half-faces in conn_pos order. 1-based tables."""
+    nc = p.shape[0]
+    nz = np.zeros(nnzb * 4); r = np.zeros(2 * nc)
+    src = np.zeros((nc, 2))
+    if src_cells is not None:
+        for c, v in zip(src_cells, np.asarray(src_vals).reshape(-1, 2)):
+            src[int(c) - 1] += v
+    names = (("MassW", "DensityW", "MobilityW"), ("MassO", "DensityO", "MobilityO"))
+
+    def dual(a, c):
+        return Dual(a[0, c], np.array([a[1, c], a[2, c]]))
+    fp, cells, faces, sign = hf["face_pos"], hf["cells"], hf["faces"], hf["face_sign"]
+    for c in range(nc):
+        ps = Dual(p[c], np.array([1.0, 0.0]))
+        for a in range(2):
+            mass, rho, mob = (props[k] for k in names[a])
+            acc = (dual(mass, c) - M0[2 * c + a]) / dt + src[c, a]
+            rv, dv = acc.v, acc.d.copy()
+            for i in range(fp[c] - 1, fp[c + 1] - 1):
+                o = int(cells[i]) - 1
+                f = int(faces[i]) - 1
+                sg = sign[i] * gdz[f]
+                rho_avg = 0.5 * (dual(rho, c) + rho[0, o])
+                theta = ps - p[o] + sg * rho_avg
+                q = Tf[f] * theta
+                F = (dual(mob, c) * q) if q.v > 0 else (mob[0, o] * q)
+                rv += F.v
+                dv += F.d
+                pos = int(hf_pos[i])                       # block (other, self): -dF/dx_self
+                for d in range(2):
+                    nz[(pos - 1) * 4 + 2 * d + a] = -F.d[d]
+            r[2 * c + a] = rv
+            for d in range(2):
+                nz[(int(diag_pos[c]) - 1) * 4 + 2 * d + a] = dv[d]
+    return nz, r

@@ -411,3 +411,65 @@ def test_fused_bicgstab_kernel_matches_multi_kernel_driver_and_oracle(J, O, ctx,
     assert abs(its_f - its) <= max(2, its // 10)
     assert np.allclose(hist_f[:5], hist[:5], rtol=1e-6)
     assert np.linalg.norm(dx_f + x) <= amp * np.linalg.norm(x)
+
+
+# ------------------------------------------------------------------ f1 -> a5-a7: the variable graph feeding the assembly
+def _twophase_property_graph(J, ctx, params, tabulated):
+    rho0w, rho0o, cw, co, muw, muo, p0 = params
+    if tabulated:
+        xs = np.linspace(5e6, 2e7, 40)
+        muw_t = J.get_1d_interpolator(ctx, xs, muw * (1 + 2e-9 * (xs - 1e7)))
+        muo_t = J.get_1d_interpolator(ctx, xs, muo * (1 + 5e-9 * (xs - 1e7)))
+        visc = dict(ViscW=dict(kind="table1d", deps=["Pressure"], table=muw_t), ViscO=dict(kind="table1d", deps=["Pressure"], table=muo_t))
+        krw, kro = dict(kind="power", deps=["Sw"], c=[0.9, 2.5, 0.05, 0.9]), dict(kind="power", deps=["So"], c=[0.8, 1.8, 0.1, 0.85])
+    else:
+        visc = dict(ViscW=dict(kind="const", c=[muw]), ViscO=dict(kind="const", c=[muo]))
+        krw, kro = dict(kind="product", deps=["Sw", "Sw"]), dict(kind="product", deps=["So", "So"])
+    defs = {
+        "Pressure": dict(kind="primary"), "Sw": dict(kind="primary"), "PoreVolume": dict(kind="parameter"),
+        "So": dict(kind="affine", deps=["Sw"], c=[1.0, -1.0]),
+        "DensityW": dict(kind="exp", deps=["Pressure"], c=[rho0w, cw, p0], output=True),
+        "DensityO": dict(kind="exp", deps=["Pressure"], c=[rho0o, co, p0], output=True),
+        "KrW": krw, "KrO": kro, **visc,
+        "RhoKrW": dict(kind="product", deps=["DensityW", "KrW"]), "RhoKrO": dict(kind="product", deps=["DensityO", "KrO"]),
+        "MobilityW": dict(kind="quotient", deps=["RhoKrW", "ViscW"], output=True),
+        "MobilityO": dict(kind="quotient", deps=["RhoKrO", "ViscO"], output=True),
+        "MassW": dict(kind="product", deps=["PoreVolume", "DensityW", "Sw"], output=True),
+        "MassO": dict(kind="product", deps=["PoreVolume", "DensityO", "So"], output=True),
+    }
+    return defs
+
+
+@pytest.mark.parametrize("tabulated", [False, True])
+def test_variable_graph_feeds_the_twophase_assembly(J, O, ctx, tabulated):
+    """update_secondary_variables! on the device -> assembly from the property planes. With the closed forms of the built-in
+    law as graph (exp densities, S^2 relative permeabilities, constant viscosities) the result equals jb_twophase_assemble;
+    with tabulated viscosities and Brooks-Corey curves it equals the oracle, which runs the reference's fill on Duals."""
+    from conftest import oracle_system
+    w = J.workloads.unstructured_hex(9, 8, 6)
+    nc = w["nc"]
+    sim = J.TwoPhaseSimulator(ctx, w["N"], nc, w["Tf"], w["gdz"], w["pv"], w["params"], ordering=None)
+    sim.set_forces(w["src_cells"], w["src_vals"]); sim.set_state(w["p0"], w["sw0"])
+    p1 = w["p0"] * (1 + 1e-3 * np.sin(np.arange(nc)))
+    sim.p.set(p1)
+    sv = J.SecondaryVariables(ctx, nc, _twophase_property_graph(J, ctx, w["params"], tabulated))
+    state = {"Pressure": sim.p, "Sw": ctx.transfer(w["sw0"]), "PoreVolume": ctx.transfer(w["pv"])}
+    out = {n: ctx.zeros(3 * nc) for n in sv.outputs}
+    sv.update_secondary_variables(state, out)
+    J.assemble_with_properties(sim.law, sim.p, out, sim.M0, w["dt"], sim.r)
+    nz_g, r_g = sim.jac.nonzeros(), sim.r.get()
+    props = {n: out[n].get().reshape(3, nc) for n in sv.outputs}
+    sy = oracle_system(O, w)
+    M0 = sim.M0.get()
+    nz_o, r_o = W.assemble_2ph_props(sy["hf"], sy["diag_pos"], sy["hf_pos"], w["Tf"], w["gdz"], p1, props, M0, w["dt"], sy["colidx"].shape[0],
+                                     w["src_cells"], w["src_vals"])
+    assert np.abs(r_g - r_o).max() <= 1e-11 * np.abs(r_o).max()
+    assert np.abs(nz_g - nz_o).max() <= 1e-11 * np.abs(nz_o).max()
+    if not tabulated:
+        sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r)
+        assert np.abs(sim.r.get() - r_g).max() <= 1e-10 * np.abs(r_g).max()
+        assert np.abs(sim.jac.nonzeros() - nz_g).max() <= 1e-10 * np.abs(nz_g).max()
+    else:
+        # the assembled system drives a Newton step with the device solver
+        ok, its, hist, st = J.linear_solve(sim.krylov, sim.r, sim.dx)
+        assert ok and hist[-1] <= 1e-3 * hist[0]

@@ -195,3 +195,25 @@ def test_secondary_variable_graph_against_closed_forms():
     h = 1.0
     mu_p = np.array([mu_tab(x + h) for x in p]); mu_m = np.array([mu_tab(x - h) for x in p])
     assert np.allclose(mob.d[0], -(state["Kr"].v / state["Viscosity"].v ** 2) * (mu_p - mu_m) / (2 * h), rtol=1e-6, atol=1e-12)
+
+
+def test_property_dual_assembly_equals_closed_form_oracle(O, J):
+    """fill_conservation_eq! on property Duals (oracle/widen.py) with the closed forms of the built-in law as properties
+    reproduces the C++ restatement of the same law to rounding: the two derivations of the Jacobian agree."""
+    from conftest import oracle_system
+    w = J.workloads.unstructured_hex(6, 5, 4)
+    nc = w["nc"]; sy = oracle_system(O, w)
+    p = w["p0"] * (1 + 1e-3 * np.sin(np.arange(nc))); sw = w["sw0"]; pv = w["pv"]; par = w["params"]
+    M0 = O.mass_2ph(pv, par, w["p0"], sw)
+    rho = [par[0] * np.exp(par[2] * (p - par[6])), par[1] * np.exp(par[3] * (p - par[6]))]
+    S = [sw, 1 - sw]; dS = [1.0, -1.0]
+    props = {}
+    for a, n in enumerate("WO"):
+        mob = rho[a] * S[a] ** 2 / par[4 + a]
+        props["Density" + n] = np.stack([rho[a], par[2 + a] * rho[a], 0 * p])
+        props["Mobility" + n] = np.stack([mob, par[2 + a] * mob, rho[a] * 2 * S[a] * dS[a] / par[4 + a]])
+        props["Mass" + n] = np.stack([pv * rho[a] * S[a], pv * par[2 + a] * rho[a] * S[a], pv * rho[a] * dS[a]])
+    nnzb = sy["colidx"].shape[0]
+    nz, r = W.assemble_2ph_props(sy["hf"], sy["diag_pos"], sy["hf_pos"], w["Tf"], w["gdz"], p, props, M0, w["dt"], nnzb, w["src_cells"], w["src_vals"])
+    nz2, r2 = O.assemble_2ph(sy["hf"], sy["diag_pos"], sy["hf_pos"], w["Tf"], w["gdz"], pv, par, p, sw, M0, w["dt"], nnzb, w["src_cells"], w["src_vals"])
+    assert np.abs(r - r2).max() <= 1e-14 * np.abs(r2).max() and np.abs(nz - nz2).max() <= 1e-14 * np.abs(nz2).max()
