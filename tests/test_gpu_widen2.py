@@ -473,3 +473,33 @@ def test_variable_graph_feeds_the_twophase_assembly(J, O, ctx, tabulated):
         # the assembled system drives a Newton step with the device solver
         ok, its, hist, st = J.linear_solve(sim.krylov, sim.r, sim.dx)
         assert ok and hist[-1] <= 1e-3 * hist[0]
+
+
+def test_poisson_adjoint_gradients_reference_goldens(J, O, ctx):
+    """test/test_systems/variable_poisson.jl:40-67 ("data_domain gradients"): objective sum(U) of the 3 x 1 Poisson case,
+    solve_adjoint_sensitivities -> gradients [-0.33333, -0.5, -0.16666] w.r.t. poisson_coefficient and [-2/3, -1/3] w.r.t.
+    the face areas (rtol 1e-3 in the reference). On the device: forward solve, J^T by jb_csr_transpose_update, Lagrange
+    multipliers lambda = -(J^T)^-1 (dG/dU)^T with the unchanged ILU(0)-BiCGStab (src/ad/gradients.jl:519-590), gradient with respect
+    to the face coefficients (dR/dK)^T lambda, chain rule of compute_face_trans on the host."""
+    N = O.cart_neighbors(3, 1, 1)
+    K = np.full(2, 3.0)                                   # compute_face_trans of the unit square cut in 3: A / (dx/2) = 6, harmonic -> 3
+    sim = J.PoissonSimulator(ctx, N, 3, K)
+    sim.set_state(np.ones(3))
+    sim.set_forces([1, 3], [1.0, -1.0])
+    assert sim.step(1.0)
+    U = sim.U.get()
+    assert np.allclose(U - U[0], [0.0, 1.0 / 3.0, 2.0 / 3.0], atol=1e-8)
+    sim.assemble(1.0)                                     # Jacobian at the solution (adjoint_reassemble!)
+    JT = sim.jac.adjoint(); JT.update_adjoint()
+    kry = J.GenericKrylov(JT, "bicgstab", J.ILUZeroPreconditioner(JT), relative_tolerance=1e-13, absolute_tolerance=1e-30, max_iterations=50)
+    lam = ctx.zeros(3)
+    ok, its, hist, st = J.linear_solve(kry, ctx.transfer(np.ones(3)), lam)      # rhs = (dG/dU)^T; the solver leaves dx = -x = lambda
+    lam = lam.get()
+    left, right = N[:, 0] - 1, N[:, 1] - 1
+    gK = (lam[left] - lam[right]) * (U[left] - U[right])  # (dR/dK_f)^T lambda: R_l has -K_f (U_r - U_l), R_r has -K_f (U_l - U_r)
+    assert np.allclose(gK, [-2.0 / 9.0, -1.0 / 9.0], rtol=1e-3)
+    k = np.ones(3)                                        # T_f = 1 / (1/(6 k_l) + 1/(6 k_r)),  T_f proportional to the face area
+    gk = np.zeros(3)
+    np.add.at(gk, left, gK * K ** 2 / (6.0 * k[left] ** 2)); np.add.at(gk, right, gK * K ** 2 / (6.0 * k[right] ** 2))
+    assert np.allclose(gk, [-0.33333492279052723, -0.4999980926513673, -0.1666631698608399], rtol=1e-3)      # the reference's own numbers
+    assert np.allclose(gK * K / 1.0, [-2.0 / 3.0, -1.0 / 3.0], rtol=1e-3)
