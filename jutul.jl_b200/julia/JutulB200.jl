@@ -626,6 +626,137 @@ function update_dx_from_vector!(S::B200Schur, d_dx::B200Vector)
     return y
 end
 
+# ------------------------------------------------------------------------------------------------ secondary variables, tables
+# LinearInterpolant / BilinearInterpolant (src/interpolation.jl:69-99,156-222) resident on the device; the interpolant's own X / F
+# arrays and its lookup choice are handed over (constant_dx: -1 = detect like `missing`, 0 / 1 = forced).
+mutable struct B200Table
+    handle::Ptr{Cvoid}
+    ctx::B200Context
+end
+function B200Table(ctx::B200Context, I::Jutul.LinearInterpolant)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    X, F = Vector{Float64}(I.X), Vector{Float64}(I.F)
+    check(ccall((:jb_table_create_1d, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Int32, Ref{Ptr{Cvoid}}),
+                ctx.handle, length(X), X, F, ismissing(I.lookup) ? Int32(0) : Int32(1), h), ctx.handle)
+    t = B200Table(h[], ctx)
+    finalizer(x -> ccall((:jb_table_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle), t)
+    return t
+end
+function B200Table(ctx::B200Context, I::Jutul.BilinearInterpolant)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    X, Y, F = Vector{Float64}(I.X), Vector{Float64}(I.Y), Matrix{Float64}(I.F)      # F is nx x ny, column-major as the C ABI expects
+    check(ccall((:jb_table_create_2d, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Ref{Ptr{Cvoid}}),
+                ctx.handle, length(X), length(Y), X, Y, F, ismissing(I.lookup_x) ? Int32(0) : Int32(1), ismissing(I.lookup_y) ? Int32(0) : Int32(1), h), ctx.handle)
+    t = B200Table(h[], ctx)
+    finalizer(x -> ccall((:jb_table_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle), t)
+    return t
+end
+# interpolate(I, x[, y]) on device vectors, with the slopes ForwardDiff would propagate
+function interpolate!(f::B200Vector, t::B200Table, x::B200Vector; y = nothing, dfdx = nothing, dfdy = nothing)
+    dp(v) = isnothing(v) ? Ptr{Float64}(C_NULL) : v.ptr
+    check(ccall((:jb_table_eval, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                t.handle, x.n, x.ptr, dp(y), f.ptr, dp(dfdx), dp(dfdy)), t.ctx.handle)
+    return f
+end
+
+# jb_var_spec of include/jutul_b200.h (isbits, same layout as the C struct)
+struct B200VarSpec
+    kind::Int32
+    dep::NTuple{3, Int32}
+    table::Int32
+    output::Int32
+    c::NTuple{4, Float64}
+end
+const VAR_KINDS = (primary = 0, parameter = 1, constant = 2, affine = 3, product = 4, quotient = 5, exp = 6, power = 7, table1d = 8, table2d = 9)
+# update_secondary_variables! (src/variable_evaluation.jl:87-148) for a model whose secondary variables are expressed in the
+# library's menu: the graph is sorted as sort_secondary_variables! does (:289-350) and evaluated by one kernel per call.
+mutable struct B200SecondaryVariables
+    handle::Ptr{Cvoid}
+    ctx::B200Context
+    nin::Int
+    nout::Int
+    tables::Vector{B200Table}
+end
+function B200SecondaryVariables(ctx::B200Context, nc::Integer, specs::Vector{B200VarSpec}, tables::Vector{B200Table} = B200Table[])
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    th = Ptr{Cvoid}[t.handle for t in tables]
+    check(ccall((:jb_varprog_create, LIB), Int32, (Ptr{Cvoid}, Int64, Int32, Ptr{B200VarSpec}, Int32, Ptr{Ptr{Cvoid}}, Ref{Ptr{Cvoid}}),
+                ctx.handle, nc, length(specs), specs, length(th), th, h), ctx.handle)
+    counts = zeros(Int64, 4)
+    check(ccall((:jb_varprog_order, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), h[], C_NULL, counts), ctx.handle)
+    v = B200SecondaryVariables(h[], ctx, counts[2], counts[3], tables)
+    finalizer(x -> ccall((:jb_varprog_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle), v)
+    return v
+end
+function update_secondary_variables!(v::B200SecondaryVariables, inputs::Vector{B200Vector}, outputs::Vector{B200Vector})
+    @assert length(inputs) == v.nin && length(outputs) == v.nout
+    ip, op = Ptr{Float64}[x.ptr for x in inputs], Ptr{Float64}[x.ptr for x in outputs]
+    GC.@preserve inputs outputs check(ccall((:jb_varprog_evaluate, LIB), Int32, (Ptr{Cvoid}, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}), v.handle, ip, op), v.ctx.handle)
+    return outputs
+end
+# update_equation! + update_linearized_system_equation! of the two-phase law from the evaluated property planes
+# (props: MassW, MassO, DensityW, DensityO, MobilityW, MobilityO; each value, d/dp, d/dSw planes)
+function assemble_with_properties!(s::B200TPFAStorage, props::Vector{B200Vector}, dt::Float64)
+    @assert length(props) == 6
+    pp = Ptr{Float64}[x.ptr for x in props]
+    GC.@preserve props check(ccall((:jb_twophase_assemble_props, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Ptr{Float64}}, Ptr{Float64}, Float64, Ptr{Float64}),
+                                   s.law, s.d_p.ptr, pp, s.d_M0.ptr, dt, s.d_r.ptr), s.ctx.handle)
+    return nothing
+end
+# update_after_step! for the device-resident stepping (state0 <- accepted state; masses formed on the device)
+update_after_step_b200!(s::B200TPFAStorage) = (check(ccall((:jb_twophase_update_after_step, LIB), Int32, (Ptr{Cvoid},), s.law), s.ctx.handle); nothing)
+
+# ------------------------------------------------------------------------------------------------ NFVM law (PotentialFlow{:fvm})
+# NFVMLinearDiscretization / NFVMNonLinearDiscretization per face (src/NFVM/types.jl:5-35) -> device; stencils, pattern, alignment
+# and the face-based assembly of src/conservation/fvm_assembly.jl with the flux partials of src/NFVM/evaluation.jl.
+mutable struct B200NFVM
+    handle::Ptr{Cvoid}
+    ctx::B200Context
+end
+function B200NFVM(ctx::B200Context, kgrad::Vector, nc::Integer)
+    nonlinear = first(kgrad) isa Jutul.NFVM.NFVMNonLinearDiscretization
+    scheme = !nonlinear ? Int32(0) : (first(kgrad).scheme == :ntpfa ? Int32(1) : Int32(2))
+    half(sel) = begin
+        Tl, Tr, ptr, cell, T = Float64[], Float64[], Int64[1], Int64[], Float64[]
+        for d in kgrad
+            h = sel(d)
+            push!(Tl, h.T_left); push!(Tr, h.T_right)
+            for (c, t) in h.mpfa
+                push!(cell, c); push!(T, t)
+            end
+            push!(ptr, length(cell) + 1)
+        end
+        (Tl, Tr, ptr, cell, T)
+    end
+    L = half(d -> nonlinear ? d.ft_left : d)
+    R = nonlinear ? half(d -> d.ft_right) : L
+    left = Int64[Jutul.cell_pair(d)[1] for d in kgrad]; right = Int64[Jutul.cell_pair(d)[2] for d in kgrad]
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:jb_nfvm_create, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                ctx.handle, length(kgrad), nc, scheme, left, right, L[1], L[2], L[3], L[4], L[5], R[1], R[2], R[3], R[4], R[5], h), ctx.handle)
+    d = B200NFVM(h[], ctx)
+    finalizer(x -> ccall((:jb_nfvm_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle), d)
+    return d
+end
+function nfvm_jacobian(d::B200NFVM, nc::Integer)      # declare_pattern + build_jacobian + align_to_jacobian!
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:jb_nfvm_pattern, LIB), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), d.handle, h), d.ctx.handle)
+    nnz = ccall((:jb_csr_nnz, LIB), Int64, (Ptr{Cvoid},), h[])
+    rowptr, colidx = zeros(Int64, nc + 1), zeros(Int64, nnz)
+    check(ccall((:jb_csr_get, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), h[], rowptr, colidx), d.ctx.handle)
+    A = B200Matrix{Float64}(h[], d.ctx, nc, 1, rowptr, colidx, zeros(Float64, nnz))
+    finalizer(a -> ccall((:jb_csr_destroy, LIB), Int32, (Ptr{Cvoid},), a.handle), A)
+    check(ccall((:jb_nfvm_align, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), d.handle, A.handle), d.ctx.handle)
+    return A
+end
+function nfvm_assemble!(d::B200NFVM, p::B200Vector, r::B200Vector; acc = nothing, dacc = nothing, q = nothing, nph = 1, ph = 1)
+    dp(v) = isnothing(v) ? Ptr{Float64}(C_NULL) : v.ptr
+    check(ccall((:jb_nfvm_assemble, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                d.handle, p.ptr, nph, ph, dp(acc), dp(dacc), r.ptr, dp(q)), d.ctx.handle)
+    return r
+end
+
 # partition(N, np, weights; partitioner = MetisPartitioner()) (src/partitioning.jl:244-307)
 function partition_metis(N::Matrix{Int64}, nc::Int, k::Int; weights = nothing)
     p = zeros(Int64, nc)
