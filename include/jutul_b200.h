@@ -361,6 +361,12 @@ int32_t jb_update_scalar(jb_ctx* ctx, double* d_v, const double* d_dx, int64_t d
                          double w, double abs_max, double rel_max, double minv, double maxv, double scale);
 int32_t jb_update_fraction_pair(jb_ctx* ctx, double* d_s /*2 x n*/, const double* d_dx, int64_t dx_stride,
                                 int64_t n, double w, double abs_max, double minval, double maxval);
+/* unit_sum_update! for nf fractions (src/variables/utils.jl:393-521): nf == 2 is jb_update_fraction_pair; nf > 2 runs
+ * unit_update_direction_local! (preserve_direction = 1, the FractionVariables default) with its fall-back
+ * unit_update_magnitude_local!, or the magnitude-preserving update alone (0). d_s is nf x n (fraction fastest), the nf - 1
+ * increments of cell c are d_dx[i + dx_stride * c]; minval / maxval are minimum_value / maximum_value of the variable. nf <= 8. */
+int32_t jb_update_fractions(jb_ctx* ctx, double* d_s, const double* d_dx, int64_t dx_stride, int32_t nf, int64_t n, double w, double abs_max,
+                            double minval, double maxval, int32_t preserve_direction);
 int32_t jb_increment_norm(jb_ctx* ctx, const double* d_dx, int64_t stride, int64_t n, double* sum_abs,
                           double* max_abs);
 int32_t jb_maxabs_rows(jb_ctx* ctx, const double* d_r, int32_t bs, int64_t n, double* out /*bs, host*/);

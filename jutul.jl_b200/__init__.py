@@ -522,6 +522,12 @@ def unit_update_pairs(ctx, s, dx, n, dx_stride=1, w=1.0, abs_max=None, minval=0.
           "jb_update_fraction_pair")
 
 
+def unit_sum_update(ctx, s, dx, nf, n, dx_stride=None, w=1.0, abs_max=None, minval=0.0, maxval=1.0, preserve_direction=True):
+    """unit_sum_update!(s, p, model, dx, w) for FractionVariables with nf values per cell (src/variables/utils.jl:393-521)."""
+    check(ctx.lib.jb_update_fractions(ctx.h, _dp(s), _dp(dx), nf - 1 if dx_stride is None else dx_stride, nf, n, w, _opt(abs_max), minval, maxval,
+                                      int(bool(preserve_direction))), ctx.h, "jb_update_fractions")
+
+
 def increment_norm(ctx, dx, n, stride=1):
     a = C.c_double(0); b = C.c_double(0)
     check(ctx.lib.jb_increment_norm(ctx.h, _dp(dx), stride, n, C.byref(a), C.byref(b)), ctx.h, "jb_increment_norm")

@@ -36,6 +36,56 @@ __global__ void __launch_bounds__(256) update_pair_kernel(i64 n, double* __restr
         reinterpret_cast<double2*>(s)[i] = sv;
     }
 }
+// unit_sum_update! for more than two fractions (src/variables/utils.jl:393-521): unit_update_direction_local! with its
+// fall-back unit_update_magnitude_local!, restated operation by operation (pick_relaxation included as written, :519-526).
+// s is nf x n (fraction fastest), dx holds the nf - 1 increments of a cell at dx[i + stride * cell].
+#define JB_MAX_FRACTIONS 8
+#define JB_MINIMUM_SAT_RELAX 1e-3
+__device__ __forceinline__ double pick_relaxation(double w, double dv, double dv0) {
+    const double r = dv / dv0;
+    if (dv0 != 0.0) w = fmin(w, r);
+    return fmin(w, JB_MINIMUM_SAT_RELAX);
+}
+__device__ __forceinline__ void unit_update_magnitude_local(double* s, const double* dx, int nf, double minval, double maxval, double abs_max) {
+    double dlast0 = 0.0;
+    for (int i = 0; i < nf - 1; i++) {
+        const double dv = choose_increment(s[i], dx[i], abs_max, NAN, minval, maxval, NAN);
+        s[i] += dv;
+        dlast0 -= dv;
+    }
+    const double dlast = choose_increment(s[nf - 1], dlast0, abs_max, NAN, minval, maxval, NAN);
+    s[nf - 1] += dlast;
+    if (dlast != dlast0) {      // the last value was not within bounds: renormalise
+        double t = 0.0;
+        for (int i = 0; i < nf; i++) t += s[i];
+        for (int i = 0; i < nf; i++) s[i] = fmin(fmax(s[i], minval), maxval) / t;
+    }
+}
+__global__ void __launch_bounds__(256) update_fractions_kernel(i64 n, int nf, double* __restrict__ sg, const double* __restrict__ dxg, i64 stride, double w0,
+                                                               double abs_max, double minval, double maxval, int preserve_direction) {
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (i64)gridDim.x * blockDim.x) {
+        double s[JB_MAX_FRACTIONS], dx[JB_MAX_FRACTIONS];
+        for (int i = 0; i < nf; i++) s[i] = sg[c * nf + i];
+        for (int i = 0; i < nf - 1; i++) dx[i] = __ldg(dxg + c * stride + i);
+        if (!preserve_direction) unit_update_magnitude_local(s, dx, nf, minval, maxval, abs_max);
+        else {
+            double w = 1.0, dlast0 = 0.0;
+            for (int i = 0; i < nf - 1; i++) {
+                const double dv = choose_increment(s[i], dx[i], abs_max, NAN, minval, maxval, NAN);
+                dlast0 -= dx[i];
+                w = pick_relaxation(w, dv, dx[i]);
+            }
+            const double dlast = choose_increment(s[nf - 1], dlast0, abs_max, NAN, minval, maxval, NAN);
+            w = w0 * pick_relaxation(w, dlast, dlast0);
+            if (w <= JB_MINIMUM_SAT_RELAX) unit_update_magnitude_local(s, dx, nf, minval, maxval, abs_max);
+            else {
+                for (int i = 0; i < nf - 1; i++) s[i] += w * dx[i];
+                s[nf - 1] += w * dlast0;
+            }
+        }
+        for (int i = 0; i < nf; i++) sg[c * nf + i] = s[i];
+    }
+}
 __global__ void __launch_bounds__(256) increment_norm_kernel(i64 n, const double* __restrict__ dx, i64 stride, double* out, double* partials,
                                                              unsigned int* counter) {
     double a[1] = {0.0}, b[1] = {0.0};
@@ -222,6 +272,20 @@ int32_t jb_update_fraction_pair(jb_ctx* ctx, double* d_s, const double* d_dx, in
     if (n == 0) return JB_OK;
     int rc = jb_launch_update_pair(ctx, d_s, d_dx, dx_stride, n, w, abs_max, minval, maxval);
     if (rc != JB_OK) return rc;
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+int32_t jb_update_fractions(jb_ctx* ctx, double* d_s, const double* d_dx, int64_t dx_stride, int32_t nf, int64_t n, double w, double abs_max,
+                            double minval, double maxval, int32_t preserve_direction) {
+    if (!ctx || !d_s || !d_dx || n < 0 || nf < 2 || nf > JB_MAX_FRACTIONS || dx_stride < nf - 1) return JB_ERR_ARG;
+    if (n == 0) return JB_OK;
+    if (nf == 2) return jb_update_fraction_pair(ctx, d_s, d_dx, dx_stride, n, w, abs_max, minval, maxval);
+    {
+        ProfScope _ps(ctx, JB_PROF_NEWTON);
+        update_fractions_kernel<<<sgrid(ctx, n), 256, 0, ctx->stream>>>(n, nf, d_s, d_dx, dx_stride, w, abs_max, minval, maxval - nf * minval,
+                                                                       preserve_direction);
+        JB_CHECK_LAUNCH(ctx);
+    }
     JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return JB_OK;
 }

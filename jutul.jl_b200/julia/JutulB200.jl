@@ -518,10 +518,11 @@ function update_primary_variable!(state, p::Jutul.ScalarVariable, state_symbol, 
     return v
 end
 function update_primary_variable!(state, p::Jutul.FractionVariables, state_symbol, model::B200Model, dx::B200Vector, w; offset = 1, stride = 2)
-    s = state[state_symbol]::B200Vector                      # 2 x nc
-    check(ccall((:jb_update_fraction_pair, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Float64, Float64, Float64, Float64),
-                s.ctx.handle, s.ptr, dx.ptr + 8 * offset, stride, s.n ÷ 2, Float64(w), _lim(Jutul.absolute_increment_limit(p)),
-                Float64(Jutul.minimum_value(p)), Float64(Jutul.maximum_value(p))), s.ctx.handle)
+    s = state[state_symbol]::B200Vector                      # nf x nc, fraction fastest
+    nf = Jutul.values_per_entity(model, p)
+    check(ccall((:jb_update_fractions, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int32, Int64, Float64, Float64, Float64, Float64, Int32),
+                s.ctx.handle, s.ptr, dx.ptr + 8 * offset, stride, nf, s.n ÷ nf, Float64(w), _lim(Jutul.absolute_increment_limit(p)),
+                Float64(Jutul.minimum_value(p)), Float64(Jutul.maximum_value(p)), Int32(Jutul.unit_update_preserve_direction(p))), s.ctx.handle)
     return s
 end
 

@@ -477,3 +477,70 @@ def assemble_2ph_props(hf, diag_pos, hf_pos, Tf, gdz, p, props, M0, dt, nnzb, sr
             for d in range(2):
                 nz[(int(diag_pos[c]) - 1) * 4 + 2 * d + a] = dv[d]
     return nz, r
+
+
+# ------------------------------------------------------------------ unit_sum_update! for nf > 2 (src/variables/utils.jl:393-526)
+MINIMUM_SAT_RELAX = 1e-3
+
+
+def _choose_increment(v, dv, abs_change=None, rel_change=None, minval=None, maxval=None, scale=None):
+    """choose_increment (src/variables/utils.jl:149-174)"""
+    if scale is not None:
+        dv = dv * scale
+    if abs_change is not None:
+        dv = np.sign(dv) * min(abs(dv), abs_change)
+    if rel_change is not None:
+        dv = np.sign(dv) * min(abs(dv), rel_change * abs(v))
+    if minval is not None:
+        dv = max(dv, minval - v)
+    if maxval is not None:
+        dv = min(dv, maxval - v)
+    return dv
+
+
+def _pick_relaxation(w, dv, dv0):
+    with np.errstate(all="ignore"):
+        r = np.float64(dv) / np.float64(dv0)
+    if dv0 != 0:
+        w = min(w, r)
+    return min(w, MINIMUM_SAT_RELAX)
+
+
+def _unit_update_magnitude_local(s, dx, nf, minval, maxval, abs_max):
+    dlast0 = 0.0
+    for i in range(nf - 1):
+        dv = _choose_increment(s[i], dx[i], abs_max, None, minval, maxval)
+        s[i] += dv
+        dlast0 -= dv
+    dlast = _choose_increment(s[nf - 1], dlast0, abs_max, None, minval, maxval)
+    s[nf - 1] += dlast
+    if dlast != dlast0:
+        t = 0.0
+        for i in range(nf):
+            t += s[i]
+        for i in range(nf):
+            s[i] = min(max(s[i], minval), maxval) / t
+
+
+def unit_sum_update(s, dx, nf, w0=1.0, abs_max=None, minval=0.0, maxval=1.0, preserve_direction=True):
+    """unit_sum_update! for nf > 2: s is (n, nf), dx is (n, nf - 1). In place."""
+    maxval = maxval - nf * minval
+    for c in range(s.shape[0]):
+        sc, dc = s[c], dx[c]
+        if not preserve_direction:
+            _unit_update_magnitude_local(sc, dc, nf, minval, maxval, abs_max)
+            continue
+        w = 1.0; dlast0 = 0.0
+        for i in range(nf - 1):
+            dv = _choose_increment(sc[i], dc[i], abs_max, None, minval, maxval)
+            dlast0 -= dc[i]
+            w = _pick_relaxation(w, dv, dc[i])
+        dlast = _choose_increment(sc[nf - 1], dlast0, abs_max, None, minval, maxval)
+        w = w0 * _pick_relaxation(w, dlast, dlast0)
+        if w <= MINIMUM_SAT_RELAX:
+            _unit_update_magnitude_local(sc, dc, nf, minval, maxval, abs_max)
+        else:
+            for i in range(nf - 1):
+                sc[i] += w * dc[i]
+            sc[nf - 1] += w * dlast0
+    return s

@@ -503,3 +503,21 @@ def test_poisson_adjoint_gradients_reference_goldens(J, O, ctx):
     np.add.at(gk, left, gK * K ** 2 / (6.0 * k[left] ** 2)); np.add.at(gk, right, gK * K ** 2 / (6.0 * k[right] ** 2))
     assert np.allclose(gk, [-0.33333492279052723, -0.4999980926513673, -0.1666631698608399], rtol=1e-3)      # the reference's own numbers
     assert np.allclose(gK * K / 1.0, [-2.0 / 3.0, -1.0 / 3.0], rtol=1e-3)
+
+
+@pytest.mark.parametrize("nf", [3, 4])
+@pytest.mark.parametrize("preserve_direction", [True, False])
+def test_unit_sum_update_many_fractions(J, ctx, nf, preserve_direction):
+    """a17 beyond two phases: unit_sum_update! with nf fractions (direction-preserving with its magnitude fall-back, and the
+    magnitude-preserving form) against the restatement: the same operations in the same order, so bit-exact."""
+    rng = np.random.default_rng(nf)
+    n = 4000
+    s = rng.random((n, nf)); s /= s.sum(axis=1, keepdims=True)
+    dx = 0.4 * rng.standard_normal((n, nf - 1))
+    dx[::7] = 0.0                                          # zero increments (dv0 == 0 branch of pick_relaxation)
+    ds = ctx.transfer(s.ravel()); ddx = ctx.transfer(dx.ravel())
+    J.unit_sum_update(ctx, ds, ddx, nf, n, w=1.0, abs_max=0.2, minval=0.0, maxval=1.0, preserve_direction=preserve_direction)
+    ref = W.unit_sum_update(s.copy(), dx, nf, 1.0, 0.2, 0.0, 1.0, preserve_direction)
+    got = ds.get().reshape(n, nf)
+    assert np.array_equal(got, ref)
+    assert np.all(got >= 0.0) and np.all(got <= 1.0) and np.allclose(got.sum(axis=1), 1.0, atol=1e-12)
