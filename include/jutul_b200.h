@@ -420,6 +420,9 @@ int32_t jb_dist_p2p_export(jb_dist* dist, char* handle64);
 int32_t jb_dist_p2p_open(jb_dist* dist, const char* handles /*world x 64*/, const int64_t* remote_off, const int64_t* remote_cap,
                          const int64_t* remote_nowned, const int64_t* remote_nlocal /* per neighbour: its n_owned, n_local */);
 int32_t jb_dist_p2p_status(jb_dist* dist);
+/* setup fallback: every rank calls this when ANY rank failed to export / open (the launcher agrees on it with a reduction);
+ * halo exchanges and all-reduces then take the NCCL path */
+int32_t jb_dist_p2p_disable(jb_dist* dist);
 int32_t jb_dist_halo_exchange(jb_dist* dist, double* d_vec, int32_t bs);
 int32_t jb_dist_allreduce(jb_dist* dist, double* vals /*host, in/out*/, int32_t n, int32_t op /*0 sum, 1 max*/);
 /* distributed Krylov: vector updates and inner products over owned rows, all-reduced; halo exchange before

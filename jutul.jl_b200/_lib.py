@@ -133,6 +133,7 @@ PROTOTYPES = {
     "jb_dist_p2p_export": (I32, [P, C.c_char_p]),
     "jb_dist_p2p_open": (I32, [P, C.c_char_p, PI64, PI64, PI64, PI64]),
     "jb_dist_p2p_status": (I32, [P]),
+    "jb_dist_p2p_disable": (I32, [P]),
     "jb_dist_halo_exchange": (I32, [P, P, I32]),
     "jb_dist_allreduce": (I32, [P, PF64, I32, I32]),
     "jb_krylov_set_dist": (I32, [P, P]),

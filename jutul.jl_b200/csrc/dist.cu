@@ -413,6 +413,13 @@ void jb_dist_pk_done(jb_dist* D, unsigned long long ar_epoch, unsigned long long
 }
 
 extern "C" {
+// Take the NCCL path from now on (setup fallback: some rank could not export / map the peer buffers and all ranks agreed
+// to drop the peer-memory path together). The mapped resources are released with the handle.
+int32_t jb_dist_p2p_disable(jb_dist* D) {
+    if (!D) return JB_ERR_ARG;
+    D->p2p = false;
+    return JB_OK;
+}
 // 0 ok; 1 an all-reduce timed out; 2 a halo exchange timed out (a peer is gone) — the caller must abort the run
 int32_t jb_dist_p2p_status(jb_dist* D) {
     if (!D || !D->p2p) return 0;

@@ -177,37 +177,53 @@ class HaloPlan:
             self._setup_peer_memory(td)
 
     def _setup_peer_memory(self, td):
-        """All-gather the IPC handles of the symmetric buffers and every rank's staging offsets (setup only)."""
+        """All-gather the IPC handles of the symmetric buffers and every rank's staging offsets (setup only). If ANY rank
+        cannot export or map the peer buffers (world > 16, no peer access, a multi-node launch), all ranks agree on it with a
+        reduction and continue on the NCCL path together; the collectives below are executed by every rank either way."""
         import torch
         ctx, comm, plan = self.ctx, self.comm, self.plan
         W = comm.world
         buf = C.create_string_buffer(64)
-        check(ctx.lib.jb_dist_p2p_export(self.h, buf), ctx.h, "jb_dist_p2p_export")
+        ok = 1
+        why = ""
+        if ctx.lib.jb_dist_p2p_export(self.h, buf) != 0:
+            ok, why = 0, "jb_dist_p2p_export: " + _lib.last_error(ctx.h)
         dev = torch.device("cuda", ctx.device) if td.get_backend() == "nccl" else torch.device("cpu")
         mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone().to(dev)
         allh = [torch.zeros_like(mine) for _ in range(W)]
         td.all_gather(allh, mine)
         handles = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
         # off[src] = where src's data starts in my staging / ghost section; off[W] = my ghost count, then my n_owned, n_local
-        off = np.full(W + 3, -1, dtype=np.int64)
+        off = np.full(W + 4, -1, dtype=np.int64)
         for k, q in enumerate(plan["neigh"]):
             off[int(q)] = plan["recv_ptr"][k]
         off[W] = max(plan["n_ghost"], 1)
-        off[W + 1] = plan["n_owned"]; off[W + 2] = plan["n_local"]
+        off[W + 1] = plan["n_owned"]; off[W + 2] = plan["n_local"]; off[W + 3] = ok
         t_off = torch.from_numpy(off).to(dev)
         allo = [torch.zeros_like(t_off) for _ in range(W)]
         td.all_gather(allo, t_off)
         tab = np.stack([t.cpu().numpy() for t in allo])        # tab[q][src]
-        ro = np.array([tab[int(q)][comm.rank] for q in plan["neigh"]], dtype=np.int64)
-        rc = np.array([tab[int(q)][W] for q in plan["neigh"]], dtype=np.int64)
-        rno = np.array([tab[int(q)][W + 1] for q in plan["neigh"]], dtype=np.int64)
-        rnl = np.array([tab[int(q)][W + 2] for q in plan["neigh"]], dtype=np.int64)
-        assert np.all(ro >= 0), "halo plans of neighbouring ranks are inconsistent"
-        check(ctx.lib.jb_dist_p2p_open(self.h, handles, ro.ctypes.data_as(_lib.PI64), rc.ctypes.data_as(_lib.PI64),
-                                       rno.ctypes.data_as(_lib.PI64), rnl.ctypes.data_as(_lib.PI64)), ctx.h, "jb_dist_p2p_open")
+        if not np.all(tab[:, W + 3] == 1):
+            ok = 0                                             # some rank could not export: nobody opens
+        if ok:
+            ro = np.array([tab[int(q)][comm.rank] for q in plan["neigh"]], dtype=np.int64)
+            rc = np.array([tab[int(q)][W] for q in plan["neigh"]], dtype=np.int64)
+            rno = np.array([tab[int(q)][W + 1] for q in plan["neigh"]], dtype=np.int64)
+            rnl = np.array([tab[int(q)][W + 2] for q in plan["neigh"]], dtype=np.int64)
+            assert np.all(ro >= 0), "halo plans of neighbouring ranks are inconsistent"
+            if ctx.lib.jb_dist_p2p_open(self.h, handles, ro.ctypes.data_as(_lib.PI64), rc.ctypes.data_as(_lib.PI64),
+                                        rno.ctypes.data_as(_lib.PI64), rnl.ctypes.data_as(_lib.PI64)) != 0:
+                ok, why = 0, "jb_dist_p2p_open: " + _lib.last_error(ctx.h)
         ctx.synchronize()
-        td.barrier()
-        self.p2p = True
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        td.all_reduce(flag, op=td.ReduceOp.MIN)               # every rank takes the same decision
+        if int(flag.item()) == 1:
+            self.p2p = True
+        else:
+            ctx.lib.jb_dist_p2p_disable(self.h)
+            self.p2p = False
+            if comm.rank == 0 or why:
+                print(f"[jutul_b200] rank {comm.rank}: peer-memory collectives unavailable ({why or 'another rank failed'}); using NCCL", flush=True)
 
     def check(self):
         st = self.ctx.lib.jb_dist_p2p_status(self.h)
