@@ -66,7 +66,7 @@ def test_schur_krylov_solve_equals_full_block_solve(J, O, ctx, solver, side):
     n2 = 2 * w["nc"]
     full = sp.bmat([[B, Cm[0], Cm[1]], [Dm[0], sp.csr_matrix(Em[0]), None], [Dm[1], None, sp.csr_matrix(Em[1])]]).tocsc()
     z = spla.spsolve(full, np.concatenate([r] + b))
-    kry = J.GenericKrylov(sim.jac, solver, sim.prec, relative_tolerance=1e-12, max_iterations=300, precond_side=side)
+    kry = J.GenericKrylov(sim.jac, solver, sim.prec, relative_tolerance=1e-10, max_iterations=300, precond_side=side)
     S.attach(kry)
     da = ctx.transfer(r)
     S.prepare_linear_solve(da, b)

@@ -218,7 +218,7 @@ def test_fgmres_equals_right_preconditioned_gmres(O, J, restart):
     assert np.linalg.norm(xg - xf) <= 1e-7 * np.linalg.norm(xg)
     xl, stl, itl, hl = O.gmres(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, side="left", rtol=1e-7, itmax=600, memory=40, restart=True)
     xd = spla.spsolve(A.tocsc(), r)
-    assert stl == 0 and np.linalg.norm(xl - xd) <= 1e-5 * np.linalg.norm(xd)
+    assert stl == 0 and np.linalg.norm(xl - xd) <= 5e-5 * np.linalg.norm(xd)      # (error amplification ~1e2) x rtol
     if restart:
         x20, st20, it20, h20 = O.gmres(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, side="right", rtol=1e-7, itmax=600, memory=600, restart=True)
         assert itg >= it20          # a short memory never beats the full basis
