@@ -66,13 +66,13 @@ def test_schur_krylov_solve_equals_full_block_solve(J, O, ctx, solver, side):
     n2 = 2 * w["nc"]
     full = sp.bmat([[B, Cm[0], Cm[1]], [Dm[0], sp.csr_matrix(Em[0]), None], [Dm[1], None, sp.csr_matrix(Em[1])]]).tocsc()
     z = spla.spsolve(full, np.concatenate([r] + b))
-    kry = J.GenericKrylov(sim.jac, solver, sim.prec, relative_tolerance=1e-10, max_iterations=1000, precond_side=side)
+    kry = J.GenericKrylov(sim.jac, solver, sim.prec, relative_tolerance=1e-12, max_iterations=600, precond_side=side)
     S.attach(kry)
     da = ctx.transfer(r)
     S.prepare_linear_solve(da, b)
     dx = ctx.zeros(n2)
     ok, its, hist, st = J.linear_solve(kry, da, dx)
-    # BiCGStab may stagnate a little above 1e-10 on this system (round-off floor of the recurrence); what is pinned is the
+    # BiCGStab may stagnate a little above 1e-12 on this system (round-off floor of the recurrence); what is pinned is the
     # solution against the direct solve of the full block system below
     assert ok or hist[-1] <= 1e-9 * hist[0], (st, its, hist[-1] / hist[0])
     y = S.update_dx_from_vector(dx)
@@ -85,7 +85,8 @@ def test_schur_krylov_solve_equals_full_block_solve(J, O, ctx, solver, side):
     S.detach(kry)
     ok, its, hist, st = J.linear_solve(kry, ctx.transfer(r), dx)
     xb = spla.spsolve(B.tocsc(), r)
-    assert (ok or hist[-1] <= 1e-9 * hist[0]) and np.linalg.norm(dx.get() + xb) <= 1e-7 * np.linalg.norm(xb)
+    assert (ok or hist[-1] <= 1e-9 * hist[0]) and np.linalg.norm(dx.get() + xb) <= 1e-7 * np.linalg.norm(xb), \
+        (ok, st, its, hist[-1] / hist[0], np.linalg.norm(dx.get() + xb) / np.linalg.norm(xb))
 
 
 def test_schur_multimodel_known_answer(J, ctx):
