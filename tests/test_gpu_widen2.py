@@ -524,3 +524,54 @@ def test_unit_sum_update_many_fractions(J, ctx, nf, preserve_direction):
     got = ds.get().reshape(n, nf)
     assert np.array_equal(got, ref)
     assert np.all(got >= 0.0) and np.all(got <= 1.0) and np.allclose(got.sum(axis=1), 1.0, atol=1e-12)
+
+
+def test_widen_edge_cases_and_error_codes(J, O, ctx):
+    """Empty, degenerate and bad inputs of the round-2 entry points: hard errors are raised with a message, nothing hangs."""
+    import ctypes as C
+    lib = ctx.lib
+    # single-node table: constant extrapolation (LinearInterpolant with one input, src/interpolation.jl:80-84)
+    t = J.LinearInterpolant(ctx, [2.0], [7.0])
+    f = ctx.zeros(3)
+    t.interpolate(ctx.transfer(np.array([-5.0, 2.0, 9.0])), f)
+    assert np.array_equal(f.get(), [7.0, 7.0, 7.0])
+    # unsorted 1-D input is sorted like the reference does; unsorted 2-D axes are rejected
+    t2 = J.LinearInterpolant(ctx, [1.0, 0.0, 2.0], [10.0, 0.0, 20.0])
+    t2.interpolate(ctx.transfer(np.array([0.5, 1.5, 1.0])), f)
+    assert np.allclose(f.get(), [5.0, 15.0, 10.0])
+    with pytest.raises(J.JutulB200Error):
+        J.BilinearInterpolant(ctx, [0.0, 2.0, 1.0], [0.0, 1.0], np.zeros((3, 2)))
+    # Schur handle without eliminated groups: the operator is the plain Jacobian
+    A = J.build_sparse_matrix(ctx, [1, 1, 2, 2], [1, 2, 1, 2], 2, 1)
+    A.set_nonzeros(np.array([4.0, 1.0, 2.0, 3.0]))
+    S = J.MultiLinearizedSystemSchur(A, [], [], [])
+    assert S.M == 0 and S.update([], [], []) == 0
+    x = ctx.transfer(np.array([1.0, -1.0])); y = ctx.zeros(2)
+    S.mul(y, x)
+    assert np.array_equal(y.get(), [3.0, -1.0])
+    # transpose_update on a matrix that is not a transpose
+    assert lib.jb_csr_transpose_update(A.h) == -2
+    AT = A.adjoint(); AT.update_adjoint()
+    assert np.array_equal(AT.nonzeros(), [4.0, 2.0, 1.0, 3.0])
+    # fraction update: more than 8 fractions unsupported, zero cells is a no-op
+    assert lib.jb_update_fractions(ctx.h, x.ptr, x.ptr, 8, 9, 1, 1.0, 0.2, 0.0, 1.0, 1) == -2
+    assert lib.jb_update_fractions(ctx.h, x.ptr, x.ptr, 2, 3, 0, 1.0, 0.2, 0.0, 1.0, 1) == 0
+    # variable graph: too many variables, wrong dependency count, empty cell set
+    with pytest.raises(J.JutulB200Error):
+        J.SecondaryVariables(ctx, 4, {"P": dict(kind="primary"), **{f"V{i}": dict(kind="exp", deps=["P"]) for i in range(40)}})
+    with pytest.raises(J.JutulB200Error):
+        J.SecondaryVariables(ctx, 4, {"P": dict(kind="primary"), "Q": dict(kind="quotient", deps=["P"])})
+    sv = J.SecondaryVariables(ctx, 0, {"P": dict(kind="primary"), "E": dict(kind="exp", deps=["P"], output=True)})
+    sv.update_secondary_variables({"P": ctx.zeros(1)}, {"E": ctx.zeros(1)})
+    # NFVM law: alignment against a Jacobian of the wrong size
+    disc = J.NFVMDiscretization(ctx, [1, 2], [2, 3], 3, dict(T_left=[1.0, 1.0], T_right=[-1.0, -1.0], ptr=[1, 1, 1], cell=np.zeros(0, dtype=np.int64), T=np.zeros(0)))
+    with pytest.raises(J.JutulB200Error):
+        disc.align_to_jacobian(A)
+    jac = disc.declare_pattern()
+    rp, ci = jac.pattern()
+    assert np.array_equal(rp, [1, 3, 6, 8]) and np.array_equal(ci, [1, 2, 1, 2, 3, 2, 3])      # tridiagonal: TPFA stencil
+    disc.align_to_jacobian(jac)
+    r = ctx.zeros(3); q = ctx.zeros(2)
+    disc.update_equation_and_linearized_system(ctx.transfer(np.array([3.0, 2.0, 0.0])), r, q=q)
+    assert np.array_equal(q.get(), [1.0, 2.0]) and np.array_equal(r.get(), [1.0, 1.0, -2.0])
+    assert np.array_equal(jac.nonzeros(), [1.0, -1.0, -1.0, 2.0, -1.0, -1.0, 1.0])
