@@ -188,7 +188,7 @@ struct jb_twophase {
     DBuf<int32_t> d_pos_lr, d_pos_rl;   // per face: block index of (l,r) and (r,l) (variant B)
     DBuf<double> d_pv;
     DBuf<double> d_rec;               // per cell {p, sw, rho_w, rho_o}
-    DBuf<double> d_rec16;             // per cell {p, -, -, -, rho_w (v, dp, ds), rho_o, lambda_w, lambda_o}: props_assembly.cu
+    DBuf<double> d_rec16;             // per cell and phase {p, rho (v, dp, ds), lambda (v, dp, ds), -}: props_assembly.cu
     DBuf<double> d_src;               // dense 2 x nc source buffer (only if nsrc > 0)
     DBuf<int32_t> d_src_cells;
     DBuf<double> d_src_vals;

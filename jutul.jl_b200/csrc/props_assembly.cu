@@ -7,8 +7,8 @@
 //   theta = p_self - p_other + sign*g*dz * (rho_self + rho_other)/2,  q = T theta,  F_a = lambda_a|upstream * q,
 //   r_a,c = (M_a - M0_a)/dt + sum_hf F_a,  J[c,c] = d(acc) + sum dF/dx_c,  J[c,o] = -dF_{o->c}/dx_o,
 // with every property partial taken from the planes (chain rule through whatever tables / power laws produced them).
-// Schedule: a pack kernel writes one 128-byte record per cell {p, rho_w.., rho_o.., lambda_w.., lambda_o..} so that a neighbour
-// gather is one aligned 128-byte line; lane pair (2j, 2j+1) owns cell j, lane a evaluates phase a of every half-face in conn_pos
+// Schedule: a pack kernel writes one 128-byte record per cell, a 64-byte half per phase {p, rho, lambda with partials}, so that a
+// neighbour gather is two 256-bit loads of one aligned line; lane pair (2j, 2j+1) owns cell j, lane a evaluates phase a of every half-face in conn_pos
 // order with register sums (the summation order of fill_conservation_eq!), the pair writes each 2x2 off-diagonal block with two
 // 16-byte stores. Row-owner form: no atomics, every entry written once.
 #include "jb_internal.cuh"
@@ -16,23 +16,25 @@
 __global__ void __launch_bounds__(256) props_pack_kernel(i64 nc, const double* __restrict__ p, const double* __restrict__ rw, const double* __restrict__ ro,
                                                          const double* __restrict__ mw, const double* __restrict__ mo, double* __restrict__ rec) {
     for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (i64)gridDim.x * blockDim.x) {
+        // one 64-byte half per phase: {p, rho, rho_p, rho_s | lambda, lambda_p, lambda_s, -}: a lane reads its phase with two 256-bit loads
         double* o = rec + 16 * (size_t)c;
-        double4 q0 = make_double4(__ldg(p + c), 0.0, 0.0, 0.0);
-        double4 q1 = make_double4(__ldg(rw + c), __ldg(rw + nc + c), __ldg(rw + 2 * nc + c), __ldg(ro + c));
-        double4 q2 = make_double4(__ldg(ro + nc + c), __ldg(ro + 2 * nc + c), __ldg(mw + c), __ldg(mw + nc + c));
-        double4 q3 = make_double4(__ldg(mw + 2 * nc + c), __ldg(mo + c), __ldg(mo + nc + c), __ldg(mo + 2 * nc + c));
-        reinterpret_cast<double4*>(o)[0] = q0; reinterpret_cast<double4*>(o)[1] = q1;
-        reinterpret_cast<double4*>(o)[2] = q2; reinterpret_cast<double4*>(o)[3] = q3;
+        const double pc = __ldg(p + c);
+        reinterpret_cast<double4*>(o)[0] = make_double4(pc, __ldg(rw + c), __ldg(rw + nc + c), __ldg(rw + 2 * nc + c));
+        reinterpret_cast<double4*>(o)[1] = make_double4(__ldg(mw + c), __ldg(mw + nc + c), __ldg(mw + 2 * nc + c), 0.0);
+        reinterpret_cast<double4*>(o)[2] = make_double4(pc, __ldg(ro + c), __ldg(ro + nc + c), __ldg(ro + 2 * nc + c));
+        reinterpret_cast<double4*>(o)[3] = make_double4(__ldg(mo + c), __ldg(mo + nc + c), __ldg(mo + 2 * nc + c), 0.0);
     }
 }
 
 struct PhaseRec { double p, rho, rho_p, rho_s, mob, mob_p, mob_s; };
 __device__ __forceinline__ PhaseRec load_phase(const double* __restrict__ rec, size_t c, int a) {
-    const double* r = rec + 16 * c;
+    const double* r = rec + 16 * c + 8 * a;
+    double u[4], v[4];
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(u[0]), "=d"(u[1]), "=d"(u[2]), "=d"(u[3]) : "l"(r));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(r + 4));
     PhaseRec o;
-    o.p = __ldg(r);
-    o.rho = __ldg(r + 4 + 3 * a); o.rho_p = __ldg(r + 5 + 3 * a); o.rho_s = __ldg(r + 6 + 3 * a);
-    o.mob = __ldg(r + 10 + 3 * a); o.mob_p = __ldg(r + 11 + 3 * a); o.mob_s = __ldg(r + 12 + 3 * a);
+    o.p = u[0]; o.rho = u[1]; o.rho_p = u[2]; o.rho_s = u[3];
+    o.mob = v[0]; o.mob_p = v[1]; o.mob_s = v[2];
     return o;
 }
 

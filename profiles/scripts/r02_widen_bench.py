@@ -76,6 +76,31 @@ for variant in ("cells", "faces"):
     ms = timed(lambda: sim.law.update_equation_and_linearized_system(sim.p, sim.s, sim.M0, w["dt"], sim.r, variant=variant), reps=5)
     line("two-phase assembly, variant %s (%s)" % (variant, "row owner, no atomics" if variant == "cells" else "fvm_face_assembly!: face scatter, warp-aggregated FP64 atomics"),
          ms, alg["assembly"], cells=nc, note="includes the secondary-variable (density) kernel")
+# the same law assembled from the variable graph's output planes (closed forms of the built-in law as graph)
+par = w["params"]
+gdefs = {
+    "Pressure": dict(kind="primary"), "Sw": dict(kind="primary"), "PoreVolume": dict(kind="parameter"),
+    "So": dict(kind="affine", deps=["Sw"], c=[1.0, -1.0]),
+    "DensityW": dict(kind="exp", deps=["Pressure"], c=[par[0], par[2], par[6]], output=True),
+    "DensityO": dict(kind="exp", deps=["Pressure"], c=[par[1], par[3], par[6]], output=True),
+    "KrW": dict(kind="product", deps=["Sw", "Sw"]), "KrO": dict(kind="product", deps=["So", "So"]),
+    "MobilityW": dict(kind="product", deps=["DensityW", "KrW"], c=[1.0 / par[4]], output=True),
+    "MobilityO": dict(kind="product", deps=["DensityO", "KrO"], c=[1.0 / par[5]], output=True),
+    "MassW": dict(kind="product", deps=["PoreVolume", "DensityW", "Sw"], output=True),
+    "MassO": dict(kind="product", deps=["PoreVolume", "DensityO", "So"], output=True),
+}
+sv2 = J.SecondaryVariables(ctx, nc, gdefs)
+sw_dev = ctx.transfer(w["sw0"] if sim.perm is None else sim._cells_to_device_host(w["sw0"]))
+pv_dev = ctx.transfer(w["pv"] if sim.perm is None else sim._cells_to_device_host(w["pv"]))
+gstate = {"Pressure": sim.p, "Sw": sw_dev, "PoreVolume": pv_dev}
+gout = {n: ctx.zeros(3 * nc) for n in sv2.outputs}
+ms = timed(lambda: sv2.update_secondary_variables(gstate, gout), reps=5)
+line("varprog_kernel<2> (two-phase property graph: 9 secondary variables, 6 outputs with partials)", ms, nc * (3 * 8 + 6 * 3 * 8), cells=nc)
+ms = timed(lambda: J.assemble_with_properties(sim.law, sim.p, gout, sim.M0, w["dt"], sim.r), reps=5)
+line("two-phase assembly from property planes (props_pack_kernel + twophase_props_kernel)", ms, alg["assembly"] + nc * (13 * 8 + 128) + nc * 18 * 8, cells=nc,
+     note="bytes: SURVEY formula + planes read (18 doubles per cell) + 128-byte records written and read")
+for a in gout.values():
+    a.free()
 nb = sim.jac.nnz
 JT = sim.jac.adjoint()
 ms = timed(lambda: JT.update_adjoint(), reps=5)
