@@ -110,3 +110,25 @@ def test_bench_reference_arm_contract():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out1 = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root, env=env)
     assert out1.returncode == 0 and out1.stdout.strip() == ""
+
+
+def test_interpolator_capping_matches_oracle(J):
+    """get_1d_interpolator / get_2d_interpolator end-point capping of the host mirror (jutul.jl_b200/variables.py) equals the
+    oracle restatement of src/interpolation.jl:118-154,224-285 (the device only ever sees the capped arrays)."""
+    from oracle import widen as W
+    V = J.variables
+    xs = np.array([0.0, 0.5, 1.5, 4.0]); ys = xs ** 2
+    X, F = V.cap_1d(xs, ys)
+    I = W.get_1d_interpolator(xs, ys)
+    assert np.array_equal(X, I.X) and np.array_equal(F, I.F)
+    X1, F1 = V.cap_1d([3.0], [7.0])
+    I1 = W.get_1d_interpolator([3.0], [7.0])
+    assert np.array_equal(X1, I1.X) and np.array_equal(F1, I1.F)
+    gx = np.array([0.0, 1.0, 3.0]); gy = np.array([-1.0, 0.0, 2.0, 5.0])
+    fs = np.arange(12.0).reshape(3, 4)
+    X2, Y2, F2 = V.cap_2d(gx, gy, fs)
+    I2 = W.get_2d_interpolator(gx, gy, fs)
+    assert np.array_equal(X2, I2.X) and np.array_equal(Y2, I2.Y) and np.array_equal(F2, I2.F)
+    # VarSpec mirrors jb_var_spec: 4 + 12 + 4 + 4 + 32 bytes, doubles 8-byte aligned
+    import ctypes as C
+    assert C.sizeof(V.VarSpec) == 56 and V.VarSpec.c.offset == 24
