@@ -667,11 +667,12 @@ __device__ __forceinline__ double4 ld_coef(const double4* __restrict__ p) {
     const double2 a = __ldg(q), b = __ldg(q + 1);
     return make_double4(a.x, a.y, b.x, b.y);
 }
-__global__ void __launch_bounds__(256) nfvm_law_init_kernel(i64 nc, i64 nnz, const int32_t* __restrict__ diag, const double* __restrict__ acc,
-                                                            const double* __restrict__ dacc, double* __restrict__ nz, double* __restrict__ r) {
+// zero the touched Jacobian entries (here: all of them, the law is the only equation of the system) and start the residual
+// from the accumulation term (fvm_assembly.jl:216-236)
+__global__ void __launch_bounds__(256) nfvm_law_init_kernel(i64 nc, i64 nnz, const double* __restrict__ acc, double* __restrict__ nz,
+                                                            double* __restrict__ r) {
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (i64)gridDim.x * blockDim.x) nz[i] = 0.0;
     for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (i64)gridDim.x * blockDim.x) r[c] = acc ? __ldg(acc + c) : 0.0;
-    (void)diag; (void)dacc;
 }
 __global__ void __launch_bounds__(256) nfvm_law_diag_kernel(i64 nc, const int32_t* __restrict__ diag, const double* __restrict__ dacc, double* __restrict__ nz) {
     for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (i64)gridDim.x * blockDim.x) nz[__ldg(diag + c)] = __ldg(dacc + c);
@@ -815,7 +816,7 @@ int32_t jb_nfvm_assemble(jb_nfvm* d, const double* d_p, int64_t nph, int64_t ph,
     jb_csr* A = d->csr;
     {
         ProfScope _ps(ctx, JB_PROF_ASSEMBLY);
-        nfvm_law_init_kernel<<<sgrid(ctx, std::max(A->nnzb, d->nc)), 256, 0, ctx->stream>>>(d->nc, A->nnzb, A->d_diag.p, d_acc, d_dacc, A->d_val.p, d_r);
+        nfvm_law_init_kernel<<<sgrid(ctx, std::max(A->nnzb, d->nc)), 256, 0, ctx->stream>>>(d->nc, A->nnzb, d_acc, A->d_val.p, d_r);
         JB_CHECK_LAUNCH(ctx);
         if (d_dacc) { nfvm_law_diag_kernel<<<sgrid(ctx, d->nc), 256, 0, ctx->stream>>>(d->nc, A->d_diag.p, d_dacc, A->d_val.p); JB_CHECK_LAUNCH(ctx); }
         nfvm_law_faces_kernel<<<sgrid(ctx, d->nf), 256, 0, ctx->stream>>>(d->nf, d->scheme, d->left.p, d->right.p, d->d_vpos.p, d->d_vars.p, d->d_coef.p,
