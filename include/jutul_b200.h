@@ -361,6 +361,9 @@ int32_t jb_update_scalar(jb_ctx* ctx, double* d_v, const double* d_dx, int64_t d
                          double w, double abs_max, double rel_max, double minv, double maxv, double scale);
 int32_t jb_update_fraction_pair(jb_ctx* ctx, double* d_s /*2 x n*/, const double* d_dx, int64_t dx_stride,
                                 int64_t n, double w, double abs_max, double minval, double maxval);
+/* dst[i * dst_stride] = src[i * src_stride], i < n (device arrays): a row of a k x n state array (Saturations, TotalMasses) as a
+ * contiguous per-cell vector for the secondary-variable graph, and back */
+int32_t jb_copy_strided(jb_ctx* ctx, double* d_dst, int64_t dst_stride, const double* d_src, int64_t src_stride, int64_t n);
 /* unit_sum_update! for nf fractions (src/variables/utils.jl:393-521): nf == 2 is jb_update_fraction_pair; nf > 2 runs
  * unit_update_direction_local! (preserve_direction = 1, the FractionVariables default) with its fall-back
  * unit_update_magnitude_local!, or the magnitude-preserving update alone (0). d_s is nf x n (fraction fastest), the nf - 1

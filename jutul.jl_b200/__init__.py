@@ -695,7 +695,7 @@ def timer_stop(ctx):
     return ms.value
 
 
-from .simulator import HeatSimulator, PoissonSimulator, TwoPhaseSimulator  # noqa: E402
+from .simulator import HeatSimulator, PoissonSimulator, PropertyTwoPhaseSimulator, TwoPhaseSimulator  # noqa: E402
 from . import workloads  # noqa: E402,F401
 from .multimodel import MultiLinearizedSystemSchur  # noqa: E402
 from .variables import (BilinearInterpolant, LinearInterpolant, SecondaryVariables, get_1d_interpolator,  # noqa: E402

@@ -113,6 +113,7 @@ PROTOTYPES = {
     "jb_scale_system": (I32, [P, P, I32, F64]),
     "jb_update_scalar": (I32, [P, P, P, I64, I64, F64, F64, F64, F64, F64, F64]),
     "jb_update_fraction_pair": (I32, [P, P, P, I64, I64, F64, F64, F64, F64]),
+    "jb_copy_strided": (I32, [P, P, I64, P, I64, I64]),
     "jb_update_fractions": (I32, [P, P, P, I64, I32, I64, F64, F64, F64, F64, I32]),
     "jb_increment_norm": (I32, [P, P, I64, I64, PF64, PF64]),
     "jb_maxabs_rows": (I32, [P, P, I32, I64, PF64]),

@@ -86,6 +86,9 @@ __global__ void __launch_bounds__(256) update_fractions_kernel(i64 n, int nf, do
         for (int i = 0; i < nf; i++) sg[c * nf + i] = s[i];
     }
 }
+__global__ void __launch_bounds__(256) copy_strided_kernel(i64 n, double* __restrict__ dst, i64 ds, const double* __restrict__ src, i64 ss) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) dst[i * ds] = __ldg(src + i * ss);
+}
 __global__ void __launch_bounds__(256) increment_norm_kernel(i64 n, const double* __restrict__ dx, i64 stride, double* out, double* partials,
                                                              unsigned int* counter) {
     double a[1] = {0.0}, b[1] = {0.0};
@@ -272,6 +275,19 @@ int32_t jb_update_fraction_pair(jb_ctx* ctx, double* d_s, const double* d_dx, in
     if (n == 0) return JB_OK;
     int rc = jb_launch_update_pair(ctx, d_s, d_dx, dx_stride, n, w, abs_max, minval, maxval);
     if (rc != JB_OK) return rc;
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+// dst[i * dst_stride] = src[i * src_stride]: rows of a k x n state array (Saturations is 2 x n) as the contiguous per-cell
+// vectors the secondary-variable graph reads, and back (total masses of two phases -> 2 x n)
+int32_t jb_copy_strided(jb_ctx* ctx, double* d_dst, int64_t dst_stride, const double* d_src, int64_t src_stride, int64_t n) {
+    if (!ctx || !d_dst || !d_src || n < 0 || dst_stride < 1 || src_stride < 1) return JB_ERR_ARG;
+    if (n == 0) return JB_OK;
+    {
+        ProfScope _ps(ctx, JB_PROF_NEWTON);
+        copy_strided_kernel<<<sgrid(ctx, n), 256, 0, ctx->stream>>>(n, d_dst, dst_stride, d_src, src_stride);
+        JB_CHECK_LAUNCH(ctx);
+    }
     JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return JB_OK;
 }

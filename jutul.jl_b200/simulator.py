@@ -190,6 +190,59 @@ class TwoPhaseSimulator:
         check(self.ctx.lib.jb_twophase_update_after_step(self.law.h), self.ctx.h, "jb_twophase_update_after_step")
 
 
+class PropertyTwoPhaseSimulator(TwoPhaseSimulator):
+    """The two-phase model with its properties given as a secondary-variable graph (tables, power laws, ...) instead of the
+    closed forms of the built-in law: every Newton iteration runs update_secondary_variables! (one kernel over the graph,
+    src/variable_evaluation.jl:87-148) and assembles from the evaluated planes (jb_twophase_assemble_props); state0's masses
+    come from the same graph. `definitions` must declare the primaries Pressure and Sw, the parameter PoreVolume and the
+    outputs MassW, MassO, DensityW, DensityO, MobilityW, MobilityO (jutul_b200.SecondaryVariables)."""
+
+    OUTPUTS = ("MassW", "MassO", "DensityW", "DensityO", "MobilityW", "MobilityO")
+
+    def __init__(self, ctx, N, nc, Tf, gdz, pv, definitions, **kw):
+        J = _pkg()
+        kw.setdefault("ordering", None)
+        assert kw["ordering"] is None, "the property-driven simulator keeps the caller's numbering"
+        super().__init__(ctx, N, nc, Tf, gdz, pv, **kw)
+        self.graph = J.SecondaryVariables(ctx, nc, definitions)
+        assert set(self.OUTPUTS) <= set(self.graph.outputs) and set(self.graph.inputs) == {"Pressure", "Sw", "PoreVolume"}
+        self.sw = ctx.empty(nc)
+        self.pv_dev = ctx.transfer(np.asarray(pv, dtype=np.float64))
+        self.planes = {n: ctx.zeros(3 * nc) for n in self.graph.outputs}
+
+    def update_secondary_variables(self):
+        lib = self.ctx.lib
+        check(lib.jb_copy_strided(self.ctx.h, self.sw.ptr, 1, self.s.ptr, 2, self.nc), self.ctx.h, "jb_copy_strided")
+        self.graph.update_secondary_variables({"Pressure": self.p, "Sw": self.sw, "PoreVolume": self.pv_dev}, self.planes)
+
+    def update_before_step(self):
+        """state0 <- state: the conserved masses of the graph at the start of the step."""
+        lib = self.ctx.lib
+        self.update_secondary_variables()
+        for a, name in enumerate(("MassW", "MassO")):
+            check(lib.jb_copy_strided(self.ctx.h, self.M0.offset(a), 2, self.planes[name].ptr, 1, self.nc), self.ctx.h, "jb_copy_strided")
+
+    def perform_step(self, dt, solve=True, report=None):
+        J = _pkg()
+        rep = {} if report is None else report
+        self.update_secondary_variables()
+        J.assemble_with_properties(self.law, self.p, self.planes, self.M0, dt, self.r)
+        e = J.convergence_criterion(self.ctx, self.r, 2, self.nc)
+        rep["errors"] = e
+        if not np.all(np.isfinite(e)):
+            rep["failure"] = "non-finite residual"
+            return False, e, rep
+        converged = bool(np.all(e <= self.tolerance))
+        rep["converged"] = converged
+        if converged or not solve:
+            return converged, e, rep
+        ok, its, hist, st = J.linear_solve(self.krylov, self.r, self.dx)
+        rep["linear_iterations"], rep["linear_status"], rep["linear_residuals"] = its, st, hist
+        J.update_primary_variable(self.ctx, self.p, self.dx, self.nc, dx_stride=2, abs_max=self.dp_abs_max)
+        J.unit_update_pairs(self.ctx, self.s, self.dx.offset(1), self.nc, dx_stride=2, abs_max=self.ds_abs_max)
+        return False, e, rep
+
+
 class HeatSimulator:
     """SimpleHeatSystem on a periodic nx x ny CartesianMesh (config 1)."""
 

@@ -23,6 +23,7 @@ i64 = np.int64
 # ------------------------------------------------------------------ ForwardDiff.Dual written out
 class Dual:
     __slots__ = ("v", "d")
+    __array_ufunc__ = None             # ndarray (op) Dual defers to Dual.__r<op>__ instead of broadcasting over objects
 
     def __init__(self, v, d):
         self.v = v                     # float or ndarray (n,)

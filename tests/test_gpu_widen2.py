@@ -577,3 +577,57 @@ def test_widen_edge_cases_and_error_codes(J, O, ctx):
     disc.update_equation_and_linearized_system(ctx.transfer(np.array([3.0, 2.0, 0.0])), r, q=q)
     assert np.array_equal(q.get(), [1.0, 2.0]) and np.array_equal(r.get(), [1.0, 1.0, -2.0])
     assert np.array_equal(jac.nonzeros(), [1.0, -1.0, -1.0, 2.0, -1.0, -1.0, 1.0])
+
+
+def test_property_driven_timestep_matches_oracle_newton_loop(J, O, ctx):
+    """A whole implicit timestep of the two-phase model whose properties are a secondary-variable graph with tabulated
+    viscosities and Brooks-Corey curves (PropertyTwoPhaseSimulator: graph kernel -> property assembly -> ILU(0)-BiCGStab ->
+    update, every Newton iteration) against the same Newton loop on the CPU: graph on Duals in sort_symbols order, the
+    reference's fill on property Duals, direct solve, the reference's update rules. Same Newton count, iterate to 1e-7."""
+    import scipy.sparse.linalg as spla2
+    from conftest import oracle_system
+    w = J.workloads.unstructured_hex(8, 7, 5)
+    nc = w["nc"]
+    defs_g = _twophase_property_graph(J, ctx, w["params"], True)
+    sim = J.PropertyTwoPhaseSimulator(ctx, w["N"], nc, w["Tf"], w["gdz"], w["pv"], defs_g, rtol=1e-11, max_linear_iterations=400, tolerance=1e-6)
+    sim.set_forces(w["src_cells"], w["src_vals"])
+    sim.set_state(w["p0"], w["sw0"])
+    ok, reps = sim.solve_ministep(w["dt"])
+    assert ok
+    p_g, sw_g = sim.get_state()
+    # oracle loop
+    xs = np.linspace(5e6, 2e7, 40)
+    muw, muo = w["params"][4], w["params"][5]
+    tabs = dict(ViscW=W.get_1d_interpolator(xs, muw * (1 + 2e-9 * (xs - 1e7))), ViscO=W.get_1d_interpolator(xs, muo * (1 + 5e-9 * (xs - 1e7))))
+    defs_o = {k: dict(v) for k, v in defs_g.items()}
+    for k in tabs:
+        defs_o[k]["table"] = tabs[k]
+    for v in defs_o.values():
+        v.setdefault("c", [1.0, 0.0, 0.0, 0.0] if v["kind"] not in ("affine",) else [0.0, 1.0, 1.0, 1.0])
+    prim = ["Pressure", "Sw"]; par = ["PoreVolume"]
+    sec = {k: v.get("deps", []) for k, v in defs_o.items() if v["kind"] not in ("primary", "parameter")}
+    order = W.sort_secondary_variables(prim, sec, par)
+    e2 = np.eye(2)
+
+    def props_of(p, sw):
+        st = {"Pressure": W.Dual(p, e2[:, :1] * np.ones(nc)), "Sw": W.Dual(sw, e2[:, 1:] * np.ones(nc)), "PoreVolume": w["pv"]}
+        W.update_secondary_variables_state(st, defs_o, order)
+        return {n: np.vstack([st[n].v, st[n].d]) for n in sim.OUTPUTS}
+    sy = oracle_system(O, w)
+    nnzb = sy["colidx"].shape[0]
+    p = w["p0"].copy(); s = np.stack([w["sw0"], 1 - w["sw0"]], axis=1).ravel().copy()
+    pr0 = props_of(p, s[0::2].copy())
+    M0 = np.stack([pr0["MassW"][0], pr0["MassO"][0]], axis=1).ravel()
+    n_newton = 0
+    for it in range(1, 17):
+        pr = props_of(p, s[0::2].copy())
+        nz, r = W.assemble_2ph_props(sy["hf"], sy["diag_pos"], sy["hf_pos"], w["Tf"], w["gdz"], p, pr, M0, w["dt"], nnzb, w["src_cells"], w["src_vals"])
+        if np.all(O.maxabs_rows(r, 2) <= 1e-6):
+            break
+        A = to_scipy(nc, 2, sy["rowptr"], sy["colidx"], nz)
+        dx = -spla2.spsolve(A.tocsc(), r)
+        O.update_scalar(p, dx, dx_stride=2)
+        O.update_fraction_pair(s, dx[1:], abs_max=0.2, dx_stride=2)
+        n_newton += 1
+    assert n_newton == sum(1 for rp in reps if "linear_iterations" in rp)
+    assert np.abs(p_g - p).max() <= 1e-7 * np.abs(p).max() and np.abs(sw_g - s[0::2]).max() <= 1e-7
