@@ -704,6 +704,10 @@ function assemble_with_properties!(s::B200TPFAStorage, props::Vector{B200Vector}
                                    s.law, s.d_p.ptr, pp, s.d_M0.ptr, dt, s.d_r.ptr), s.ctx.handle)
     return nothing
 end
+# a row of a k x n device state array as a contiguous per-cell vector (inputs of the graph), and back (masses -> 2 x n)
+copy_strided!(dst::B200Vector, dst_offset::Integer, dst_stride::Integer, src::B200Vector, src_offset::Integer, src_stride::Integer, n::Integer) =
+    (check(ccall((:jb_copy_strided, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64),
+                 dst.ctx.handle, dst.ptr + 8 * dst_offset, dst_stride, src.ptr + 8 * src_offset, src_stride, n), dst.ctx.handle); dst)
 # update_after_step! for the device-resident stepping (state0 <- accepted state; masses formed on the device)
 update_after_step_b200!(s::B200TPFAStorage) = (check(ccall((:jb_twophase_update_after_step, LIB), Int32, (Ptr{Cvoid},), s.law), s.ctx.handle); nothing)
 
