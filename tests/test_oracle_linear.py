@@ -139,6 +139,50 @@ def test_bicgstab_solves(O, J, side):
         assert abs(np.linalg.norm(r - A @ x) - hist[-1]) <= 1e-6 * hist[0]
 
 
+@pytest.mark.parametrize("side", ["right", "left"])
+def test_bicgstab_history_equals_independent_recurrence(O, J, side):
+    """The oracle's BiCGStab against an independent numpy transcription of the published recurrence (van der Vorst's
+    preconditioned BiCGStab in the operation order SURVEY §8(c) records for Krylov.jl 0.9: x0 = 0, c = b, rho' = <c,r>, ...):
+    the residual histories agree to rounding over the first iterations and the iteration counts are equal. Krylov.jl itself is
+    not vendored, so this pins the restatement to the algorithm, not to a Julia run."""
+    w, s, M0, p, nz, r = _twophase_system(O, J)
+    n = w["nc"]
+    O.scale_diagonal(n, 2, s["rowptr"], s["colidx"], nz, r)
+    A = to_scipy(n, 2, s["rowptr"], s["colidx"], nz)
+    ilu = O.ILU0(n, 2, s["rowptr"], s["colidx"]); ilu.factor(nz)
+    rtol, atol = 1e-8, 1e-12
+    x, st, its, hist = O.bicgstab(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, side=side, rtol=rtol, atol=atol, itmax=500)
+    P = ilu.solve
+    N = P if side == "right" else (lambda v: v)
+    M = P if side == "left" else (lambda v: v)
+    b = r
+    rr = M(b).copy(); c = b.copy()                       # Krylov.jl: c = b also with a left preconditioner
+    pp = rr.copy(); xx = np.zeros_like(b)
+    rho_next = c @ rr
+    h = [np.linalg.norm(rr)]
+    eps = atol + rtol * h[0]
+    for _ in range(500):
+        rho = rho_next
+        y = N(pp); v = M(A @ y)
+        alpha = rho / (c @ v)
+        sv = rr - alpha * v
+        xx = xx + alpha * y
+        z = N(sv); t = M(A @ z)
+        omega = (t @ sv) / (t @ t)
+        xx = xx + omega * z
+        rr = sv - omega * t
+        rho_next = c @ rr
+        beta = (rho_next / rho) * (alpha / omega)
+        pp = rr + beta * (pp - omega * v)
+        h.append(np.linalg.norm(rr))
+        if h[-1] <= eps:
+            break
+    m = min(8, len(h), len(hist))
+    assert np.allclose(hist[:m], h[:m], rtol=1e-8)
+    assert abs(its - (len(h) - 1)) <= max(1, its // 20)
+    assert np.linalg.norm(x - xx) <= 1e-6 * np.linalg.norm(xx)
+
+
 def test_bicgstab_min_iterations_and_itmax(O, J):
     w, s, M0, p, nz, r = _twophase_system(O, J)
     n = w["nc"]
