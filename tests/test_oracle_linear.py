@@ -243,6 +243,30 @@ def test_gmres_solves(O, J, side, restart):
         assert abs(np.linalg.norm(r - A @ x) - hist[-1]) <= 1e-6 * hist[0]
 
 
+def test_gmres_history_is_the_minimal_residual_over_the_krylov_space(O, J):
+    """Independent pin of the oracle's GMRES (Krylov.jl order): for right preconditioning the j-th entry of stats.residuals is
+    min over x in N^-1 K_j(A N^-1, b) of |b - A x| — computed here by dense least squares on an explicitly orthonormalised
+    Krylov basis, without Arnoldi recurrences or Givens rotations."""
+    w, s, M0, p, nz, r = _twophase_system(O, J, dims=(5, 4, 3))
+    n = w["nc"]
+    O.scale_diagonal(n, 2, s["rowptr"], s["colidx"], nz, r)
+    A = to_scipy(n, 2, s["rowptr"], s["colidx"], nz)
+    ilu = O.ILU0(n, 2, s["rowptr"], s["colidx"]); ilu.factor(nz)
+    x, st, its, hist = O.gmres(n, 2, s["rowptr"], s["colidx"], nz, r, ilu, side="right", rtol=1e-12, itmax=12, memory=20, restart=False)
+    op = lambda v: A @ ilu.solve(v)
+    K = [r / np.linalg.norm(r)]
+    for j in range(1, min(8, len(hist))):
+        # orthonormal basis of K_j by repeated full orthogonalisation (numerically independent of the oracle's modified Gram-Schmidt)
+        W_ = np.column_stack([op(q) for q in K])
+        y, *_ = np.linalg.lstsq(W_, r, rcond=None)
+        assert np.isclose(np.linalg.norm(r - W_ @ y), hist[j], rtol=1e-6), j
+        v = op(K[-1])
+        Q = np.column_stack(K)
+        for _ in range(2):
+            v = v - Q @ (Q.T @ v)
+        K.append(v / np.linalg.norm(v))
+
+
 @pytest.mark.parametrize("restart", [False, True])
 def test_fgmres_equals_right_preconditioned_gmres(O, J, restart):
     """Krylov.jl fgmres! with a FIXED preconditioner spans the same spaces as right-preconditioned gmres!: same residual
