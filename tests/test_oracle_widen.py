@@ -217,3 +217,23 @@ def test_property_dual_assembly_equals_closed_form_oracle(O, J):
     nz, r = W.assemble_2ph_props(sy["hf"], sy["diag_pos"], sy["hf_pos"], w["Tf"], w["gdz"], p, props, M0, w["dt"], nnzb, w["src_cells"], w["src_vals"])
     nz2, r2 = O.assemble_2ph(sy["hf"], sy["diag_pos"], sy["hf_pos"], w["Tf"], w["gdz"], pv, par, p, sw, M0, w["dt"], nnzb, w["src_cells"], w["src_vals"])
     assert np.abs(r - r2).max() <= 1e-14 * np.abs(r2).max() and np.abs(nz - nz2).max() <= 1e-14 * np.abs(nz2).max()
+
+
+def test_two_restatements_of_the_update_rules_agree(O):
+    """choose_increment / unit_update_pairs! exist twice in the checker (C++ in oracle.cpp, Python in oracle/widen.py, written
+    at different times from src/variables/utils.jl:149-174,471-482): bit-equal on random inputs, and the nf = 2 case of the
+    many-fraction update reduces to the pair update."""
+    rng = np.random.default_rng(6)
+    n = 500
+    v = rng.uniform(0, 2, n); dx = rng.normal(0, 1, n)
+    a = v.copy()
+    O.update_scalar(a, dx, w=0.7, abs_max=0.3, rel_max=0.2, minv=0.1, maxv=1.9, scale=1.5)
+    b = np.array([vi + W._choose_increment(vi, 0.7 * di, 0.3, 0.2, 0.1, 1.9, 1.5) for vi, di in zip(v, dx)])
+    assert np.array_equal(a, b)
+    sw = rng.uniform(0, 1, n)
+    s = np.stack([sw, 1 - sw], axis=1).ravel().copy()
+    ds = rng.normal(0, 0.5, n)
+    O.update_fraction_pair(s, ds, w=1.0, abs_max=0.2, minval=0.0, maxval=1.0)
+    maxval = min(1 - 0.0, 1.0 - 2 * 0.0); minval = max(0.0, maxval - 1)
+    ref = np.array([swi + 1.0 * W._choose_increment(swi, di, 0.2, None, minval, maxval) for swi, di in zip(sw, ds)])
+    assert np.array_equal(s[0::2], ref) and np.allclose(s[0::2] + s[1::2], 1.0, atol=1e-15)
