@@ -500,8 +500,13 @@ void orc_assemble_poisson(i64 nc, const i64* face_pos, const i64* faces, const i
 // v[e] = v[e] + sum_p A[e,p]*x[p] (column-major blocks).
 // mul! src/StaticCSR/mat.jl:24-39: beta != 0 => y scaled by beta first.
 // ----------------------------------------------------------------------------
-void orc_spmv(i64 n, int bs, const i64* rowptr, const i64* colidx, const double* nz, double alpha, const double* x,
-              double beta, double* y) {
+}  // extern "C" (templates need C++ linkage)
+// BS > 0 fixes the block size at compile time (the reference's SMatrix blocks are unrolled the same way); BS == 0 reads it
+// at run time. Operands and operation order are the same in both, so the results are bitwise equal.
+template <int BS>
+static void spmv_impl(i64 n, int bs_rt, const i64* rowptr, const i64* colidx, const double* nz, double alpha, const double* x,
+                      double beta, double* y) {
+    const int bs = BS ? BS : bs_rt;
     if (beta != 0.0 && beta != 1.0) for (i64 i = 0; i < n * bs; i++) y[i] *= beta;
 #pragma omp parallel for schedule(static)
     for (i64 row = 0; row < n; row++) {
@@ -520,6 +525,13 @@ void orc_spmv(i64 n, int bs, const i64* rowptr, const i64* colidx, const double*
             if (beta != 0.0) y[row * bs + e] += alpha * v[e]; else y[row * bs + e] = alpha * v[e];
         }
     }
+}
+extern "C" {
+void orc_spmv(i64 n, int bs, const i64* rowptr, const i64* colidx, const double* nz, double alpha, const double* x,
+              double beta, double* y) {
+    if (bs == 2) spmv_impl<2>(n, bs, rowptr, colidx, nz, alpha, x, beta, y);
+    else if (bs == 1) spmv_impl<1>(n, bs, rowptr, colidx, nz, alpha, x, beta, y);
+    else spmv_impl<0>(n, bs, rowptr, colidx, nz, alpha, x, beta, y);
 }
 
 // ----------------------------------------------------------------------------
@@ -716,8 +728,10 @@ i64 orc_ilu0_set_level_schedule(void* h, int on, i64 max_levels) {
     for (i64 i = 0; i < n; i++) { F->levF[lf[i]].push_back(i); F->levB[lb[i]].push_back(i); }
     return nf;
 }
+}  // extern "C"
+template <int BS>
 static void ilu0_solve_levels(OrcIlu* F, const double* b, double* x) {
-    const int bs = F->bs, b2 = bs * bs;
+    const int bs = BS ? BS : F->bs, b2 = bs * bs;
     for (const auto& rows : F->levF) {
         const i64 nr = (i64)rows.size();
 #pragma omp parallel for schedule(static)
@@ -749,10 +763,10 @@ static void ilu0_solve_levels(OrcIlu* F, const double* b, double* x) {
     }
 }
 // ldiv!(x, LU, b): forward with unit diagonal, then backward with inverted D.
-void orc_ilu0_solve(void* h, const double* b, double* x) {
-    OrcIlu* F = (OrcIlu*)h;
-    const int bs = F->bs, b2 = bs * bs;
-    if (!F->levF.empty()) { ilu0_solve_levels(F, b, x); return; }
+template <int BS>
+static void ilu0_solve_impl(OrcIlu* F, const double* b, double* x) {
+    const int bs = BS ? BS : F->bs, b2 = bs * bs;
+    if (!F->levF.empty()) { ilu0_solve_levels<BS>(F, b, x); return; }
 #pragma omp parallel for schedule(dynamic, 1)
     for (i64 blk = 0; blk < F->nblocks; blk++) {
         const auto& act = F->active[blk];
@@ -776,6 +790,13 @@ void orc_ilu0_solve(void* h, const double* b, double* x) {
             for (int e = 0; e < bs; e++) x[i * bs + e] = t[e];
         }
     }
+}
+extern "C" {
+void orc_ilu0_solve(void* h, const double* b, double* x) {
+    OrcIlu* F = (OrcIlu*)h;
+    if (F->bs == 2) ilu0_solve_impl<2>(F, b, x);
+    else if (F->bs == 1) ilu0_solve_impl<1>(F, b, x);
+    else ilu0_solve_impl<0>(F, b, x);
 }
 
 // ----------------------------------------------------------------------------
