@@ -10,6 +10,11 @@
  *  - plain C, opaque handles, POD scalars, raw pointers + explicit sizes;
  *  - index arrays cross the boundary 1-based int64, exactly as Julia holds
  *    them; they are converted to 0-based int32 inside (overflow-checked);
+ *  - size limit per context (= per GPU): the kernels index vector and matrix
+ *    VALUES with int32, so n*bs and nnz_blocks*bs*bs must stay below 2^31
+ *    (bs = 2: 536M blocks, about 76M hexahedral cells per GPU); larger systems
+ *    get JB_ERR_UNSUPPORTED at jb_csr_create_* and are meant to be decomposed
+ *    over several GPUs (jb_dist_*);
  *  - pointers named d_* are DEVICE pointers (from jb_malloc or any CUDA
  *    allocation of the same device); all others are HOST pointers borrowed for
  *    the duration of the call;

@@ -100,7 +100,8 @@ static int csr_finish(jb_ctx* ctx, jb_csr* A) {
 int32_t jb_csr_create_from_coo(jb_ctx* ctx, const int64_t* I, const int64_t* J, int64_t nnz_in, int64_t n, int32_t bs,
                                jb_csr** out) {
     if (!ctx || !out || n <= 0 || nnz_in < 0 || bs < 1 || bs > 4) JB_FAIL(ctx, JB_ERR_ARG, "jb_csr_create_from_coo: bad argument");
-    if (!fits_i32(n) || !fits_i32(nnz_in)) JB_FAIL(ctx, JB_ERR_UNSUPPORTED, "jb_csr_create_from_coo: index overflow (int32)");
+    // kernels index values as int32 (block index * bs*bs, row * bs): the limit is on the scalar entries, not on the blocks
+    if (!fits_i32(n * bs) || !fits_i32(nnz_in * bs * bs)) JB_FAIL(ctx, JB_ERR_UNSUPPORTED, "jb_csr_create_from_coo: index overflow (int32)");
     std::vector<int32_t> ptr(n + 1, 0);
     for (i64 k = 0; k < nnz_in; k++) {
         if (I[k] < 1 || I[k] > n || J[k] < 1 || J[k] > n) JB_FAIL(ctx, JB_ERR_ARG, "jb_csr_create_from_coo: index out of range");
@@ -132,7 +133,7 @@ int32_t jb_csr_create_from_coo(jb_ctx* ctx, const int64_t* I, const int64_t* J, 
 int32_t jb_csr_create_tpfa(jb_mesh* m, int32_t bs, jb_csr** out) {
     if (!m || !out || bs < 1 || bs > 4) return JB_ERR_ARG;
     jb_ctx* ctx = m->ctx;
-    if (!fits_i32(m->nhf + m->nc)) JB_FAIL(ctx, JB_ERR_UNSUPPORTED, "jb_csr_create_tpfa: index overflow (int32)");
+    if (!fits_i32((m->nhf + m->nc) * (i64)bs * bs)) JB_FAIL(ctx, JB_ERR_UNSUPPORTED, "jb_csr_create_tpfa: index overflow (int32)");
     jb_csr* A = new jb_csr();
     A->ctx = ctx; A->n = m->nc; A->bs = bs;
     A->h_rowptr.assign(m->nc + 1, 0);

@@ -42,6 +42,18 @@ def test_generic_cache_fill_bad_tables(J, ctx):
     assert np.array_equal(A.nonzeros(), [1.0, 2.0, 3.0, 4.0]) and np.array_equal(r.get(), [10.0, 20.0])
 
 
+def test_value_index_range_is_guarded(J, ctx):
+    """Kernels index values with int32: nnz_blocks*bs*bs at or above 2^31 is refused when the matrix is created (the count
+    is checked before the index arrays are read, so tiny arrays suffice here), not discovered as a wild write later."""
+    import ctypes as C
+    I = np.ones(4, dtype=np.int64)
+    pi = I.ctypes.data_as(C.POINTER(C.c_int64))
+    h = C.c_void_p()
+    assert ctx.lib.jb_csr_create_from_coo(ctx.h, pi, pi, 2**29, 10, 2, C.byref(h)) == -4    # JB_ERR_UNSUPPORTED
+    assert ctx.lib.jb_csr_create_from_coo(ctx.h, pi, pi, 4, 2**30, 2, C.byref(h)) == -4     # n*bs
+    assert b"overflow" in ctx.lib.jb_last_error(ctx.h)
+
+
 @pytest.mark.parametrize("solver,side,restart,memory", [("gmres", "right", True, 40), ("gmres", "left", True, 40), ("gmres", "none", True, 40),
                                                         ("fgmres", "right", False, 20), ("fgmres", "right", True, 40)])
 def test_gmres_restart_and_fgmres_match_oracle(J, O, ctx, solver, side, restart, memory):
