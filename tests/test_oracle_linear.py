@@ -180,7 +180,11 @@ def test_bicgstab_history_equals_independent_recurrence(O, J, side):
     m = min(8, len(h), len(hist))
     assert np.allclose(hist[:m], h[:m], rtol=1e-8)
     assert abs(its - (len(h) - 1)) <= max(1, its // 20)
-    assert np.linalg.norm(x - xx) <= 1e-6 * np.linalg.norm(xx)
+    # Both iterates satisfy the stopping rule, so they agree in the norm the rule uses (the preconditioned residual). The plain
+    # difference is only bounded by cond(A) * rtol and moves with the summation order of the OpenMP inner products, hence the
+    # looser second bound.
+    assert np.linalg.norm(M(A @ (x - xx))) <= 4 * eps
+    assert np.linalg.norm(x - xx) <= 1e-4 * np.linalg.norm(xx)
 
 
 def test_bicgstab_min_iterations_and_itmax(O, J):
