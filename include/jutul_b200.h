@@ -248,7 +248,8 @@ int32_t jb_nfvm_assemble(jb_nfvm* d, const double* d_p, int64_t nph, int64_t ph,
  *        POWER      c0 clamp((a - c2) / c3, 0, 1)^c1  (Brooks-Corey relative permeability)
  *        TABLE1D    c0 I(a),  TABLE2D  c0 I(a, b)
  *      The evaluation order is sort_symbols' (depth-first post-order, dependencies in ascending node order); a cycle or a
- *      dangling dependency is an error. Outputs: per flagged variable (1 + np) planes of nc doubles (value, d/d primary q). */
+ *      dangling dependency is an error. Outputs: per flagged variable (1 + np) planes of nc doubles (value, d/d primary q).
+ *      Limits: 32 variables, 4 primaries per program. A program borrows its tables: destroy it before them. */
 enum { JB_VAR_PRIMARY = 0, JB_VAR_PARAMETER = 1, JB_VAR_CONST = 2, JB_VAR_AFFINE = 3, JB_VAR_PRODUCT = 4, JB_VAR_QUOTIENT = 5,
        JB_VAR_EXP = 6, JB_VAR_POWER = 7, JB_VAR_TABLE1D = 8, JB_VAR_TABLE2D = 9 };
 typedef struct { int32_t kind; int32_t dep[3]; int32_t table; int32_t output; double c[4]; } jb_var_spec;
@@ -340,7 +341,8 @@ int32_t jb_twophase_assemble_props(jb_twophase* m, const double* d_p, const doub
  *      jb_schur_prepare: prepare_linear_solve! (:17-33), d_a -= C (E \ b); b (host, sum m_i) stays resident.
  *      jb_schur_mul: schur_mul! (:139-160), res <- beta res + alpha (B x - C (E \ (D x))).
  *      jb_krylov_set_schur: linear_operator(sys) (:70-91) — the Krylov solve then runs on S = B - C E^-1 D while the
- *      preconditioner keeps acting on B (jacobian(sys), :162-169). NULL restores the plain operator.
+ *      preconditioner keeps acting on B (jacobian(sys), :162-169). NULL restores the plain operator. The solver borrows
+ *      s: detach it (NULL) or destroy the solver before jb_schur_destroy.
  *      jb_schur_dx_update: update_dx_from_vector! / schur_dx_update! (:97-137) with d_dx as jb_krylov_solve left it
  *      (dx = -x): y_i = E_i \ (D_i x - b_i), written to the host array y (sum m_i). */
 int32_t jb_schur_create(jb_csr* B, int32_t ngroups, const int64_t* msize, const int64_t* C_ptr, const int64_t* C_I, const int64_t* C_J,

@@ -736,8 +736,8 @@ __global__ void __launch_bounds__(256) nfvm_law_faces_kernel(i64 nf, int scheme,
 }
 
 // discretization_stencil of every face: unique!([left, right, mpfa cells of ft_left..., (left, right,) mpfa cells of ft_right...])
-static void nfvm_build_stencil(jb_nfvm* d) {
-    if (!d->h_vpos.empty()) return;
+static int nfvm_build_stencil(jb_nfvm* d) {
+    if (!d->h_vpos.empty()) return JB_OK;
     const i64 nf = d->nf;
     d->h_vpos.assign(nf + 1, 0);
     std::vector<double4> coef;
@@ -758,9 +758,12 @@ static void nfvm_build_stencil(jb_nfvm* d) {
         }
         d->h_vpos[f + 1] = (int32_t)d->h_vars.size();
     }
-    d->d_coef.upload(coef, d->ctx->stream);
-    d->d_vpos.upload(d->h_vpos, d->ctx->stream);
-    d->d_vars.upload(d->h_vars, d->ctx->stream);
+    if (d->d_coef.upload(coef, d->ctx->stream) != cudaSuccess || d->d_vpos.upload(d->h_vpos, d->ctx->stream) != cudaSuccess ||
+        d->d_vars.upload(d->h_vars, d->ctx->stream) != cudaSuccess) {
+        d->h_vpos.clear(); d->h_vars.clear();
+        JB_FAIL(d->ctx, JB_ERR_ALLOC, "jb_nfvm: allocation of the face stencils failed");
+    }
+    return JB_OK;
 }
 
 extern "C" {
@@ -768,7 +771,7 @@ extern "C" {
 // parity dump of the face stencils (face_cache.vpos / .variables): vpos[nf+1] and vars[vpos[nf]-1], 1-based
 int32_t jb_nfvm_stencil(jb_nfvm* d, int64_t* vpos, int64_t* vars, int64_t cap, int64_t* n_out) {
     if (!d) return JB_ERR_ARG;
-    nfvm_build_stencil(d);
+    { const int rc_ = nfvm_build_stencil(d); if (rc_ != JB_OK) return rc_; }
     if (n_out) *n_out = (int64_t)d->h_vars.size();
     if (vpos) for (i64 f = 0; f <= d->nf; f++) vpos[f] = d->h_vpos[f] + 1;
     if (vars) {
@@ -780,7 +783,7 @@ int32_t jb_nfvm_stencil(jb_nfvm* d, int64_t* vpos, int64_t* vars, int64_t cap, i
 // declare_pattern (fvm_assembly.jl:55-89): diagonal, and for every face and stencil cell c: (l,c), (r,c), (c,l), (c,r)
 int32_t jb_nfvm_pattern(jb_nfvm* d, jb_csr** out) {
     if (!d || !out) return JB_ERR_ARG;
-    nfvm_build_stencil(d);
+    { const int rc_ = nfvm_build_stencil(d); if (rc_ != JB_OK) return rc_; }
     std::vector<int64_t> I, J;
     I.reserve(d->nc + 4 * d->h_vars.size()); J.reserve(d->nc + 4 * d->h_vars.size());
     for (i64 c = 1; c <= d->nc; c++) { I.push_back(c); J.push_back(c); }
@@ -797,7 +800,7 @@ int32_t jb_nfvm_pattern(jb_nfvm* d, jb_csr** out) {
 // align_to_jacobian! (fvm_assembly.jl:98-165): left / right positions of every stencil slot
 int32_t jb_nfvm_align(jb_nfvm* d, jb_csr* A) {
     if (!d || !A || A->bs != 1 || A->n != d->nc) return JB_ERR_ARG;
-    nfvm_build_stencil(d);
+    { const int rc_ = nfvm_build_stencil(d); if (rc_ != JB_OK) return rc_; }
     jb_ctx* ctx = d->ctx;
     auto find = [&](int32_t row, int32_t col) -> int32_t {
         const int32_t* b = A->h_colidx.data() + A->h_rowptr[row];

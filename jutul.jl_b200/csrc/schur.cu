@@ -181,6 +181,11 @@ int32_t jb_schur_create(jb_csr* B, int32_t ngroups, const int64_t* msize, const 
     S->M = S->goff[ngroups];
     const i64 M = S->M;
     if (ngroups > 0 && (C_ptr[0] != 1 || D_ptr[0] != 1 || E_ptr[0] != 1)) { delete S; JB_FAIL(ctx, JB_ERR_ARG, "jb_schur_create: *_ptr must start at 1"); }
+    for (int g = 0; g < ngroups; g++)
+        if (C_ptr[g + 1] < C_ptr[g] || D_ptr[g + 1] < D_ptr[g] || E_ptr[g + 1] < E_ptr[g]) {
+            delete S;
+            JB_FAIL(ctx, JB_ERR_ARG, "jb_schur_create: *_ptr must be non-decreasing");
+        }
     // concatenate the groups: C columns and D rows shifted into the common eliminated index space
     const i64 nC = ngroups ? C_ptr[ngroups] - 1 : 0, nD = ngroups ? D_ptr[ngroups] - 1 : 0, nE = ngroups ? E_ptr[ngroups] - 1 : 0;
     std::vector<int64_t> cI(nC), cJ(nC), dI(nD), dJ(nD);
