@@ -28,6 +28,54 @@ def test_prototype_table_matches_header(J):
     assert J._lib.load().jb_version() == 100
 
 
+def _header_prototypes():
+    """name -> (return kind, [argument kinds]) parsed from the header; kinds: p (any pointer), i32, i64, f64, void."""
+    src = open(os.path.join(ROOT, "include", "jutul_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+
+    def kind(t):
+        t = t.strip()
+        if "*" in t:
+            return "p"
+        base = re.sub(r"\bconst\b", "", t).split()[0]
+        return {"int32_t": "i32", "int64_t": "i64", "double": "f64", "void": "void"}[base]
+    out = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(jb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        out[name] = (kind(ret), [] if args in ("", "void") else [kind(a) for a in args.split(",")])
+    return out
+
+
+def test_ctypes_prototypes_match_header_signatures(J):
+    """Argument by argument: pointer / int32 / int64 / double in the ctypes table = the C declaration."""
+    protos = _header_prototypes()
+    assert sorted(protos) == _header_functions()
+
+    def ck(t):
+        return "void" if t is None else {C.c_int32: "i32", C.c_int64: "i64", C.c_double: "f64"}.get(t, "p")
+    for name, (ret, args) in J._lib.PROTOTYPES.items():
+        assert (ck(ret), [ck(a) for a in args]) == protos[name], name
+
+
+def test_julia_ccall_signatures_match_header():
+    """Every ccall of julia/JutulB200.jl passes the return type and the argument types (Ptr / Ref / Cstring, Int32, Int64,
+    Float64) the C declaration has, in the same order — the check a first run under Julia would otherwise make."""
+    protos = _header_prototypes()
+    jl = open(os.path.join(ROOT, "jutul.jl_b200", "julia", "JutulB200.jl")).read()
+
+    def jk(t):
+        t = t.strip()
+        if t.startswith(("Ptr{", "Ref{")) or t == "Cstring":
+            return "p"
+        return {"Int32": "i32", "Cint": "i32", "Int64": "i64", "Float64": "f64", "Cdouble": "f64", "Cvoid": "void"}[t]
+    n = 0
+    for m in re.finditer(r"ccall\(\(:(jb_[a-z0-9_]+), LIB\),\s*([\w{}]+),\s*\((.*?)\)\s*[,)]", jl, flags=re.S):
+        name, ret, tup = m.groups()
+        assert (jk(ret), [jk(t) for t in tup.split(",") if t.strip()]) == protos[name], name
+        n += 1
+    assert n == jl.count("ccall(") and n >= 70
+
+
 def test_sm100a_cubin_present(J):
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", J._lib.SO_PATH], capture_output=True, text=True).stdout
