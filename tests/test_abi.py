@@ -76,6 +76,45 @@ def test_julia_ccall_signatures_match_header():
     assert n == jl.count("ccall(") and n >= 70
 
 
+def test_julia_glue_blocks_and_brackets_balance():
+    """Structural lint of the unexecuted glue: with strings and comments removed, every bracket closes and every block opener
+    (function / if / for / while / let / struct / begin / try / do / module / macro / quote) has its `end`. Generators'
+    for / if inside brackets and `a[end]` are not blocks."""
+    src = open(os.path.join(ROOT, "jutul.jl_b200", "julia", "JutulB200.jl")).read()
+    src = re.sub(r'"""(?:.|\n)*?"""', '""', src)
+    src = re.sub(r'"(?:\\.|[^"\\])*"', '""', src)
+    src = re.sub(r"#=(?:.|\n)*?=#", "", src)
+    src = re.sub(r"#[^\n]*", "", src)
+    pairs, stack = {")": "(", "]": "[", "}": "{"}, []
+    for ch in src:
+        if ch in "([{":
+            stack.append(ch)
+        elif ch in ")]}":
+            assert stack and stack.pop() == pairs[ch]
+    assert not stack
+    openers = {"function", "if", "for", "while", "let", "struct", "begin", "try", "do", "module", "macro", "quote"}
+    dp = db = 0
+    blocks, prev = [], None
+    for t in re.findall(r"[A-Za-z_][A-Za-z_0-9!]*|\S", src):
+        if t == "(":
+            dp += 1
+        elif t == ")":
+            dp -= 1
+        elif t == "[":
+            db += 1
+        elif t == "]":
+            db -= 1
+        elif t in openers and prev not in (":", "."):
+            if not (t in ("for", "if") and (dp > 0 or db > 0)):
+                blocks.append(db)
+        elif t == "end" and prev != ":":
+            if not (db > 0 and (not blocks or blocks[-1] < db)):
+                assert blocks, "unmatched end"
+                blocks.pop()
+        prev = t
+    assert not blocks
+
+
 def test_sm100a_cubin_present(J):
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", J._lib.SO_PATH], capture_output=True, text=True).stdout
