@@ -195,3 +195,27 @@ def test_scalar_and_multimodel_known_answers(O):
     # ungrouped (single sparse matrix): the same answer from the full 2x2 system
     Jm = np.array([[2.0, -1.0], [-1.0, 2.0]])
     assert np.allclose(-np.linalg.solve(Jm, [rA, rB]), [1.0 / 3.0, -1.0 / 3.0])
+
+
+def test_block_spmv_reference_fixture_system_1(O):
+    """system_1() of the reference's test/linalg/linear_operators.jl:60-78: A = sparse([1, 1, 2], [1, 2, 1], [a, b, c]) with 2x2
+    SMatrix entries, X = [(pi, 3), (sqrt 3, 23.1)]. The property that file states (:119-123) — the block operator on the
+    block-ordered vector equals the scalar matrix of block_system_to_scalar(reorder = true) (:8-37, entry[k, l] at
+    ((k-1) n + i, (l-1) n + j)) on the equation-ordered vector, mapped back by equation_major_to_block_major_view — is checked
+    here with the scalar matrix written out by hand, so it pins the oracle's column-major block convention to the reference's."""
+    a = np.array([[1.0, 2], [3, 4]]); b = np.array([[5.0, 6], [7, 8]]); c = np.array([[9.0, 10], [11, 12]])
+    x = np.array([[np.pi, 3.0], [np.sqrt(3.0), 23.1]])          # x[i] = block i
+    # CSR of the 2x2 block matrix: row 1 = {a @ col 1, b @ col 2}, row 2 = {c @ col 1}; blocks stored column-major
+    rowptr = np.array([1, 3, 4], dtype=np.int64); colidx = np.array([1, 2, 1], dtype=np.int64)
+    nz = np.concatenate([m.flatten(order="F") for m in (a, b, c)])
+    y = O.spmv(2, 2, rowptr, colidx, nz, x.ravel())
+    # scalar matrix in equation-major order, by hand: rows/cols (k-1)*2 + i
+    A_s = np.array([[1.0, 5, 2, 6],
+                    [9.0, 0, 10, 0],
+                    [3.0, 7, 4, 8],
+                    [11.0, 0, 12, 0]])
+    X_s = np.array([x[0, 0], x[1, 0], x[0, 1], x[1, 1]])
+    res_s = A_s @ X_s
+    renum = np.array([res_s[0], res_s[2], res_s[1], res_s[3]])   # equation_major_to_block_major_view(res_s, 2)
+    assert np.allclose(y, renum, rtol=1e-15, atol=0)
+    assert np.allclose(y, np.concatenate([a @ x[0] + b @ x[1], c @ x[0]]), rtol=1e-15, atol=0)
