@@ -121,3 +121,57 @@ def test_diagonal_preconditioners_match_oracle(J, O, ctx, kind):
     kb = J.GenericKrylov(sim.jac, "bicgstab", prec, relative_tolerance=1e-6, max_iterations=600)
     ok, its, hist, st = J.linear_solve(kb, sim.r, sim.dx)
     assert np.linalg.norm(r + A @ sim.dx.get()) <= 1e-4 * np.linalg.norm(r) or not ok
+
+
+@pytest.mark.parametrize("layout", ["equation_major", "entity_major"])
+def test_scalar_jacobian_layouts_on_device(J, O, ctx, layout):
+    """a3: the reference's scalar layouts. The two-phase Jacobian as a scalar CSR of 2 nc rows, dofs numbered by
+    EquationMajorLayout (index = n (e-1) + c) or EntityMajorLayout (index = 2 (c-1) + e) — the oracle's index formulas,
+    pinned to test/adjoints/utils.jl:57-68 by test_layout_goldens. Pattern bit-exact; SpMV, ILU(0) and the Krylov solve on the
+    bs = 1 device path reproduce the 2x2-block results up to the dof permutation."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from test_gpu_parity import _jacobian_on_gpu
+    w, s, sim, nz, r = _jacobian_on_gpu(J, O, ctx, dims=(7, 6, 5))
+    n = w["nc"]
+    nz = sim.jac.nonzeros(); r = sim.r.get()
+    rp, ci = s["rowptr"], s["colidx"]
+    idx = (lambda c, d: O.index_equation_major(c, d, n)) if layout == "equation_major" else (lambda c, d: O.index_entity_major(c, d, 2))
+    rows = np.repeat(np.arange(n), np.diff(rp)); cols = ci - 1
+    I, Jc, V = [], [], []
+    for e in range(2):
+        for q in range(2):
+            I.append(np.array([idx(c + 1, e + 1) for c in rows])); Jc.append(np.array([idx(c + 1, q + 1) for c in cols]))
+            V.append(nz[2 * q + e::4])                       # block entry (eq e, partial q), column-major blocks
+    I, Jc, V = np.concatenate(I).astype(np.int64), np.concatenate(Jc).astype(np.int64), np.concatenate(V)
+    M = sp.coo_matrix((V, (I - 1, Jc - 1)), shape=(2 * n, 2 * n)).tocsr(); M.sort_indices()
+    A = J.build_sparse_matrix(ctx, I, Jc, 2 * n, 1)
+    rps, cis = A.pattern()
+    rpo, cio = O.csr_from_coo(I, Jc, 2 * n)
+    assert np.array_equal(rps, rpo) and np.array_equal(cis, cio) and np.array_equal(rps, M.indptr + 1) and np.array_equal(cis, M.indices + 1)
+    A.set_nonzeros(M.data)
+    P = np.array([idx(c + 1, e + 1) - 1 for c in range(n) for e in range(2)])     # block dof 2c+e -> layout dof
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(2 * n); xs = np.zeros(2 * n); xs[P] = x
+    y = ctx.zeros(2 * n)
+    A.mul(y, ctx.transfer(xs))
+    yb = O.spmv(n, 2, rp, ci, nz, x)
+    assert np.abs(y.get()[P] - yb).max() <= 1e-13 * np.abs(yb).max()
+    prec = J.ILUZeroPreconditioner(A); assert prec.update_preconditioner() == 0
+    ilu = O.ILU0(2 * n, 1, rps, cis); assert ilu.factor(M.data) == 0
+    z = ctx.zeros(2 * n)
+    prec.apply(z, ctx.transfer(xs))
+    zo = ilu.solve(xs)
+    assert np.abs(z.get() - zo).max() <= 1e-8 * np.abs(zo).max()
+    rs = np.zeros(2 * n); rs[P] = r
+    kry = J.GenericKrylov(A, "bicgstab", prec, relative_tolerance=1e-10, max_iterations=500)
+    dx = ctx.zeros(2 * n)
+    ok, its, hist, st = J.linear_solve(kry, ctx.transfer(rs), dx)
+    assert ok and st == 0
+    xb = spla.spsolve(to_scipy_block(n, rp, ci, nz), r)       # the block system's own solution
+    assert np.linalg.norm(-dx.get()[P] - xb) <= 1e-5 * np.linalg.norm(xb)
+
+
+def to_scipy_block(n, rp, ci, nz):
+    from conftest import to_scipy
+    return to_scipy(n, 2, rp, ci, nz).tocsc()
