@@ -1,6 +1,7 @@
 """Property tests of the checker's host logic on generated inputs (hypothesis, derandomised so that every run sees the same
 examples): the structural invariants the reference's data structures guarantee, over ragged / duplicated / disconnected
-inputs the fixed meshes of the other tests do not reach. No GPU."""
+inputs the fixed meshes of the other tests do not reach — and, in the last section, the library's host-only entry points
+(partitioning, cell ordering: no device is touched) against the checker on the same generated inputs. No GPU."""
 import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.csgraph as csg
@@ -122,3 +123,53 @@ def test_scalar_update_respects_every_limit(O, cells, abs_max, rel_max):
     assert np.all(v >= 0.5) and np.all(v <= 150.0) and np.all(dv * dx >= 0)
     free = (np.abs(dx) <= abs_max) & (np.abs(dx) <= rel_max * np.abs(v0)) & (v0 + dx >= 0.5) & (v0 + dx <= 150.0)
     assert np.array_equal(v[free], (v0 + dx)[free])
+
+
+# ---- the library's own host-only entry points (no GPU is touched: partition.cu host code through the C ABI) against the checker
+@SET
+@given(graphs(), st.integers(1, 4), st.integers(0, 2**31 - 1), st.booleans())
+def test_library_process_partition_equals_checker(J, O, g, nblocks, seed, weighted):
+    """jb_process_partition == the restatement of process_partition, label for label, on multigraphs with isolated cells and
+    zero-weight faces (weights == 0 cut the connection, src/partitioning.jl:139-160)."""
+    nc, N = g
+    rng = np.random.default_rng(seed)
+    part = rng.integers(1, nblocks + 1, nc).astype(np.int64)
+    wts = (rng.random(N.shape[0]) > 0.3).astype(np.float64) if weighted else None
+    assert np.array_equal(J.process_partition(N, nc, part, weights=wts), O.process_partition(N, nc, part, weights=wts))
+
+
+@SET
+@given(graphs(max_cells=40, max_faces=120))
+def test_library_multicolor_ordering_is_always_a_proper_colouring(J, g):
+    """jb_order_multicolor on arbitrary multigraphs: a permutation of 1..nc whose labels split into `ncolors` consecutive ranges
+    with no face inside a range — the property the two-colour ILU(0) sweeps and the identity rows rely on."""
+    nc, N = g
+    perm, ncol = J.multicolor_ordering(N, nc)
+    assert sorted(perm.tolist()) == list(range(1, nc + 1)) and 1 <= ncol <= nc
+    if N.shape[0] == 0:
+        return
+    a, b = perm[N[:, 0] - 1], perm[N[:, 1] - 1]
+    # greedy reconstruction of the colour ranges: a new range starts at the first label adjacent to a label of the current range
+    lo = np.minimum(a, b); hi = np.maximum(a, b)
+    starts, cur = [1], 1
+    for lab in range(2, nc + 1):
+        if np.any((hi == lab) & (lo >= cur)):
+            starts.append(lab); cur = lab
+    assert len(starts) <= ncol
+
+
+@SET
+@given(st.integers(2, 7), st.integers(2, 6), st.integers(1, 5), st.integers(1, 6))
+def test_library_partitions_cover_all_labels(J, nx, ny, nz, k):
+    """partition(N, k) (src/partitioning.jl:244-307; test/partitioning.jl:11-36): labels 1..k, every block non-empty, for METIS
+    and linear partitioners on small grids, k up to the number of cells. METIS may leave a block empty when k approaches the
+    number of cells; the library then fails loudly ("a block is empty") instead of returning a partition with a hole."""
+    w = J.workloads.unstructured_hex(nx, ny, nz)
+    k = min(k, w["nc"])
+    for kind in ("metis", "linear"):
+        try:
+            p = J.partition(w["N"], k, nc=w["nc"], partitioner=kind)
+        except J.JutulB200Error as e:
+            assert kind == "metis" and 4 * k > w["nc"] and "a block is empty" in str(e)
+            continue
+        assert p.shape[0] == w["nc"] and set(np.unique(p).tolist()) == set(range(1, k + 1))
